@@ -1,0 +1,121 @@
+"""ctypes binding of libb200ssl.so (the C ABI declared in include/b200ssl.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Loading fails loudly when the shared
+object is missing, and every compute call raises if it returns a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200ssl.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200ssl.h")
+
+ABI_VERSION = 1
+
+LABEL_U8, LABEL_I64 = 0, 1
+PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONV_DGRAD_D2S, PACK_DECONV_FWD, PACK_DECONV_DGRAD = range(5)
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("n", "id", "ih", "iw", "c0", "c1", "cout", "kd", "kh", "kw", "stride", "pd", "ph", "pw")]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_P = C.c_void_p          # device pointer
+_S = C.c_void_p          # cudaStream_t
+_I = C.c_int
+_L = C.c_longlong
+_F = C.c_float
+_U64 = C.c_ulonglong
+_U32 = C.c_uint
+_D = C.POINTER(ConvDesc)
+
+# name -> (restype, argtypes).  Functions returning int status are checked by `call`.
+SIGNATURES = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_abi_version": (_I, []),
+    "b200_device_sm": (_I, []),
+    "b200_conv_packed_floats": (_L, [_I, _I, _I, _I]),
+    "b200_conv_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_conv_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _I, _S]),
+    "b200_conv_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _I, _S]),
+    "b200_conv_k2s2_dgrad": (_I, [_D, _P, _P, _P, _I, _I, _S]),
+    "b200_conv_wgrad_workspace_bytes": (_L, [_D]),
+    "b200_conv_wgrad": (_I, [_D, _P, _P, _P, _P, _L, _P, _P, _I, _I, _S]),
+    "b200_deconv_k2s2_fwd": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_deconv_k2s2_dgrad": (_I, [_D, _P, _P, _P, _I, _I, _S]),
+    "b200_deconv_k2s2_wgrad_workspace_bytes": (_L, [_D]),
+    "b200_deconv_k2s2_wgrad": (_I, [_D, _P, _P, _P, _L, _P, _I, _I, _S]),
+    "b200_bn_workspace_bytes": (_L, [_L, _I]),
+    "b200_bn_stats_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _L, _S]),
+    "b200_bn_eval_state": (_I, [_I, _P, _P, _F, _P, _P, _P, _S]),
+    "b200_bn_act_fwd": (_I, [_P, _P, _P, _L, _I, _F, _F, _I, _U64, _P, _U32, _L, _S]),
+    "b200_bn_act_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _F, _F, _I, _U64, _P, _U32, _L, _P, _L, _S]),
+    "b200_dropout_mask": (_I, [_P, _L, _I, _F, _I, _U64, _P, _U32, _L, _S]),
+    "b200_maxpool2_fwd": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_maxpool2_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _S]),
+    "b200_upsample2x_fwd": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_upsample2x_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
+    "b200_nchw_to_nhwc": (_I, [_P, _P, _L, _I, _L, _S]),
+    "b200_nhwc_to_nchw": (_I, [_P, _P, _L, _I, _L, _S]),
+    "b200_colsum_workspace_bytes": (_L, [_L, _I]),
+    "b200_colsum": (_I, [_P, _L, _I, _P, _I, _P, _L, _S]),
+    "b200_add": (_I, [_P, _P, _P, _L, _S]),
+    "b200_ssl_loss_workspace_bytes": (_L, [_I, _L]),
+    "b200_ssl_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
+    "b200_ssl_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _I, _S]),
+    "b200_sgd_ema_step": (_I, [_P, _P, _P, _P, _L, _P, _I, _S]),
+    "b200_ema_update": (_I, [_P, _P, _L, _P, _S]),
+    "b200_noise_add": (_I, [_P, _P, _L, _F, _F, _U64, _P, _U32, _S]),
+}
+
+# entry points whose int return value is NOT a status code
+_NON_STATUS = {"b200_abi_version", "b200_device_sm"}
+
+_lib = None
+launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C cv_ssl_mis_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200_abi_version() != ABI_VERSION:
+        raise B200Error(f"ABI mismatch: library {lib.b200_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Call a status-returning entry point; raise B200Error with the library's message on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name in _NON_STATUS or SIGNATURES[name][0] is not _I:
+        return rc
+    launch_count += 1
+    if rc != 0:
+        msg = lib.b200_last_error()
+        raise B200Error(f"{name} failed ({rc}): {msg.decode() if msg else '?'}")
+    return rc
+
+
+def query(name: str, *args):
+    """Call a size/metadata query (returns the raw value)."""
+    return getattr(load(), name)(*args)

@@ -1,0 +1,299 @@
+// 2x2 max-pool, bilinear x2 upsampling (align_corners=True) and layout helpers over channels-last fp32.
+//
+// Replaces nn.MaxPool2d(2) (code/networks/unet.py:56) and nn.Upsample(scale_factor=2, mode='bilinear',
+// align_corners=True) (code/networks/unet.py:74-75) of the reference, forward and backward.
+#include "common.cuh"
+#include "../../include/b200ssl.h"
+
+static inline int ew_grid(long long work) {
+    long long blocks = (work + 255) / 256;
+    long long cap = (long long)b200_num_sms() * 16;
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// ---------------------------------------------------------------- max pool 2x2 stride 2
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ a, float* __restrict__ out, int N,
+                                                           int H, int W, int C) {
+    const int CQ = C >> 2, OH = H >> 1, OW = W >> 1;
+    const long long total = (long long)N * OH * OW * CQ;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(q % CQ);
+        long long r = q / CQ;
+        const int ow = (int)(r % OW); r /= OW;
+        const int oh = (int)(r % OH);
+        const int n = (int)(r / OH);
+        const float* base = a + (((long long)n * H + 2 * oh) * W + 2 * ow) * C + cq * 4;
+        float4 v = max4(max4(ldg4(base), ldg4(base + C)), max4(ldg4(base + (long long)W * C), ldg4(base + (long long)W * C + C)));
+        stg4(out + q * 4, v);
+    }
+}
+
+// da[window] (+)= dp routed to the first maximum of the window (scan order (0,0),(0,1),(1,0),(1,1), strict >)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dp,
+                                                           float* __restrict__ da, int N, int H, int W, int C,
+                                                           int accumulate) {
+    const int CQ = C >> 2, OH = H >> 1, OW = W >> 1;
+    const long long total = (long long)N * OH * OW * CQ;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(q % CQ);
+        long long r = q / CQ;
+        const int ow = (int)(r % OW); r /= OW;
+        const int oh = (int)(r % OH);
+        const int n = (int)(r / OH);
+        const long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
+        const long long base = (((long long)n * H + 2 * oh) * W + 2 * ow) * C + cq * 4;
+        float v[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 t = ldg4(a + base + off[k]);
+            v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+        }
+        const float4 g4 = ldg4(dp + q * 4);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        float o[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int arg = 0;
+            float best = v[0][c];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (v[k][c] > best) { best = v[k][c]; arg = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][c] = (k == arg) ? g[c] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 w = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+            float* d = da + base + off[k];
+            if (accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(d);
+                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+            }
+            stg4(d, w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- bilinear x2, align_corners=True
+// source coordinate exactly as ATen's area_pixel_compute_source_index: scale = (in-1)/(out-1) in fp32
+__device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int& i1, float& l0, float& l1) {
+    const float s = scale * (float)o;
+    i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
+                                                             int H, int W, int C, float sh, float sw) {
+    const int CQ = C >> 2, OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)N * OH * OW * CQ;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(q % CQ);
+        long long r = q / CQ;
+        const int ow = (int)(r % OW); r /= OW;
+        const int oh = (int)(r % OH);
+        const int n = (int)(r / OH);
+        int h0, h1, w0, w1;
+        float lh0, lh1, lw0, lw1;
+        bil_src(oh, sh, H, h0, h1, lh0, lh1);
+        bil_src(ow, sw, W, w0, w1, lw0, lw1);
+        const float* b = x + (long long)n * H * W * C + cq * 4;
+        const float4 v00 = ldg4(b + ((long long)h0 * W + w0) * C), v01 = ldg4(b + ((long long)h0 * W + w1) * C);
+        const float4 v10 = ldg4(b + ((long long)h1 * W + w0) * C), v11 = ldg4(b + ((long long)h1 * W + w1) * C);
+        float4 o;
+        o.x = lh0 * (lw0 * v00.x + lw1 * v01.x) + lh1 * (lw0 * v10.x + lw1 * v11.x);
+        o.y = lh0 * (lw0 * v00.y + lw1 * v01.y) + lh1 * (lw0 * v10.y + lw1 * v11.y);
+        o.z = lh0 * (lw0 * v00.z + lw1 * v01.z) + lh1 * (lw0 * v10.z + lw1 * v11.z);
+        o.w = lh0 * (lw0 * v00.w + lw1 * v01.w) + lh1 * (lw0 * v10.w + lw1 * v11.w);
+        stg4(y + q * 4, o);
+    }
+}
+
+// gather form of the transpose (deterministic, no atomics): every low-res pixel sums the <= 4x4 high-res
+// pixels whose interpolation footprint touches it.
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N,
+                                                             int H, int W, int C, float sh, float sw, int accumulate) {
+    const int CQ = C >> 2, OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)N * H * W * CQ;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(q % CQ);
+        long long r = q / CQ;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        // candidate output rows/cols: src = scale*o in (h-1, h+1)
+        int oh_lo = sh > 0.f ? (int)floorf((float)(h - 1) / sh) - 1 : 0;
+        int oh_hi = sh > 0.f ? (int)ceilf((float)(h + 1) / sh) + 1 : OH - 1;
+        int ow_lo = sw > 0.f ? (int)floorf((float)(w - 1) / sw) - 1 : 0;
+        int ow_hi = sw > 0.f ? (int)ceilf((float)(w + 1) / sw) + 1 : OW - 1;
+        oh_lo = max(oh_lo, 0); ow_lo = max(ow_lo, 0);
+        oh_hi = min(oh_hi, OH - 1); ow_hi = min(ow_hi, OW - 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* b = dy + (long long)n * OH * OW * C + cq * 4;
+        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+            int h0, h1;
+            float lh0, lh1;
+            bil_src(oh, sh, H, h0, h1, lh0, lh1);
+            float wh = 0.f;
+            if (h0 == h) wh += lh0;
+            if (h1 == h) wh += lh1;
+            if (wh == 0.f) continue;
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                int w0, w1;
+                float lw0, lw1;
+                bil_src(ow, sw, W, w0, w1, lw0, lw1);
+                float ww = 0.f;
+                if (w0 == w) ww += lw0;
+                if (w1 == w) ww += lw1;
+                if (ww == 0.f) continue;
+                const float4 g = ldg4(b + ((long long)oh * OW + ow) * C);
+                const float f = wh * ww;
+                acc.x += f * g.x; acc.y += f * g.y; acc.z += f * g.z; acc.w += f * g.w;
+            }
+        }
+        float* d = dx + q * 4;
+        if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(d);
+            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+        }
+        stg4(d, acc);
+    }
+}
+
+// ---------------------------------------------------------------- layout helpers
+// [N][C][S] <-> [N][S][C]
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           long long N, int C, long long S) {
+    const long long total = N * S * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        const long long s = r % S, n = r / S;
+        dst[i] = src[(n * C + c) * S + s];
+    }
+}
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                           long long N, int C, long long S) {
+    const long long total = N * S * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i % S;
+        const long long r = i / S;
+        const int c = (int)(r % C);
+        const long long n = r / C;
+        dst[i] = src[(n * S + s) * C + c];
+    }
+}
+
+// column sums of a [M][C] matrix (bias gradient of a ConvTranspose): two-stage deterministic
+__global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restrict__ g, long long M, int C,
+                                                          float* __restrict__ part) {
+    __shared__ float sred[256];
+    const int tid = threadIdx.x;
+    const int c = tid % C, sl = tid / C, SL = 256 / C;
+    float s = 0.f;
+    if (sl < SL)
+        for (long long m = (long long)blockIdx.x * SL + sl; m < M; m += (long long)gridDim.x * SL) s += __ldg(g + m * C + c);
+    sred[tid] = s;
+    __syncthreads();
+    if (tid < C) {
+        float v = 0.f;
+        for (int k = 0; k < SL; ++k) v += sred[k * C + tid];
+        part[(size_t)blockIdx.x * C + tid] = v;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ out, int accumulate) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int b = 0; b < nblk; ++b) s += part[(size_t)b * C + c];
+        out[c] = accumulate ? out[c] + (float)s : (float)s;
+    }
+}
+
+// c = a + b (VNet additive skips, code/networks/vnet.py:210,214,218,222)
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                  float* __restrict__ c, long long total4) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(a + q * 4), y = ldg4(b + q * 4);
+        stg4(c + q * 4, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
+    }
+}
+
+// ================================================================ C ABI
+B200_API int b200_maxpool2_fwd(const float* a, float* out, int N, int H, int W, int C, cudaStream_t st) {
+    B200_REQUIRE(a && out && N > 0 && C > 0 && (C & 3) == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_fwd: bad arguments");
+    maxpool2_fwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(a, out, N, H, W, C);
+    B200_CHECK_LAUNCH("maxpool2_fwd");
+    return B200_OK;
+}
+
+B200_API int b200_maxpool2_bwd(const float* a, const float* dp, float* da, int N, int H, int W, int C, int accumulate,
+                               cudaStream_t st) {
+    B200_REQUIRE(a && dp && da && N > 0 && C > 0 && (C & 3) == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2_bwd: bad arguments");
+    maxpool2_bwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4)), 256, 0, st>>>(a, dp, da, N, H, W, C, accumulate);
+    B200_CHECK_LAUNCH("maxpool2_bwd");
+    return B200_OK;
+}
+
+static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+B200_API int b200_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st) {
+    B200_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample2x_fwd: bad arguments");
+    upsample2x_fwd_kernel<<<ew_grid((long long)N * 4 * H * W * (C / 4)), 256, 0, st>>>(x, y, N, H, W, C, ac_scale(H, 2 * H),
+                                                                                      ac_scale(W, 2 * W));
+    B200_CHECK_LAUNCH("upsample2x_fwd");
+    return B200_OK;
+}
+
+B200_API int b200_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st) {
+    B200_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample2x_bwd: bad arguments");
+    upsample2x_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, st>>>(dy, dx, N, H, W, C, ac_scale(H, 2 * H),
+                                                                                  ac_scale(W, 2 * W), accumulate);
+    B200_CHECK_LAUNCH("upsample2x_bwd");
+    return B200_OK;
+}
+
+B200_API int b200_nchw_to_nhwc(const float* src, float* dst, long long N, int C, long long S, cudaStream_t st) {
+    B200_REQUIRE(src && dst && N > 0 && C > 0 && S > 0, "nchw_to_nhwc: bad arguments");
+    nchw_to_nhwc_kernel<<<ew_grid(N * C * S), 256, 0, st>>>(src, dst, N, C, S);
+    B200_CHECK_LAUNCH("nchw_to_nhwc");
+    return B200_OK;
+}
+
+B200_API int b200_nhwc_to_nchw(const float* src, float* dst, long long N, int C, long long S, cudaStream_t st) {
+    B200_REQUIRE(src && dst && N > 0 && C > 0 && S > 0, "nhwc_to_nchw: bad arguments");
+    nhwc_to_nchw_kernel<<<ew_grid(N * C * S), 256, 0, st>>>(src, dst, N, C, S);
+    B200_CHECK_LAUNCH("nhwc_to_nchw");
+    return B200_OK;
+}
+
+B200_API long long b200_colsum_workspace_bytes(long long M, int C) {
+    (void)M;
+    return (long long)b200_num_sms() * 4 * C * sizeof(float);
+}
+
+B200_API int b200_colsum(const float* g, long long M, int C, float* out, int accumulate, float* workspace,
+                         long long workspace_bytes, cudaStream_t st) {
+    B200_REQUIRE(g && out && workspace && M > 0 && C > 0 && C <= 256, "colsum: bad arguments (C <= 256)");
+    B200_REQUIRE(workspace_bytes >= b200_colsum_workspace_bytes(M, C), "colsum: workspace too small");
+    const int SL = 256 / C;
+    long long want = (M + SL - 1) / SL;
+    int grid = (int)(want < (long long)b200_num_sms() * 4 ? want : (long long)b200_num_sms() * 4);
+    colsum_part_kernel<<<grid, 256, 0, st>>>(g, M, C, workspace);
+    B200_CHECK_LAUNCH("colsum_part");
+    colsum_final_kernel<<<1, 256, 0, st>>>(workspace, grid, C, out, accumulate);
+    B200_CHECK_LAUNCH("colsum_final");
+    return B200_OK;
+}
+
+B200_API int b200_add(const float* a, const float* b, float* c, long long n, cudaStream_t st) {
+    B200_REQUIRE(a && b && c && n > 0 && (n & 3) == 0, "add: bad arguments (n multiple of 4)");
+    add_kernel<<<ew_grid(n / 4), 256, 0, st>>>(a, b, c, n / 4);
+    B200_CHECK_LAUNCH("add");
+    return B200_OK;
+}

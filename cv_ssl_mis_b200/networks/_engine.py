@@ -1,0 +1,162 @@
+"""Host-side building blocks shared by the network engines.
+
+`FlatParams` keeps all parameters (and their gradients) of a module in two flat fp32 device buffers so the
+optimizer/EMA/all-reduce each touch one contiguous range.  `ConvLayer` is one convolution of the reference
+networks together with the BatchNorm -> activation -> dropout that follows it, executed through the C ABI
+(`ops`), forward and backward, on channels-last buffers that are allocated once per input geometry.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._lib import (PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONV_DGRAD_D2S, PACK_DECONV_FWD, PACK_DECONV_DGRAD)
+
+
+class FlatParams:
+    """Re-homes module.parameters() (in registration order, like the reference's EMA zip) into one flat buffer."""
+
+    def __init__(self, module: nn.Module, device):
+        self.params = [p for p in module.parameters()]
+        self.numel = sum(p.numel() for p in self.params)
+        # every tensor starts on a 16-byte boundary (vectorised optimizer); padding is zero and stays zero
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.padded = off
+        self.data = torch.zeros(self.padded, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(self.padded, dtype=torch.float32, device=device)
+        for p, o in zip(self.params, self.offsets):
+            view = self.data[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def grad_of(self, p):
+        return p.grad
+
+
+class Runtime:
+    """Per-engine execution context: precision mode, RNG key and shared scratch."""
+
+    def __init__(self, device, seed=1337, exact=False):
+        self.device = device
+        self.exact = exact
+        self.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        # bumped once per forward so every pass draws fresh dropout masks, including CUDA-graph replays
+        self.seed_off = torch.zeros(1, dtype=torch.int64, device=device)
+        self.scratch = None
+        self.scratch_bytes = 0
+
+    def need_scratch(self, nbytes):
+        self.scratch_bytes = max(self.scratch_bytes, int(nbytes))
+
+    def alloc_scratch(self):
+        if self.scratch is None or self.scratch.numel() * 4 < self.scratch_bytes:
+            self.scratch = torch.empty((self.scratch_bytes + 3) // 4 + 4, dtype=torch.float32, device=self.device)
+
+
+class ConvLayer:
+    """conv (or k2s2 transposed conv) [+ BatchNorm(train) + LeakyReLU/ReLU + Dropout] on channels-last buffers."""
+
+    def __init__(self, conv, bn=None, slope=None, p_drop=0.0, drop_mode=0, rng_stream=0, kind="conv", dims=2,
+                 out_nchw=False, name=""):
+        self.conv, self.bn, self.slope = conv, bn, slope
+        self.p_drop, self.drop_mode, self.rng_stream = float(p_drop), int(drop_mode), int(rng_stream)
+        self.kind, self.dims, self.out_nchw, self.name = kind, dims, out_nchw, name
+        self.k = conv.kernel_size[0]
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+        if kind == "conv":
+            self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+        else:
+            self.cin, self.cout = conv.weight.shape[0], conv.weight.shape[1]
+        self.T = self.k ** dims
+        self.has_act = bn is not None
+        assert (bn is None) == (slope is None)
+
+    # ---- planning: geometry -> descriptor + buffers
+    def plan(self, rt: Runtime, n, id_, ih, iw, c0, c1, need_grad):
+        assert c0 + c1 == self.cin, (self.name, c0, c1, self.cin)
+        dev = rt.device
+        self.n, self.c0, self.c1 = n, c0, c1
+        self.desc = ops.conv_desc(n, id_, ih, iw, c0, c1, self.cout, self.k, self.stride, self.pad, self.dims)
+        if self.kind == "conv":
+            self.od, self.oh, self.ow = ops.desc_out_dims(self.desc)
+        else:
+            self.od, self.oh, self.ow = (id_ * 2 if self.dims == 3 else id_), ih * 2, iw * 2
+        self.M = n * self.od * self.oh * self.ow
+        self.spatial = self.od * self.oh * self.ow
+        shape = (n, self.cout, self.spatial) if self.out_nchw else (self.M, self.cout)
+        self.y = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.a = torch.empty_like(self.y) if self.has_act else self.y
+        # d/d(output) and then, in place, d/d(raw conv out); always channels-last
+        self.g = torch.empty((self.M, self.cout), dtype=torch.float32, device=dev) if need_grad else None
+        if self.has_act:
+            self.state = torch.empty(4 * self.cout, dtype=torch.float32, device=dev)
+            rt.need_scratch(ops.bn_workspace_bytes(self.M, self.cout))
+        O, I = self.cout, self.cin
+        fwd_mode = PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD
+        self.wp_fwd = torch.empty(ops.conv_packed_floats(fwd_mode, O, I, self.T), dtype=torch.float32, device=dev)
+        self.wp_bwd = None
+        if need_grad:
+            if self.kind == "conv":
+                self.bwd_mode = PACK_CONV_DGRAD if self.stride == 1 else PACK_CONV_DGRAD_D2S
+                rt.need_scratch(ops.conv_wgrad_workspace_bytes(self.desc))
+            else:
+                self.bwd_mode = PACK_DECONV_DGRAD
+                rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
+                                    ops.colsum_workspace_bytes(self.M, self.cout)))
+            self.wp_bwd = torch.empty(ops.conv_packed_floats(self.bwd_mode, O, I, self.T), dtype=torch.float32, device=dev)
+        return self
+
+    def pack(self, need_dgrad):
+        O, I = self.cout, self.cin
+        ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
+        if need_dgrad and self.wp_bwd is not None:
+            ops.conv_pack_weights(self.conv.weight, self.wp_bwd, self.bwd_mode, O, I, self.T)
+
+    # ---- forward
+    def forward(self, rt: Runtime, src0, src1=None, train=True):
+        if self.kind == "conv":
+            ops.conv_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw, rt.exact)
+        else:
+            ops.deconv_k2s2_fwd(self.desc, src0, self.wp_fwd, self.conv.bias, self.y, rt.exact)
+        if not self.has_act:
+            return self.y
+        bn = self.bn
+        if train:
+            ops.bn_stats_fwd(self.y, self.M, self.cout, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean,
+                             bn.running_var, self.state, rt.scratch)
+            ops.bn_act_fwd(self.y, self.state, self.a, self.M, self.cout, self.slope, self.p_drop, self.drop_mode,
+                           rt.seed, rt.seed_off, self.rng_stream, self.spatial)
+        else:
+            ops.bn_eval_state(self.cout, bn.weight, bn.bias, bn.eps, bn.running_mean, bn.running_var, self.state)
+            ops.bn_act_fwd(self.y, self.state, self.a, self.M, self.cout, self.slope, 0.0, 0, 0, None, 0, self.spatial)
+        return self.a
+
+    # ---- backward: self.g holds d/d(output); writes parameter grads and (optionally) input grads
+    def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False):
+        conv, bn = self.conv, self.bn
+        if self.has_act:
+            ops.bn_act_bwd(self.y, self.g, self.state, self.g, bn.weight.grad, bn.bias.grad, self.M, self.cout,
+                           self.slope, rt.scratch, self.p_drop, self.drop_mode, rt.seed, rt.seed_off, self.rng_stream,
+                           self.spatial)
+        dy = self.g
+        bias_grad = conv.bias.grad if conv.bias is not None else None
+        if self.kind == "conv":
+            ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
+            if dx0 is not None:
+                if self.stride == 1:
+                    ops.conv_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx, rt.exact)
+                else:
+                    ops.conv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
+        else:
+            ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch, conv.weight.grad, False, rt.exact)
+            if bias_grad is not None:
+                ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch)
+            if dx0 is not None:
+                ops.deconv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)

@@ -1,0 +1,202 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/b200ssl.h).
+
+Every function takes CUDA fp32 tensors that the caller owns, borrows their `data_ptr()` for the duration of
+the (asynchronous) call on torch's current stream, and returns nothing: outputs are written in place into
+caller-provided tensors so the step allocates nothing and can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, B200Error  # noqa: F401  (re-exported)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise B200Error("b200ssl ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise B200Error("b200ssl ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def _pf(t):
+    if t is not None and t.dtype != torch.float32:
+        raise B200Error(f"expected float32 tensor, got {t.dtype}")
+    return _p(t)
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def conv_desc(n, id_, ih, iw, c0, c1, cout, k, stride=1, pad=None, dims=2) -> ConvDesc:
+    """k: kernel size per spatial dim (same in all); dims: 2 or 3."""
+    if pad is None:
+        pad = k // 2 if stride == 1 else 0
+    kd = k if dims == 3 else 1
+    pd = pad if dims == 3 else 0
+    return ConvDesc(n, id_, ih, iw, c0, c1, cout, kd, k, k, stride, pd, pad, pad)
+
+
+def desc_out_dims(d: ConvDesc):
+    od = (d.id + 2 * d.pd - d.kd) // d.stride + 1
+    oh = (d.ih + 2 * d.ph - d.kh) // d.stride + 1
+    ow = (d.iw + 2 * d.pw - d.kw) // d.stride + 1
+    return od, oh, ow
+
+
+# ------------------------------------------------------------------ convolutions
+def conv_packed_floats(mode, O, I, T) -> int:
+    return int(_lib.query("b200_conv_packed_floats", mode, O, I, T))
+
+
+def conv_pack_weights(w, out, mode, O, I, T):
+    _lib.call("b200_conv_pack_weights", _pf(w), _pf(out), mode, O, I, T, _st())
+
+
+def conv_fwd(d, src0, src1, wp, bias, dst, out_nchw=False, exact=False):
+    _lib.call("b200_conv_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wp), _pf(bias), _pf(dst), int(out_nchw), int(exact), _st())
+
+
+def conv_dgrad(d, dy, wp_dgrad, dx0, dx1=None, accumulate=False, exact=False):
+    _lib.call("b200_conv_dgrad", C.byref(d), _pf(dy), _pf(wp_dgrad), _pf(dx0), _pf(dx1), int(accumulate), int(exact), _st())
+
+
+def conv_k2s2_dgrad(d, dy, wp_d2s, dx, accumulate=False, exact=False):
+    _lib.call("b200_conv_k2s2_dgrad", C.byref(d), _pf(dy), _pf(wp_d2s), _pf(dx), int(accumulate), int(exact), _st())
+
+
+def conv_wgrad_workspace_bytes(d) -> int:
+    return int(_lib.query("b200_conv_wgrad_workspace_bytes", C.byref(d)))
+
+
+def conv_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False, exact=False):
+    _lib.call("b200_conv_wgrad", C.byref(d), _pf(src0), _pf(src1), _pf(dy), _p(ws), ws.numel() * ws.element_size(),
+              _pf(dw), _pf(db), int(accumulate), int(exact), _st())
+
+
+def deconv_k2s2_fwd(d, x, wp, bias, y, exact=False):
+    _lib.call("b200_deconv_k2s2_fwd", C.byref(d), _pf(x), _pf(wp), _pf(bias), _pf(y), int(exact), _st())
+
+
+def deconv_k2s2_dgrad(d, dy, wp_dgrad, dx, accumulate=False, exact=False):
+    _lib.call("b200_deconv_k2s2_dgrad", C.byref(d), _pf(dy), _pf(wp_dgrad), _pf(dx), int(accumulate), int(exact), _st())
+
+
+def deconv_k2s2_wgrad_workspace_bytes(d) -> int:
+    return int(_lib.query("b200_deconv_k2s2_wgrad_workspace_bytes", C.byref(d)))
+
+
+def deconv_k2s2_wgrad(d, x, dy, ws, dw, accumulate=False, exact=False):
+    _lib.call("b200_deconv_k2s2_wgrad", C.byref(d), _pf(x), _pf(dy), _p(ws), ws.numel() * ws.element_size(), _pf(dw),
+              int(accumulate), int(exact), _st())
+
+
+# ------------------------------------------------------------------ norm / activation / dropout
+def bn_workspace_bytes(M, C_) -> int:
+    return int(_lib.query("b200_bn_workspace_bytes", M, C_))
+
+
+def bn_stats_fwd(y, M, C_, gamma, beta, eps, momentum, running_mean, running_var, state, ws):
+    _lib.call("b200_bn_stats_fwd", _pf(y), M, C_, _pf(gamma), _pf(beta), eps, momentum, _pf(running_mean),
+              _pf(running_var), _pf(state), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def bn_eval_state(C_, gamma, beta, eps, running_mean, running_var, state):
+    _lib.call("b200_bn_eval_state", C_, _pf(gamma), _pf(beta), eps, _pf(running_mean), _pf(running_var), _pf(state), _st())
+
+
+def bn_act_fwd(y, state, a, M, C_, slope, p_drop=0.0, drop_mode=0, seed=0, seed_off=None, rng_stream=0, spatial=1):
+    _lib.call("b200_bn_act_fwd", _pf(y), _pf(state), _pf(a), M, C_, slope, p_drop, drop_mode, seed, _p(seed_off),
+              rng_stream, spatial, _st())
+
+
+def bn_act_bwd(y, da, state, dy, dgamma, dbeta, M, C_, slope, ws, p_drop=0.0, drop_mode=0, seed=0, seed_off=None,
+               rng_stream=0, spatial=1, accumulate=False):
+    _lib.call("b200_bn_act_bwd", _pf(y), _pf(da), _pf(state), _pf(dy), _pf(dgamma), _pf(dbeta), int(accumulate), M, C_,
+              slope, p_drop, drop_mode, seed, _p(seed_off), rng_stream, spatial, _p(ws),
+              ws.numel() * ws.element_size(), _st())
+
+
+def dropout_mask(mask, M, C_, p_drop, drop_mode, seed, seed_off=None, rng_stream=0, spatial=1):
+    _lib.call("b200_dropout_mask", _pf(mask), M, C_, p_drop, drop_mode, seed, _p(seed_off), rng_stream, spatial, _st())
+
+
+# ------------------------------------------------------------------ resampling / layout
+def maxpool2_fwd(a, out, N, H, W, C_):
+    _lib.call("b200_maxpool2_fwd", _pf(a), _pf(out), N, H, W, C_, _st())
+
+
+def maxpool2_bwd(a, dp, da, N, H, W, C_, accumulate=False):
+    _lib.call("b200_maxpool2_bwd", _pf(a), _pf(dp), _pf(da), N, H, W, C_, int(accumulate), _st())
+
+
+def upsample2x_fwd(x, y, N, H, W, C_):
+    _lib.call("b200_upsample2x_fwd", _pf(x), _pf(y), N, H, W, C_, _st())
+
+
+def upsample2x_bwd(dy, dx, N, H, W, C_, accumulate=False):
+    _lib.call("b200_upsample2x_bwd", _pf(dy), _pf(dx), N, H, W, C_, int(accumulate), _st())
+
+
+def nchw_to_nhwc(src, dst, N, C_, S):
+    _lib.call("b200_nchw_to_nhwc", _pf(src), _pf(dst), N, C_, S, _st())
+
+
+def nhwc_to_nchw(src, dst, N, C_, S):
+    _lib.call("b200_nhwc_to_nchw", _pf(src), _pf(dst), N, C_, S, _st())
+
+
+def colsum_workspace_bytes(M, C_) -> int:
+    return int(_lib.query("b200_colsum_workspace_bytes", M, C_))
+
+
+def colsum(g, M, C_, out, ws, accumulate=False):
+    _lib.call("b200_colsum", _pf(g), M, C_, _pf(out), int(accumulate), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def add(a, b, c):
+    _lib.call("b200_add", _pf(a), _pf(b), _pf(c), a.numel(), _st())
+
+
+# ------------------------------------------------------------------ loss / optimizer / noise
+def _label_dtype(labels):
+    if labels is None:
+        return _lib.LABEL_U8
+    if labels.dtype == torch.uint8:
+        return _lib.LABEL_U8
+    if labels.dtype == torch.int64:
+        return _lib.LABEL_I64
+    raise B200Error(f"labels must be uint8 or int64, got {labels.dtype}")
+
+
+def ssl_loss_workspace_bytes(B, S) -> int:
+    return int(_lib.query("b200_ssl_loss_workspace_bytes", B, S))
+
+
+def ssl_loss_fwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, ws):
+    _lib.call("b200_ssl_loss_fwd", _pf(logits), _pf(teacher), _p(labels), _label_dtype(labels), int(nhwc), B, Lb, C_, S,
+              _pf(w_cons), _pf(lossbuf), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+    _lib.call("b200_ssl_loss_bwd", _pf(logits), _pf(teacher), _p(labels), _label_dtype(labels), int(nhwc), B, Lb, C_, S,
+              _pf(w_cons), _pf(lossbuf), grad_scale, _pf(dlogits), int(dlogits_nhwc), _st())
+
+
+def sgd_ema_step(params, grads, momentum_buf, ema_params, hparams, zero_grad=False):
+    _lib.call("b200_sgd_ema_step", _pf(params), _pf(grads), _pf(momentum_buf), _pf(ema_params), params.numel(),
+              _pf(hparams), int(zero_grad), _st())
+
+
+def ema_update(ema_params, params, hparams):
+    _lib.call("b200_ema_update", _pf(ema_params), _pf(params), params.numel(), _pf(hparams), _st())
+
+
+def noise_add(x, out, sigma, clip, seed, seed_off=None, rng_stream=0):
+    _lib.call("b200_noise_add", _pf(x), _pf(out), out.numel(), sigma, clip, seed, _p(seed_off), rng_stream, _st())

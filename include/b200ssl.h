@@ -1,0 +1,139 @@
+/* b200ssl -- C ABI of the B200 (sm_100a) kernels behind the semi-supervised training step.
+ *
+ * The reference (ziyangwang007/CV-SSL-MIS) has no FFI layer: its hot path is Python calling ATen/cuDNN.
+ * Each entry point below therefore cites the reference Python call it replaces (paths relative to the
+ * reference root). Conventions:
+ *   - plain pointers and sizes, no framework types; all tensor pointers are DEVICE pointers (fp32 unless
+ *     stated), activations are channels-last: [N][D][H][W][C] with C contiguous (a 2D image has D = 1);
+ *   - every call is asynchronous on `stream`, allocates nothing, and keeps no global state; scratch memory
+ *     comes from the caller (query the size with the matching *_workspace_bytes function);
+ *   - return value: 0 on success, negative on error (B200_ERR_*), message via b200_last_error();
+ *   - `exact` != 0 selects 3xTF32 (fp32-equivalent) tensor-core math, 0 selects TF32 inputs with fp32
+ *     accumulation (what cuDNN runs for the reference by default, torch.backends.cudnn.allow_tf32 = True).
+ */
+#ifndef B200SSL_H
+#define B200SSL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum { B200_LABEL_U8 = 0, B200_LABEL_I64 = 1 };
+
+/* weight packing modes (b200_conv_pack_weights); T = taps = kd*kh*kw */
+enum {
+    B200_PACK_CONV_FWD = 0,       /* w[O][I][T] -> rows (tap, i), cols o             : b200_conv_fwd          */
+    B200_PACK_CONV_DGRAD = 1,     /* w[O][I][T] -> rows (flipped tap, o), cols i     : b200_conv_dgrad        */
+    B200_PACK_CONV_DGRAD_D2S = 2, /* w[O][I][T] -> rows o, cols (tap, i)             : b200_conv_k2s2_dgrad   */
+    B200_PACK_DECONV_FWD = 3,     /* w[I][O][T] -> rows i, cols (tap, o)             : b200_deconv_k2s2_fwd   */
+    B200_PACK_DECONV_DGRAD = 4    /* w[I][O][T] -> rows (tap, o), cols i             : b200_deconv_k2s2_dgrad */
+};
+
+typedef struct b200_conv_desc {
+    int n, id, ih, iw;   /* input batch and spatial dims (id = 1 for 2D)                      */
+    int c0, c1;          /* input channels; c1 > 0: the input is the channel concat [src0|src1] */
+    int cout;            /* output channels                                                   */
+    int kd, kh, kw;      /* kernel (kd = 1 for 2D)                                            */
+    int stride;          /* 1 or 2, all dims                                                  */
+    int pd, ph, pw;      /* zero padding                                                      */
+} b200_conv_desc;
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int b200_device_sm(void);
+
+/* ------------------------------------------------------------------ convolutions
+ * nn.Conv2d / nn.Conv3d / nn.ConvTranspose3d: code/networks/unet.py:37,41,73,138 ; code/networks/vnet.py:16,73,100,175 */
+long long b200_conv_packed_floats(int mode, int O, int I, int T);
+int b200_conv_pack_weights(const float* w, float* out, int mode, int O, int I, int T, cudaStream_t stream);
+/* dst[n][od][oh][ow][cout] (out_nchw = 0) or dst[n][cout][spatial] (out_nchw = 1) */
+int b200_conv_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wp_fwd, const float* bias,
+                  float* dst, int out_nchw, int exact, cudaStream_t stream);
+/* stride-1 'same' convolution; the input gradient may be split over the two concat sources [dx0|dx1] */
+int b200_conv_dgrad(const b200_conv_desc* d, const float* dy, const float* wp_dgrad, float* dx0, float* dx1,
+                    int accumulate, int exact, cudaStream_t stream);
+/* kernel 2 / stride 2 / pad 0 convolution (code/networks/vnet.py:73) */
+int b200_conv_k2s2_dgrad(const b200_conv_desc* d, const float* dy, const float* wp_d2s, float* dx, int accumulate,
+                         int exact, cudaStream_t stream);
+long long b200_conv_wgrad_workspace_bytes(const b200_conv_desc* d);
+/* dw in the framework layout [cout][c0+c1][kd][kh][kw]; db[cout] may be NULL */
+int b200_conv_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
+                    long long workspace_bytes, float* dw, float* db, int accumulate, int exact, cudaStream_t stream);
+/* ConvTranspose kernel 2 / stride 2 (code/networks/vnet.py:100); desc dims are the LOW-resolution input,
+ * c0 = in channels, cout = out channels, weight layout [c0][cout][kd][kh][kw] */
+int b200_deconv_k2s2_fwd(const b200_conv_desc* d, const float* x, const float* wp, const float* bias, float* y,
+                         int exact, cudaStream_t stream);
+int b200_deconv_k2s2_dgrad(const b200_conv_desc* d, const float* dy, const float* wp_dgrad, float* dx, int accumulate,
+                           int exact, cudaStream_t stream);
+long long b200_deconv_k2s2_wgrad_workspace_bytes(const b200_conv_desc* d);
+int b200_deconv_k2s2_wgrad(const b200_conv_desc* d, const float* x, const float* dy, float* workspace,
+                           long long workspace_bytes, float* dw, int accumulate, int exact, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ BatchNorm(train) + activation + dropout
+ * nn.BatchNorm2d/3d + nn.LeakyReLU/ReLU + nn.Dropout/Dropout3d: code/networks/unet.py:38-43 ; code/networks/vnet.py:16-25,177
+ * state = [mean | invstd | scale | shift] (4*C floats).  drop_mode: 0 none, 1 per element, 2 per (sample, channel).
+ * The Philox key is seed + *seed_offset_dev (DEVICE scalar, may be NULL): bump it per step so a captured CUDA
+ * graph draws fresh masks/noise at every replay. */
+long long b200_bn_workspace_bytes(long long M, int C);
+int b200_bn_stats_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var, float* state, void* workspace, long long workspace_bytes,
+                      cudaStream_t stream);
+int b200_bn_eval_state(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                       const float* running_var, float* state, cudaStream_t stream);
+int b200_bn_act_fwd(const float* y, const float* state, float* a, long long M, int C, float slope, float p_drop,
+                    int drop_mode, unsigned long long seed, const unsigned long long* seed_offset_dev, unsigned rng_stream,
+                    long long spatial, cudaStream_t stream);
+int b200_bn_act_bwd(const float* y, const float* da, const float* state, float* dy, float* dgamma, float* dbeta,
+                    int accumulate, long long M, int C, float slope, float p_drop, int drop_mode, unsigned long long seed,
+                    const unsigned long long* seed_offset_dev, unsigned rng_stream, long long spatial, void* workspace,
+                    long long workspace_bytes, cudaStream_t stream);
+int b200_dropout_mask(float* mask, long long M, int C, float p_drop, int drop_mode, unsigned long long seed,
+                      const unsigned long long* seed_offset_dev, unsigned rng_stream, long long spatial, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ resampling / layout
+ * nn.MaxPool2d(2): code/networks/unet.py:56 ; nn.Upsample(bilinear, align_corners=True): code/networks/unet.py:74-75 */
+int b200_maxpool2_fwd(const float* a, float* out, int N, int H, int W, int C, cudaStream_t stream);
+int b200_maxpool2_bwd(const float* a, const float* dp, float* da, int N, int H, int W, int C, int accumulate,
+                      cudaStream_t stream);
+int b200_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+int b200_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, int accumulate, cudaStream_t stream);
+int b200_nchw_to_nhwc(const float* src, float* dst, long long N, int C, long long S, cudaStream_t stream);
+int b200_nhwc_to_nchw(const float* src, float* dst, long long N, int C, long long S, cudaStream_t stream);
+long long b200_colsum_workspace_bytes(long long M, int C);
+int b200_colsum(const float* g, long long M, int C, float* out, int accumulate, float* workspace,
+                long long workspace_bytes, cudaStream_t stream);
+int b200_add(const float* a, const float* b, float* c, long long n, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ semi-supervised loss
+ * CE + DiceLoss + softmax-MSE consistency: code/train_mean_teacher_2D.py:213-229 ; code/utils/losses.py:74-91,165-201
+ * logits [B][C][S] (layout_nhwc = 0) or [B][S][C] (1); the first Lb samples are labeled, the remaining B-Lb are
+ * compared with teacher_logits [B-Lb][..] (NULL: no consistency term).  w_cons: DEVICE scalar (consistency weight).
+ * lossbuf (>= 4 + 2*C floats): [0] ce [1] dice [2] consistency [3] total, then backward coefficients. */
+long long b200_ssl_loss_workspace_bytes(int B, long long S);
+int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
+                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, float* lossbuf,
+                      void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
+                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, const float* lossbuf,
+                      float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ optimizer / EMA / noise
+ * optim.SGD + update_ema_variables + input noise: code/train_mean_teacher_2D.py:124-128,189-190,208-210,230-233
+ * hparams_dev (DEVICE, 6 floats): [0] lr [1] momentum [2] weight_decay [3] ema_alpha [4] 1-ema_alpha [5] grad_scale */
+int b200_sgd_ema_step(float* params, float* grads, float* momentum_buf, float* ema_params, long long n,
+                      const float* hparams_dev, int zero_grad, cudaStream_t stream);
+int b200_ema_update(float* ema_params, const float* params, long long n, const float* hparams_dev, cudaStream_t stream);
+int b200_noise_add(const float* x, float* out, long long n, float sigma, float clip, unsigned long long seed,
+                   const unsigned long long* seed_offset_dev, unsigned rng_stream, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SSL_H */

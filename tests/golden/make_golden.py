@@ -1,0 +1,190 @@
+"""Generate the golden fixtures in tests/golden/ by running the REFERENCE's own modules.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Imports networks/unet.py, utils/losses.py, utils/ramps.py from /root/reference/code (read-only) and stores
+small seeded input/output vectors.  The trainer loop cannot be imported (tensorboardX/medpy/h5py missing,
+hard-coded .cuda()), so the Mean-Teacher fixture drives the reference's UNet / DiceLoss / ramps /
+torch.optim.SGD through the loop body of code/train_mean_teacher_2D.py:204-236, quoted line by line below.
+Weights are not stored (7 MB): both the reference UNet and our parameter containers draw them from
+torch.manual_seed(seed) in the same order; a checksum is stored and this script asserts they agree.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/code"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from networks.unet import UNet as RefUNet          # noqa: E402
+from utils import losses as ref_losses              # noqa: E402
+from utils import ramps as ref_ramps                # noqa: E402
+
+from cv_ssl_mis_b200.networks.unet import UNet as OurUNet   # noqa: E402  (parameter containers only; no kernels run)
+
+torch.set_num_threads(4)
+torch.backends.mkldnn.enabled = True
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for k, v in sd.items() if v.dtype.is_floating_point))
+
+
+def blocky_labels(gen, B, H, W, ncls, dtype=torch.uint8):
+    low = torch.randint(0, ncls, (B, H // 8, W // 8), generator=gen)
+    return low.repeat_interleave(8, 1).repeat_interleave(8, 2).to(dtype)
+
+
+def no_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+
+
+def unet_fixture():
+    seed = 1234
+    torch.manual_seed(seed)
+    ref = RefUNet(in_chns=1, class_num=4)
+    torch.manual_seed(seed)
+    ours = OurUNet(1, 4)
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    assert list(sd_ref.keys()) == list(sd_ours.keys()), "state_dict key schema differs from the reference"
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_ours[k]), k
+    assert [tuple(p.shape) for p in ref.parameters()] == [tuple(p.shape) for p in ours.parameters()]
+    ck0 = checksum(sd_ref)          # before the train-mode forward moves the BN running stats
+    no_dropout(ref)
+    g = torch.Generator().manual_seed(99)
+    x = torch.rand(2, 1, 32, 32, generator=g)
+    y = blocky_labels(g, 2, 32, 32, 4)
+    ref.train()
+    logits = ref(x)
+    soft = torch.softmax(logits, dim=1)
+    ce = torch.nn.CrossEntropyLoss()(logits, y.long())
+    dice = ref_losses.DiceLoss(4)(soft, y.unsqueeze(1))
+    loss = 0.5 * (dice + ce)
+    loss.backward()
+    names = [n for n, _ in ref.named_parameters()]
+    grad_norm = {n: float(p.grad.norm()) for n, p in ref.named_parameters()}
+    grad_head = {n: p.grad.flatten()[:8].clone() for n, p in ref.named_parameters()}
+    sd_after = ref.state_dict()
+    running = {k: sd_after[k].clone() for k in sd_after if "running" in k and ("in_conv" in k or "up4" in k)}
+    ref.eval()
+    with torch.no_grad():
+        logits_eval = ref(x)
+    torch.save(dict(seed=seed, checksum=ck0, keys=list(sd_ref.keys()), param_names=names, x=x, y=y,
+                    logits=logits.detach(), logits_eval=logits_eval, ce=ce.detach(), dice=dice.detach(),
+                    loss=loss.detach(), grad_norm=grad_norm, grad_head=grad_head, running=running),
+               os.path.join(HERE, "unet_small.pt"))
+    print("unet_small: loss", float(loss), "checksum", checksum(sd_ref))
+
+
+def losses_fixture():
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    for name, (B, C, shape, dt) in {"2d": (3, 4, (16, 16), torch.uint8), "3d": (2, 2, (8, 8, 8), torch.int64)}.items():
+        logits = torch.randn(B, C, *shape, generator=g, requires_grad=True)
+        tlogits = torch.randn(B, C, *shape, generator=g)
+        y = torch.randint(0, C, (B, *shape), generator=g).to(dt)
+        soft = torch.softmax(logits, dim=1)
+        dice = ref_losses.DiceLoss(C)(soft, y.unsqueeze(1))
+        ce = torch.nn.CrossEntropyLoss()(logits, y.long())
+        mse = ref_losses.softmax_mse_loss(logits, tlogits)
+        total = 0.5 * (dice + ce) + 0.37 * mse.mean()
+        (grad,) = torch.autograd.grad(total, logits)
+        out[name] = dict(logits=logits.detach(), teacher=tlogits, y=y, dice=dice.detach(), ce=ce.detach(),
+                         mse=mse.detach(), total=total.detach(), grad=grad, w=0.37)
+    torch.save(out, os.path.join(HERE, "losses.pt"))
+    print("losses: ", {k: float(v["total"]) for k, v in out.items()})
+
+
+def ramps_fixture():
+    pts = [(0, 200), (1, 200), (6, 200.0), (50, 200.0), (199, 200), (200, 200), (500, 200), (3, 0), (10, 40.0)]
+    vals = [ref_ramps.sigmoid_rampup(c, l) for c, l in pts]
+    torch.save(dict(points=pts, values=vals), os.path.join(HERE, "ramps.pt"))
+    print("ramps:", vals[:4])
+
+
+def update_ema_variables(model, ema_model, alpha, global_step):
+    # code/train_mean_teacher_2D.py:124-128 (deprecated add_(scalar, tensor) overload spelled in its modern form)
+    alpha = min(1 - 1 / (global_step + 1), alpha)
+    for ema_param, param in zip(ema_model.parameters(), model.parameters()):
+        ema_param.data.mul_(alpha).add_(param.data, alpha=1 - alpha)
+
+
+def mt_step_fixture():
+    """code/train_mean_teacher_2D.py:137-238 on a tiny batch, two iterations straddling the iter<1000 gate."""
+    seed = 4321
+    torch.manual_seed(seed)
+    model = RefUNet(in_chns=1, class_num=4)          # create_model()           :137-144
+    ema_model = RefUNet(in_chns=1, class_num=4)      # create_model(ema=True)
+    for p in ema_model.parameters():
+        p.detach_()
+    no_dropout(model)
+    no_dropout(ema_model)
+    model.train()                                    # :184 (ema_model is never put in eval mode)
+    base_lr, max_iterations, labeled_bs, ema_decay = 0.01, 30000, 2, 0.99
+    consistency, consistency_rampup = 0.1, 200.0
+    optimizer = torch.optim.SGD(model.parameters(), lr=base_lr, momentum=0.9, weight_decay=0.0001)   # :189-190
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(4)
+    g = torch.Generator().manual_seed(5)
+    init_ck = (checksum(model.state_dict()), checksum(ema_model.state_dict()))
+    # the reference installs lr after each step; emulate having just finished iteration 998
+    iter_num = 999
+    lr_ = base_lr * (1.0 - (iter_num - 1) / max_iterations) ** 0.9
+    for pg in optimizer.param_groups:
+        pg["lr"] = lr_
+    steps = []
+    for _ in range(3):
+        volume_batch = torch.rand(4, 1, 32, 32, generator=g)
+        label_batch = blocky_labels(g, 4, 32, 32, 4)
+        unlabeled_volume_batch = volume_batch[labeled_bs:]                                     # :206
+        noise = torch.clamp(torch.randn(unlabeled_volume_batch.shape, generator=g) * 0.1, -0.2, 0.2)   # :208-209
+        ema_inputs = unlabeled_volume_batch + noise                                             # :210
+        outputs = model(volume_batch)                                                           # :212
+        outputs_soft = torch.softmax(outputs, dim=1)
+        with torch.no_grad():
+            ema_output = ema_model(ema_inputs)                                                  # :215
+            ema_output_soft = torch.softmax(ema_output, dim=1)
+        loss_ce = ce_loss(outputs[:labeled_bs], label_batch[:][:labeled_bs].long())             # :218-219
+        loss_dice = dice_loss(outputs_soft[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1))   # :220-221
+        supervised_loss = 0.5 * (loss_dice + loss_ce)
+        consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :223
+        if iter_num < 1000:
+            consistency_loss = 0.0
+        else:
+            consistency_loss = torch.mean((outputs_soft[labeled_bs:] - ema_output_soft) ** 2)   # :227-228
+        loss = supervised_loss + consistency_weight * consistency_loss
+        lr_used = optimizer.param_groups[0]["lr"]
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        update_ema_variables(model, ema_model, ema_decay, iter_num)                             # :233
+        lr_ = base_lr * (1.0 - iter_num / max_iterations) ** 0.9                                # :234
+        for param_group in optimizer.param_groups:
+            param_group["lr"] = lr_
+        steps.append(dict(iter_num=iter_num, x=volume_batch, y=label_batch, noise=noise, logits=outputs.detach(),
+                          teacher_logits=ema_output, loss=loss.detach(), ce=loss_ce.detach(), dice=loss_dice.detach(),
+                          cons=torch.as_tensor(float(consistency_loss)), w=consistency_weight, lr_used=lr_used,
+                          student_ck=checksum(model.state_dict()), teacher_ck=checksum(ema_model.state_dict()),
+                          w_out=model.decoder.out_conv.weight.detach().clone(),
+                          t_out=ema_model.decoder.out_conv.weight.detach().clone(),
+                          w_in=model.encoder.in_conv.conv_conv[0].weight.detach().clone()))
+        iter_num = iter_num + 1                                                                 # :238
+    torch.save(dict(seed=seed, init_ck=init_ck, labeled_bs=labeled_bs, steps=steps), os.path.join(HERE, "mt_step.pt"))
+    print("mt_step: losses", [float(s["loss"]) for s in steps], "cons", [float(s["cons"]) for s in steps])
+
+
+if __name__ == "__main__":
+    unet_fixture()
+    losses_fixture()
+    ramps_fixture()
+    mt_step_fixture()
