@@ -81,6 +81,11 @@ _NON_STATUS = {"b200_abi_version", "b200_device_sm"}
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`
 
+# optional per-call device timing (bench.py / profiling only): when `profile` is a list, every call is
+# bracketed by CUDA events on the current stream and (entry point, tag, start, end) is appended to it
+profile = None
+tag = ""
+
 
 def load() -> C.CDLL:
     """Load the shared library (once) and bind every declared symbol."""
@@ -106,7 +111,15 @@ def call(name: str, *args):
     """Call a status-returning entry point; raise B200Error with the library's message on failure."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        profile.append((name, tag, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if name in _NON_STATUS or SIGNATURES[name][0] is not _I:
         return rc
     launch_count += 1

