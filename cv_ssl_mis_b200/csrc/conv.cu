@@ -420,8 +420,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
     const int total = K * NG;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total + NG; idx += gridDim.x * blockDim.x) {
         if (idx < total) {
-            float v = 0.f;
-            for (int z = 0; z < splits; ++z) v += part[(size_t)z * total + idx];
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;           // 4 independent chains: loads overlap
+            int z = 0;
+            for (; z + 4 <= splits; z += 4) {
+                v0 += part[(size_t)z * total + idx];
+                v1 += part[(size_t)(z + 1) * total + idx];
+                v2 += part[(size_t)(z + 2) * total + idx];
+                v3 += part[(size_t)(z + 3) * total + idx];
+            }
+            for (; z < splits; ++z) v0 += part[(size_t)z * total + idx];
+            const float v = (v0 + v1) + (v2 + v3);
             const int k = idx / NG, b = idx % NG;
             const int tap = k / A, a = k % A;
             float* d = dw + ((size_t)b * A + a) * T + tap;

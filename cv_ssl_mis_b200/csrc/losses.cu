@@ -117,10 +117,12 @@ __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nb
                                          float* __restrict__ out) {
     __shared__ double tot[SSL_NACC(SSL_MAXC)];
     const int NA = SSL_NACC(Cpad);
-    if (threadIdx.x < NA) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;      // one warp per accumulator
+    if (warp < NA) {
         double s = 0;
-        for (int b = 0; b < nblk; ++b) s += part[(size_t)b * NA + threadIdx.x];
-        tot[threadIdx.x] = s;
+        for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * NA + warp];
+        s = warp_sum_d(s);
+        if (lane == 0) tot[warp] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
 
 static inline int loss_grid(long long total) {
     long long blocks = (total + 255) / 256;
-    long long cap = (long long)b200_num_sms() * 8;
+    long long cap = (long long)b200_num_sms() * 4;
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 static inline int cpad_of(int C) { return C <= 2 ? 2 : (C <= 4 ? 4 : SSL_MAXC); }
@@ -250,7 +252,7 @@ B200_API int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits,
     else if (Cp == 4) ssl_loss_fwd_kernel<4><<<grid, 256, 0, st>>>(g, part);
     else ssl_loss_fwd_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(g, part);
     B200_CHECK_LAUNCH("ssl_loss_fwd");
-    ssl_loss_finalize_kernel<<<1, 32, 0, st>>>(part, grid, Cp, C, Lb, B - Lb, S, teacher_logits != nullptr, w_cons, lossbuf);
+    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(part, grid, Cp, C, Lb, B - Lb, S, teacher_logits != nullptr, w_cons, lossbuf);
     B200_CHECK_LAUNCH("ssl_loss_finalize");
     return B200_OK;
 }

@@ -16,7 +16,7 @@
 
 static inline int stats_grid(long long M, int RP) {
     long long want = (M + RP - 1) / RP;
-    long long cap = (long long)b200_num_sms() * 8;
+    long long cap = (long long)b200_num_sms() * 4;
     return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -46,15 +46,30 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
         const float keep_scale = (MODE == 1 && drop_mode != 0) ? 1.f / (1.f - p_drop) : 1.f;
         float f0[4] = {0, 0, 0, 0}, f1[4] = {0, 0, 0, 0};
         int cnt = 0;
-        for (long long m = (long long)blockIdx.x * RP + pr; m < M; m += (long long)gridDim.x * RP) {
+        // 4 rows per trip: all loads are issued before the first use (memory-level parallelism)
+        const long long stride = (long long)gridDim.x * RP;
+        for (long long mb = (long long)blockIdx.x * RP + pr; mb < M; mb += 4 * stride) {
+          float4 vv[4], gvv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+              const long long m = mb + u * stride;
+              if (m < M) {
+                  vv[u] = ldg4_stream(y + m * C + cq * 4);
+                  if (MODE == 1) gvv[u] = ldg4_stream(da + m * C + cq * 4);
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long long m = mb + u * stride;
+            if (m >= M) break;
             const long long e = m * C + cq * 4;
-            float4 v = ldg4_stream(y + e);
+            float4 v = vv[u];
             float a[4] = {v.x, v.y, v.z, v.w};
             if (MODE == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { f0[i] += a[i]; f1[i] += a[i] * a[i]; }
             } else {
-                float4 gv = ldg4_stream(da + e);
+                float4 gv = gvv[u];
                 float gg[4] = {gv.x, gv.y, gv.z, gv.w};
                 const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
                 const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
@@ -70,11 +85,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
                     f1[i] += gz * ((a[i] - muv[i]) * isv[i]);
                 }
             }
-            if (++cnt == 32) {
+          }
+          if (++cnt == 8) {       // flush the fp32 running sums into fp64 every 32 rows
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { d0[i] += f0[i]; d1[i] += f1[i]; f0[i] = 0.f; f1[i] = 0.f; }
-                cnt = 0;
-            }
+              for (int i = 0; i < 4; ++i) { d0[i] += f0[i]; d1[i] += f1[i]; f0[i] = 0.f; f1[i] = 0.f; }
+              cnt = 0;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { d0[i] += f0[i]; d1[i] += f1[i]; }
@@ -93,16 +109,28 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- finalize forward statistics
-__global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
+// one warp per channel: lanes stride over the per-block partials (fixed order -> deterministic)
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblk, int C, int c, double& s0,
+                                                double& s1) {
+    const int lane = threadIdx.x & 31;
+    double a = 0, b = 0;
+    for (int k = lane; k < nblk; k += 32) {
+        a += part[(size_t)k * 2 * C + c];
+        b += part[(size_t)k * 2 * C + C + c];
+    }
+    s0 = warp_sum_d(a);
+    s1 = warp_sum_d(b);
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ state) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-        double s = 0, ss = 0;
-        for (int b = 0; b < nblk; ++b) {
-            s += part[(size_t)b * 2 * C + c];
-            ss += part[(size_t)b * 2 * C + C + c];
-        }
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s, ss;
+    reduce_partials(part, nblk, C, c, s, ss);
+    if ((threadIdx.x & 31) == 0) {
         const double mean = s / (double)M;
         double var = ss / (double)M - mean * mean;
         if (var < 0) var = 0;
@@ -135,15 +163,14 @@ __global__ void bn_eval_state_kernel(int C, const float* __restrict__ gamma, con
 }
 
 // ---------------------------------------------------------------- finalize backward sums
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ coef) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-        double s = 0, sx = 0;
-        for (int b = 0; b < nblk; ++b) {
-            s += part[(size_t)b * 2 * C + c];
-            sx += part[(size_t)b * 2 * C + C + c];
-        }
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s, sx;
+    reduce_partials(part, nblk, C, c, s, sx);
+    if ((threadIdx.x & 31) == 0) {
         if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
         if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
         coef[c] = (float)(s / (double)M);
@@ -270,7 +297,7 @@ B200_API int b200_bn_stats_fwd(const float* y, long long M, int C, const float* 
     const size_t smem = (size_t)RP * 2 * C * sizeof(double);
     bn_reduce_kernel<0><<<grid, 256, smem, st>>>(y, nullptr, nullptr, M, C, 0.f, 0.f, 0, 0ull, 0u, 1, part, nullptr);
     B200_CHECK_LAUNCH("bn_stats_fwd");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, grid, M, C, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, grid, M, C, gamma, beta, eps, momentum, running_mean,
                                                         running_var, state);
     B200_CHECK_LAUNCH("bn_finalize");
     return B200_OK;
@@ -315,7 +342,7 @@ B200_API int b200_bn_act_bwd(const float* y, const float* da, const float* state
     const size_t smem = (size_t)RP * 2 * C * sizeof(double);
     bn_reduce_kernel<1><<<grid, 256, smem, st>>>(y, da, state, M, C, slope, p_drop, drop_mode, seed, stream, spatial, part, seed_offset_dev);
     B200_CHECK_LAUNCH("bn_act_bwd_reduce");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, grid, M, C, dgamma, dbeta, accumulate, coef);
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, grid, M, C, dgamma, dbeta, accumulate, coef);
     B200_CHECK_LAUNCH("bn_bwd_finalize");
     const long long total4 = M * (C >> 2);
     bn_act_bwd_kernel<<<ew_grid(total4), 256, 0, st>>>(y, da, state, coef, dy, total4, C, slope, p_drop, drop_mode, seed,

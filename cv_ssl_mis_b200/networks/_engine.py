@@ -140,11 +140,13 @@ class ConvLayer:
         return self.a
 
     # ---- backward: self.g holds d/d(output); writes parameter grads and (optionally) input grads
-    def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False):
+    def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False, g_in=None):
+        """g_in: read d/d(output) from another buffer (left untouched) instead of self.g (needs has_act)."""
         conv, bn = self.conv, self.bn
         _lib.tag = self.name
+        assert g_in is None or self.has_act
         if self.has_act:
-            ops.bn_act_bwd(self.y, self.g, self.state, self.g, bn.weight.grad, bn.bias.grad, self.M, self.cout,
+            ops.bn_act_bwd(self.y, self.g if g_in is None else g_in, self.state, self.g, bn.weight.grad, bn.bias.grad, self.M, self.cout,
                            self.slope, rt.scratch, self.p_drop, self.drop_mode, rt.seed, rt.seed_off, self.rng_stream,
                            self.spatial)
         dy = self.g

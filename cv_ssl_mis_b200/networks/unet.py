@@ -171,9 +171,8 @@ class _UNetFn(torch.autograd.Function):
     """Autograd bridge for drop-in use (`loss.backward()` in the reference trainers)."""
 
     @staticmethod
-    def forward(ctx, net, x, *params):
+    def forward(ctx, net, need_grad, x, *params):
         B, _, H, W = x.shape
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         plan = net._get_plan(B, H, W, need_grad)
         xin = x.contiguous().float()
         if net.in_chns != 1:
@@ -204,7 +203,7 @@ class _UNetFn(torch.autograd.Function):
         for p, g in zip(net._flat.params, saved):
             p.grad = g
         plan.in_flight = False
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 class UNet(nn.Module):
@@ -258,4 +257,6 @@ class UNet(nn.Module):
 
     def forward(self, x):
         self.materialize()
-        return _UNetFn.apply(self, x, *self._flat.params)
+        # autograd turns grad mode off inside Function.forward, so decide here whether backward buffers are needed
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._flat.params)
+        return _UNetFn.apply(self, need_grad, x, *self._flat.params)
