@@ -443,6 +443,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
     }
 }
 
+// shared with conv_tile.cu
+int b200_wgrad_reduce_launch(const float* part, const float* part_colsum, int splits, int K, int NG, int A, int T,
+                             float* dw, float* db, int accumulate, cudaStream_t st) {
+    const int total = K * NG + NG;
+    int blocks = (total + 255) / 256;
+    if (blocks > 4 * b200_num_sms()) blocks = 4 * b200_num_sms();
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, part_colsum, splits, K, NG, A, T, dw, db, accumulate);
+    B200_CHECK_LAUNCH("wgrad_reduce");
+    return B200_OK;
+}
+
 template <int WM, int WN, int WK, int MI, int NI>
 static int launch_wgrad_cfg(WgradP& q, int splits, bool exact, bool vec, cudaStream_t st) {
     using Cfg = WgradCfg<WM, WN, WK, MI, NI>;

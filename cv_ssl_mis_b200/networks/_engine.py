@@ -99,30 +99,47 @@ class ConvLayer:
             self.state = torch.empty(4 * self.cout, dtype=torch.float32, device=dev)
             rt.need_scratch(ops.bn_workspace_bytes(self.M, self.cout))
         O, I = self.cout, self.cin
-        fwd_mode = PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD
-        self.wp_fwd = torch.empty(ops.conv_packed_floats(fwd_mode, O, I, self.T), dtype=torch.float32, device=dev)
+        # production path for 3x3 / 3x3x3 stride-1 convs: shared-memory tile kernels (TF32); the generic implicit
+        # GEMM serves everything else and the `exact` (3xTF32) validation mode
+        is_conv = self.kind == "conv"
+        self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
+        self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
+        self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)
+        fwd_mode = PACK_CONV_FWD if is_conv else PACK_DECONV_FWD
+        nfwd = ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T)
+        self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
         self.wp_bwd = None
         if need_grad:
-            if self.kind == "conv":
+            if is_conv:
                 self.bwd_mode = PACK_CONV_DGRAD if self.stride == 1 else PACK_CONV_DGRAD_D2S
-                rt.need_scratch(ops.conv_wgrad_workspace_bytes(self.desc))
+                rt.need_scratch(ops.conv_tile_wgrad_workspace_bytes(self.desc) if self.tile_wgrad
+                                else ops.conv_wgrad_workspace_bytes(self.desc))
             else:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            self.wp_bwd = torch.empty(ops.conv_packed_floats(self.bwd_mode, O, I, self.T), dtype=torch.float32, device=dev)
+            nbwd = ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T)
+            self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
         return self
 
     def pack(self, need_dgrad):
         O, I = self.cout, self.cin
-        ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
+        if self.tile_fwd:
+            ops.conv_tile_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
+        else:
+            ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
         if need_dgrad and self.wp_bwd is not None:
-            ops.conv_pack_weights(self.conv.weight, self.wp_bwd, self.bwd_mode, O, I, self.T)
+            if self.tile_dgrad:
+                ops.conv_tile_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
+            else:
+                ops.conv_pack_weights(self.conv.weight, self.wp_bwd, self.bwd_mode, O, I, self.T)
 
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
         _lib.tag = self.name
-        if self.kind == "conv":
+        if self.tile_fwd:
+            ops.conv_tile_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
+        elif self.kind == "conv":
             ops.conv_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw, rt.exact)
         else:
             ops.deconv_k2s2_fwd(self.desc, src0, self.wp_fwd, self.conv.bias, self.y, rt.exact)
@@ -152,9 +169,14 @@ class ConvLayer:
         dy = self.g
         bias_grad = conv.bias.grad if conv.bias is not None else None
         if self.kind == "conv":
-            ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
+            if self.tile_wgrad:
+                ops.conv_tile_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False)
+            else:
+                ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
             if dx0 is not None:
-                if self.stride == 1:
+                if self.tile_dgrad:
+                    ops.conv_tile_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
+                elif self.stride == 1:
                     ops.conv_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx, rt.exact)
                 else:
                     ops.conv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)

@@ -76,6 +76,22 @@ long long b200_deconv_k2s2_wgrad_workspace_bytes(const b200_conv_desc* d);
 int b200_deconv_k2s2_wgrad(const b200_conv_desc* d, const float* x, const float* dy, float* workspace,
                            long long workspace_bytes, float* dw, int accumulate, int exact, cudaStream_t stream);
 
+/* Tile kernels for 3x3 (2D) / 3x3x3 (3D) stride-1 pad-1 convolutions -- the production path of the same
+ * nn.Conv2d/nn.Conv3d calls (TF32 only): a spatial halo tile is staged once in shared memory and all taps read
+ * it through ldmatrix.  Weights use their own packing ([16-channel chunk][tap][cout][16], TF32-rounded):
+ * dgrad = 0 for b200_conv_tile_fwd, 1 for b200_conv_tile_dgrad.  b200_conv_tile_supported tells whether a
+ * descriptor qualifies (otherwise use the generic b200_conv_* entry points above). */
+int b200_conv_tile_supported(const b200_conv_desc* d, int for_wgrad);
+long long b200_conv_tile_packed_floats(int dgrad, int O, int I, int T);
+int b200_conv_tile_pack_weights(const float* w, float* out, int dgrad, int O, int I, int T, cudaStream_t stream);
+int b200_conv_tile_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt, const float* bias,
+                       float* dst, int out_nchw, cudaStream_t stream);
+int b200_conv_tile_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
+                         int accumulate, cudaStream_t stream);
+long long b200_conv_tile_wgrad_workspace_bytes(const b200_conv_desc* d);
+int b200_conv_tile_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
+                         long long workspace_bytes, float* dw, float* db, int accumulate, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ BatchNorm(train) + activation + dropout
  * nn.BatchNorm2d/3d + nn.LeakyReLU/ReLU + nn.Dropout/Dropout3d: code/networks/unet.py:38-43 ; code/networks/vnet.py:16-25,177
  * state = [mean | invstd | scale | shift] (4*C floats).  drop_mode: 0 none, 1 per element, 2 per (sample, channel).

@@ -171,6 +171,71 @@ def deconv_k2s2_wgrad(d, x, dy, ws, dw, accumulate=False, exact=False):
     _store(dw, gw, accumulate)
 
 
+# ------------------------------------------------------------------ tile kernels (own weight packing)
+def conv_tile_supported(d, for_wgrad=False):
+    ok = (d.stride == 1 and d.kh == 3 and d.kw == 3 and d.ph == 1 and d.pw == 1 and
+          ((d.kd == 1 and d.pd == 0) or (d.kd == 3 and d.pd == 1)) and d.c0 % 4 == 0 and d.c1 % 4 == 0)
+    if for_wgrad:
+        ok = ok and d.kd == 1 and d.cout % 4 == 0
+    return bool(ok)
+
+
+def _r16(v):
+    return (v + 15) // 16 * 16
+
+
+def conv_tile_packed_floats(dgrad, O, I, T):
+    rows, cols = (O, I) if dgrad else (I, O)
+    return ((rows + 15) // 16) * T * _r16(cols) * 16
+
+
+def conv_tile_pack_weights(w, out, dgrad, O, I, T):
+    W = w.detach().reshape(O, I, T)
+    if dgrad:      # out[chunk][tap][i][kk] = W[chunk*16+kk][i][T-1-tap]
+        m = W.flip(2).permute(2, 1, 0)                 # [tap][i][o]
+        rows, cols = O, I
+    else:          # out[chunk][tap][o][kk] = W[o][chunk*16+kk][tap]
+        m = W.permute(2, 0, 1)                         # [tap][o][i]
+        rows, cols = I, O
+    chunks, colsP = (rows + 15) // 16, _r16(cols)
+    buf = torch.zeros(T, colsP, chunks * 16)
+    buf[:, :cols, :rows] = m
+    out.copy_(buf.reshape(T, colsP, chunks, 16).permute(2, 0, 1, 3).reshape(-1))
+
+
+def _tile_unpack(wt, dgrad, O, I, T):
+    rows, cols = (O, I) if dgrad else (I, O)
+    chunks, colsP = (rows + 15) // 16, _r16(cols)
+    buf = wt.reshape(chunks, T, colsP, 16).permute(1, 2, 0, 3).reshape(T, colsP, chunks * 16)[:, :cols, :rows]
+    if dgrad:
+        return buf.permute(2, 1, 0).flip(2)            # [o][i][tap]
+    return buf.permute(1, 2, 0)                        # [o][i][tap]
+
+
+def conv_tile_fwd(d, src0, src1, wt, bias, dst, out_nchw=False):
+    T = d.kd * d.kh * d.kw
+    W = _tile_unpack(wt, False, d.cout, d.c0 + d.c1, T).reshape(d.cout, d.c0 + d.c1, d.kd, d.kh, d.kw)
+    y = F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))
+    dst.copy_((y if out_nchw else _ncdhw_to_cl(y)).reshape(dst.shape))
+
+
+def conv_tile_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
+    T = d.kd * d.kh * d.kw
+    cin = d.c0 + d.c1
+    W = _tile_unpack(wt_dgrad, True, d.cout, cin, T).reshape(d.cout, cin, d.kd, d.kh, d.kw)
+    g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
+    dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
+    _split_store(dx, d, dx0, dx1, accumulate)
+
+
+def conv_tile_wgrad_workspace_bytes(d):
+    return 64
+
+
+def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
+    conv_wgrad(d, src0, src1, dy, ws, dw, db, accumulate)
+
+
 # ------------------------------------------------------------------ norm / act / dropout
 def bn_workspace_bytes(M, C):
     return 64

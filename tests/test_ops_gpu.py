@@ -305,3 +305,69 @@ def test_errors_are_loud():
     with pytest.raises(ops.B200Error):
         ops.bn_act_fwd(torch.zeros(4, 6, device=DEV), torch.zeros(24, device=DEV), torch.zeros(4, 6, device=DEV), 4, 6, 0.01)
     assert _lib.query("b200_device_sm") == 100
+
+
+TILE_CASES = [
+    # n, d, h, w, c0, c1, cout, dims
+    (2, 1, 32, 32, 16, 0, 16, 2),
+    (2, 1, 20, 24, 16, 0, 32, 2),          # partial tiles
+    (1, 1, 16, 48, 16, 16, 16, 2),         # virtual concat
+    (2, 1, 16, 16, 64, 0, 64, 2),
+    (1, 1, 16, 16, 128, 128, 128, 2),
+    (3, 1, 16, 16, 256, 0, 256, 2),
+    (2, 1, 32, 16, 16, 0, 4, 2),           # head: cout = 4
+    (1, 1, 8, 8, 32, 0, 48, 2),            # image smaller than the tile, cout not a multiple of 16
+    (1, 8, 16, 16, 16, 0, 16, 3),
+    (1, 6, 6, 10, 32, 0, 64, 3),           # ragged 3D volume
+    (2, 4, 8, 8, 64, 0, 32, 3),
+]
+
+
+@pytest.mark.parametrize("case", TILE_CASES)
+def test_conv_tile_kernels(case):
+    n, d, h, w, c0, c1, cout, dims = case
+    g = torch.Generator().manual_seed(sum(case) * 7)
+    desc = ops.conv_desc(n, d, h, w, c0, c1, cout, 3, 1, 1, dims)
+    assert ops.conv_tile_supported(desc)
+    T, cin, M = 3 ** dims, c0 + c1, n * d * h * w
+    wgt = rnd(g, cout, cin, *([3] * dims), scale=(cin * T) ** -0.5)
+    bias, x0, dy = rnd(g, cout), rnd(g, M, c0), rnd(g, M, cout)
+    x1 = rnd(g, M, c1) if c1 else None
+    tol = TOL[False]
+    # packing (the device rounds to TF32)
+    for dg in (False, True):
+        pk = torch.empty(ops.conv_tile_packed_floats(dg, cout, cin, T), device=DEV)
+        ops.conv_tile_pack_weights(cu(wgt), pk, dg, cout, cin, T)
+        pk_ref = torch.empty(ref.conv_tile_packed_floats(dg, cout, cin, T))
+        ref.conv_tile_pack_weights(wgt, pk_ref, dg, cout, cin, T)
+        torch.testing.assert_close(pk.cpu(), pk_ref, rtol=1e-3, atol=0)
+        if dg:
+            wt_d, wt_d_ref = pk, pk_ref
+        else:
+            wt_f, wt_f_ref = pk, pk_ref
+    y, y_ref = torch.empty(M, cout, device=DEV), torch.empty(M, cout)
+    ops.conv_tile_fwd(desc, cu(x0), cu(x1), wt_f, cu(bias), y)
+    ref.conv_tile_fwd(desc, x0, x1, wt_f_ref, bias, y_ref)
+    torch.testing.assert_close(y.cpu(), y_ref, **tol)
+    y2 = torch.empty(n, cout, d * h * w, device=DEV)
+    ops.conv_tile_fwd(desc, cu(x0), cu(x1), wt_f, cu(bias), y2, True)
+    torch.testing.assert_close(y2.cpu(), y_ref.view(n, -1, cout).permute(0, 2, 1), **tol)
+    if cout % 4 == 0:
+        dx0 = torch.full((M, c0), 3.0, device=DEV)
+        dx1 = torch.full((M, c1), 3.0, device=DEV) if c1 else None
+        ops.conv_tile_dgrad(desc, cu(dy), wt_d, dx0, dx1, False)
+        r0, r1 = torch.empty(M, c0), (torch.empty(M, c1) if c1 else None)
+        ref.conv_tile_dgrad(desc, dy, wt_d_ref, r0, r1)
+        torch.testing.assert_close(dx0.cpu(), r0, **tol)
+        if c1:
+            torch.testing.assert_close(dx1.cpu(), r1, **tol)
+        ops.conv_tile_dgrad(desc, cu(dy), wt_d, dx0, dx1, True)
+        torch.testing.assert_close(dx0.cpu(), 2 * r0, rtol=tol["rtol"], atol=2 * tol["atol"])
+    if ops.conv_tile_supported(desc, True):
+        ws = torch.empty(ops.conv_tile_wgrad_workspace_bytes(desc) // 4 + 4, device=DEV)
+        dw, db = torch.empty_like(cu(wgt)), torch.empty(cout, device=DEV)
+        ops.conv_tile_wgrad(desc, cu(x0), cu(x1), cu(dy), ws, dw, db)
+        dw_ref, db_ref = torch.empty_like(wgt), torch.empty(cout)
+        ref.conv_wgrad(desc, x0, x1, dy, None, dw_ref, db_ref)
+        torch.testing.assert_close(dw.cpu(), dw_ref, rtol=tol["rtol"], atol=tol["atol"] * max(float(dw_ref.abs().max()), 1.0))
+        torch.testing.assert_close(db.cpu(), db_ref, rtol=1e-4, atol=1e-4 * max(float(db_ref.abs().max()), 1.0))
