@@ -76,7 +76,7 @@ __device__ __forceinline__ int pix_to_halo(int p) {
 }
 
 // stage the halo tile of channels [c0, c0+16) into shared memory (cp.async, zero fill outside the image / Cin)
-template <int DIMS>
+template <int DIMS, int STRIDE = PSTR>
 __device__ __forceinline__ void load_halo(const TileP& p, float* sh, int n, int d0, int h0, int w0, int c0, int tid) {
     using S = TileShape<DIMS>;
     for (int s = tid; s < S::HPIX * 4; s += 256) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ void load_halo(const TileP& p, float* sh, int n, int 
             const size_t pix = (((size_t)n * p.D + id) * p.H + ih) * p.W + iw;
             src = ch < p.C0 ? p.src0 + pix * p.C0 + ch : p.src1 + pix * p.C1 + (ch - p.C0);
         }
-        cp_async16(sh + hp * PSTR + piece * 4, src, ok);
+        cp_async16(sh + hp * STRIDE + piece * 4, src, ok);
     }
 }
 
@@ -246,7 +246,8 @@ template <int DIMS, int BN>
 struct WgSmem {
     using S = TileShape<DIMS>;
     static constexpr int GSTR = BN + 8;                  // dy row stride: (BN + 8) % 32 in {8, 24} -> conflict-free B frags
-    static constexpr int HALO_F = S::HPIX * PSTR;
+    static constexpr int XSTR = 24;                      // x row stride: lanes (pixel t, channel g) -> bank 24 t + g, all distinct
+    static constexpr int HALO_F = S::HPIX * XSTR;
     static constexpr int G_F = S::PIX * GSTR;
     static constexpr int STAGE_F = HALO_F + G_F;
     static constexpr int CG = BN / 16, PG = 8 / CG;      // column groups, pixel groups
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
         const int n = q / p.tiles_d;
         const int d0 = td * S::TD, h0 = th * S::TH, w0 = tw * S::TW;
         float* st = smem + stage * SM::STAGE_F;
-        load_halo<DIMS>(p, st, n, d0, h0, w0, chunk * KC, tid);
+        load_halo<DIMS, SM::XSTR>(p, st, n, d0, h0, w0, chunk * KC, tid);
         float* sg = st + SM::HALO_F;
         for (int s = tid; s < S::PIX * (BN / 4); s += 256) {
             const int pt = s / (BN / 4), piece = s % (BN / 4);
@@ -333,12 +334,12 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
 #pragma unroll
             for (int tap = 0; tap < S::TAPS; ++tap) {
                 const int kh = tap / 3, kw = tap % 3;
-                const float* a = sh + (hoff + kh * S::HW + kw + t) * PSTR + g;
+                const float* a = sh + (hoff + kh * S::HW + kw + t) * SM::XSTR + g;
                 uint32_t au[4];
                 au[0] = __float_as_uint(a[0]);
                 au[1] = __float_as_uint(a[8]);
-                au[2] = __float_as_uint(a[4 * PSTR]);
-                au[3] = __float_as_uint(a[4 * PSTR + 8]);
+                au[2] = __float_as_uint(a[4 * SM::XSTR]);
+                au[3] = __float_as_uint(a[4 * SM::XSTR + 8]);
                 mma_tf32(acc[tap][0], au, bu[0]);
                 mma_tf32(acc[tap][1], au, bu[1]);
             }
@@ -464,7 +465,10 @@ static int launch_tile_fwd(const TileP& p, cudaStream_t st) {
         attr_done = true;
     }
     dim3 grid(p.N * p.tiles_d * p.tiles_h * p.tiles_w, (p.Cout + BN - 1) / BN);
-    kern<<<grid, 256, SM::BYTES, st>>>(p);
+    // a single (chunk, kd) step never touches the second pipeline stage: ask for half the shared memory so
+    // more CTAs are resident and hide each other's load latency
+    const bool one_step = DIMS == 2 && p.Cin <= KC;
+    kern<<<grid, 256, one_step ? SM::BYTES / 2 : SM::BYTES, st>>>(p);
     B200_CHECK_LAUNCH("conv_tile_fwd");
     return B200_OK;
 }

@@ -104,6 +104,8 @@ class UNetPlan:
             self.dec.append((l1, up, up_g, la, lb))
         self.head = ConvLayer(net.decoder.out_conv, out_nchw=True, name="out").plan(rt, B, 1, H, W, FT_CHNS[0], 0, need_grad)
         self.layers = [l for pair in self.enc for l in pair] + [l for d in self.dec for l in (d[0], d[3], d[4])] + [self.head]
+        for l in self.layers:                 # profiling tags: gradient-carrying (student) vs forward-only (teacher) plan
+            l.name = ("S." if need_grad else "T.") + l.name
         rt.alloc_scratch()
         self.in_flight = False
 
