@@ -186,9 +186,11 @@ def run_ours(args):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the single JSON line
     pg = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         pg = dist.group.WORLD
     torch.manual_seed(1337)                      # identical student/teacher init on every rank (reference seed)
     student, teacher = UNet(1, NCLS, seed=1337 + rank).cuda(), UNet(1, NCLS, seed=7331 + rank).cuda()
@@ -235,9 +237,10 @@ def run_ours(args):
     ms_e2e = timed(lambda i: tr.step(*host[i % 4], read_loss=True), args.steps)
 
     out = None
+    # every rank runs the eager profiling pass (its steps contain the gradient all-reduce); rank 0 reports
+    rows, by_name, total = profile_pass(tr, xd, yd)
     if rank == 0:
         pk = peaks()
-        rows, by_name, total = profile_pass(tr, xd, yd)
         layers = {l.name: l for l in tr.s_plan.layers + tr.t_plan.layers}
         # dominant kernel = the C-ABI entry point with the largest share of the step; its launches are summed:
         # achieved = (algorithmic bytes or flops over all its launches in one step) / (their summed device time)
@@ -288,11 +291,17 @@ def run_ours(args):
             sec = sum(ts) / len(ts)
             out["cpu_baseline"] = {"value": B / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "2 timed + 1 warm-up full bs24 256x256 Mean-Teacher steps (oracle port, torch CPU fp32)"}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        # a captured graph keeps NCCL work alive and destroy_process_group() then blocks (observed on this pool):
+        # drop the graph, drain the device, synchronise the ranks and leave without the communicator teardown
+        tr.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -304,6 +313,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if os.environ.get("B200_FAULT"):          # debugging aid: dump all Python stacks if the run is still alive after N s
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200_FAULT"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
