@@ -59,6 +59,11 @@ SIGNATURES = {
     "b200_conv_tile_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_tile_wgrad_workspace_bytes": (_L, [_D]),
     "b200_conv_tile_wgrad": (_I, [_D, _P, _P, _P, _P, _L, _P, _P, _I, _S]),
+    "b200_conv_umma_supported": (_I, [_D, _I]),
+    "b200_conv_umma_packed_floats": (_L, [_I, _I, _I, _I]),
+    "b200_conv_umma_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_conv_umma_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_umma_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_bn_workspace_bytes": (_L, [_L, _I]),
     "b200_bn_stats_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _L, _S]),
     "b200_bn_eval_state": (_I, [_I, _P, _P, _F, _P, _P, _P, _S]),
@@ -83,7 +88,7 @@ SIGNATURES = {
 }
 
 # entry points whose int return value is NOT a status code
-_NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported"}
+_NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

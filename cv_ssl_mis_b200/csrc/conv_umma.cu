@@ -1,0 +1,391 @@
+// 3x3 stride-1 "same" convolution (2D) on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) with the
+// accumulators in TMEM -- forward and data gradient (same kernel, flipped weights).
+//
+// Formulation.  The batch is treated as one tall zero-padded image of N*(H+2) rows x (W+2) columns.  A CTA owns
+// a tile of TH output rows x TW output columns; it stages the (TH+2) x (TW+2) halo of 16 input channels in shared
+// memory ONCE per channel chunk with cp.async (zero-fill at the borders = the convolution padding), laid out
+// k-chunk-major:   halo[kq = c/4][q = rr*(TW+2) + cc][4 floats]
+// so that 8 consecutive halo pixels x 16 bytes form one contiguous 128-byte UMMA "core matrix".  With the
+// no-swizzle K-major canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)) a tap (kh,kw) is then nothing but a
+// shift of the A descriptor's start address by (kh*(TW+2) + kw) pixels: 128 consecutive halo-linear positions are
+// the M = 128 rows of one MMA (the 2 halo columns per row produce junk rows that the epilogue skips).  No im2col,
+// no per-tap copies, no address arithmetic on the data path: 9 taps x 2 k-steps = 18 MMAs per 16 channels and
+// 128-pixel block, issued by one thread; tcgen05.commit arrives on an mbarrier when they retire, which both
+// frees the shared-memory stage and releases the epilogue.
+//
+// Epilogue: each warp reads its 32 TMEM lanes (= 32 pixels) with tcgen05.ld 32x32b.x16, adds the bias and writes
+// whole pixels (16 channels = 64 contiguous bytes per thread).
+#include "conv_common.cuh"
+#include "../../include/b200ssl.h"
+
+namespace {
+
+constexpr int UKC = 16;          // channels per chunk (two K = 8 TF32 MMAs per tap)
+
+struct UmmaP {
+    const float* src0;
+    const float* src1;
+    int C0, C1, Cin;
+    int N, H, W;
+    int TH, TW, HW;              // tile rows / cols, halo width (TW + 2)
+    int NPIXA;                   // halo pixel slots allocated per k-chunk plane (multiple of 8)
+    int tiles_w, tiles_r;
+    FastDiv fd_hw, fd_hp2;       // / HW, / (H + 2)
+    const float* wt;             // [chunk][tap][kq][CoutP][4], TF32-rounded
+    int Cout, CoutP;
+    const float* bias;
+    float* dst0;
+    float* dst1;
+    int D0, D1;
+    int out_nchw;
+    int accumulate;
+    int nstages;                 // 1 if the reduction is a single chunk, else 2
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    uint32_t spins = 0;
+    do {
+        if (++spins > (1u << 28)) __trap();      // a lost arrival must fail loudly, not hang the device
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B contiguous,
+// SBO = byte distance between 8-row groups, LBO = byte distance between the two 16-byte K chunks of one MMA
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+    return d;                                    // layout_type (bits 61-63) = 0: SWIZZLE_NONE
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, N from idesc, K = 8 (TF32)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+template <int BN>
+struct USmem {
+    static constexpr int W_BYTES = 9 * 4 * BN * 16;                     // [tap][kq][BN][16 B]
+    __host__ __device__ static int halo_bytes(int npixa) { return 4 * npixa * 16; }
+    __host__ __device__ static int stage_bytes(int npixa) { return halo_bytes(npixa) + W_BYTES; }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_umma_kernel(const UmmaP p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_smem;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;               // two 128-row blocks, BN fp32 columns each
+    using SM = USmem<BN>;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_w = blockIdx.x % p.tiles_w, tile_r = blockIdx.x / p.tiles_w;
+    const int w0 = tile_w * p.TW, R0 = tile_r * p.TH;
+    const int n0 = blockIdx.y * BN;
+    const int rows_total = p.N * (p.H + 2);
+    const int stage_bytes = SM::stage_bytes(p.NPIXA);
+    const int plane_a = p.NPIXA * 16;                                   // bytes between k-chunk planes of the halo
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // pixel slots past the real halo only feed junk accumulator rows; zero them once so no NaN patterns circulate
+    {
+        const int real = (p.TH + 2) * p.HW;
+        for (int s = tid; s < (p.NPIXA - real) * 4 * p.nstages; s += 256) {
+            const int st = s / ((p.NPIXA - real) * 4), r = s % ((p.NPIXA - real) * 4);
+            const int kq = r / (p.NPIXA - real), q = real + r % (p.NPIXA - real);
+            *reinterpret_cast<float4*>(smem + st * stage_bytes + kq * plane_a + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    const int nchunks = (p.Cin + UKC - 1) / UKC;
+    const int npix_real = (p.TH + 2) * p.HW;
+
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int stage = p.nstages == 2 ? (chunk & 1) : 0;
+        unsigned char* st = smem + stage * stage_bytes;
+        // the MMAs that read this stage two chunks ago must have retired before it is overwritten
+        if (chunk >= 2) mbar_wait(smem_u32(&bars[stage]), ((chunk >> 1) - 1) & 1);
+        // ---- halo of channels [16 chunk, 16 chunk + 16)
+        const uint32_t sh = smem_u32(st);
+        for (int s = tid; s < npix_real * 4; s += 256) {
+            const int kq = s & 3, q = s >> 2;
+            uint32_t rr, cc;
+            p.fd_hw.divmod((uint32_t)q, rr, cc);
+            const int P = R0 + (int)rr;
+            uint32_t n, hh;
+            p.fd_hp2.divmod((uint32_t)P, n, hh);
+            const int ih = (int)hh - 1, iw = w0 + (int)cc - 1, ch = chunk * UKC + kq * 4;
+            const bool ok = P < rows_total && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W && ch < p.Cin;
+            const float* src = p.src0;
+            if (ok) {
+                const size_t pix = ((size_t)n * p.H + ih) * p.W + iw;
+                src = ch < p.C0 ? p.src0 + pix * p.C0 + ch : p.src1 + pix * p.C1 + (ch - p.C0);
+            }
+            cp16(sh + kq * plane_a + q * 16, src, ok);
+        }
+        // ---- weights of this chunk: [tap][kq][BN][4]
+        const uint32_t sw = sh + SM::halo_bytes(p.NPIXA);
+        const float* wsrc = p.wt + (size_t)chunk * 9 * 4 * p.CoutP * 4;
+        for (int s = tid; s < 9 * 4 * BN; s += 256) {
+            const int nn = s % BN, tk = s / BN;                         // tk = tap * 4 + kq
+            const bool ok = n0 + nn < p.CoutP;
+            cp16(sw + (tk * BN + nn) * 16, wsrc + ((size_t)tk * p.CoutP + (ok ? n0 + nn : 0)) * 4, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap % 3;
+                    const uint32_t a0 = sh + (uint32_t)(b * 128 + kh * p.HW + kw) * 16;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t ad = umma_desc(a0 + 2 * ks * plane_a, plane_a, 128);
+                        const uint64_t bd = umma_desc(sw + (uint32_t)((tap * 4 + 2 * ks) * BN) * 16, BN * 16, 128);
+                        umma_tf32(tmem_base + b * BN, ad, bd, idesc, (chunk | tap | ks) != 0);
+                    }
+                }
+            }
+            umma_commit(smem_u32(&bars[stage]));
+        }
+    }
+
+    // ---- epilogue: wait for the last commit (MMAs retire in order), then TMEM -> registers -> global
+    {
+        const int last = nchunks - 1;
+        const int stage = p.nstages == 2 ? (last & 1) : 0;
+        mbar_wait(smem_u32(&bars[stage]), p.nstages == 2 ? ((last >> 1) & 1) : (last & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int b = warp >> 2, lslice = (warp & 3) * 32;
+        const int q = b * 128 + lslice + lane;
+        uint32_t rr, cc;
+        p.fd_hw.divmod((uint32_t)q, rr, cc);
+        const int P = R0 + (int)rr;
+        uint32_t n, hh;
+        p.fd_hp2.divmod((uint32_t)P, n, hh);
+        const int ow = w0 + (int)cc;
+        const bool valid = (int)rr < p.TH && (int)cc < p.TW && P < rows_total && (int)hh < p.H && ow < p.W;
+        const size_t S_img = (size_t)p.H * p.W;
+        const size_t sp = (size_t)hh * p.W + ow;
+        const size_t pix = (size_t)n * S_img + sp;
+#pragma unroll 1
+        for (int j = 0; j < BN / 16; ++j) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)lslice << 16) + (uint32_t)(b * BN + j * 16), r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int c0 = n0 + j * 16;
+            if (!valid || c0 >= p.Cout) continue;
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                v[e] = __uint_as_float(r[e]);
+                if (p.bias && c0 + e < p.Cout) v[e] += __ldg(p.bias + c0 + e);
+            }
+            if (p.out_nchw) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (c0 + e < p.Cout) {
+                        float* o = p.dst0 + ((size_t)n * p.Cout + c0 + e) * S_img + sp;
+                        *o = p.accumulate ? *o + v[e] : v[e];
+                    }
+            } else {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int c = c0 + e4 * 4;
+                    if (c >= p.Cout) break;
+                    // D0, D1, Cout are multiples of 4 on this path, so a quad never straddles the split
+                    float* o = c < p.D0 ? p.dst0 + pix * p.D0 + c : p.dst1 + pix * p.D1 + (c - p.D0);
+                    float4 val = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+                    if (p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(o);
+                        val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(o) = val;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// weights for the UMMA kernel: [chunk][tap][kq][CoutP][4], TF32-rounded, zero padded
+__global__ void pack_umma_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int dgrad, int O, int I,
+                                         int T, int rows, int cols, int colsP, int chunks) {
+    const long long total = (long long)chunks * T * 4 * colsP * 4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx & 3);
+        long long r = idx >> 2;
+        const int col = (int)(r % colsP); r /= colsP;
+        const int kq = (int)(r & 3); r >>= 2;
+        const int tap = (int)(r % T);
+        const int chunk = (int)(r / T);
+        const int row = chunk * UKC + kq * 4 + j;
+        float v = 0.f;
+        if (row < rows && col < cols) {
+            v = dgrad ? w[((size_t)row * I + col) * T + (T - 1 - tap)] : w[((size_t)col * I + row) * T + tap];
+            v = __uint_as_float(f2tf32(v));
+        }
+        out[idx] = v;
+    }
+}
+
+inline int round16(int v) { return (v + 15) / 16 * 16; }
+
+// choose the tile width that wastes the fewest of the 256 accumulator rows
+void choose_tile(int W, int& TW, int& TH) {
+    const int cand[6] = {W <= 62 ? W : 30, 14, 30, 32, 62, 64};
+    double best = -1;
+    for (int i = 0; i < 6; ++i) {
+        const int tw = cand[i] > W ? W : cand[i];
+        const int hw = tw + 2, th = 256 / hw;
+        if (th < 1) continue;
+        const int ntw = (W + tw - 1) / tw;
+        const double eff = (double)(th * tw) / 256.0 * (double)W / (double)(ntw * tw);
+        if (eff > best) { best = eff; TW = tw; TH = th; }
+    }
+}
+
+template <int BN>
+int launch_umma(const UmmaP& p, cudaStream_t st) {
+    using SM = USmem<BN>;
+    auto kern = conv_umma_kernel<BN>;
+    const int bytes = p.nstages * SM::stage_bytes(p.NPIXA);
+    static int attr_bytes = 0;
+    if (bytes > attr_bytes) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        attr_bytes = bytes;
+    }
+    dim3 grid(p.tiles_w * p.tiles_r, (p.Cout + BN - 1) / BN);
+    kern<<<grid, 256, bytes, st>>>(p);
+    B200_CHECK_LAUNCH("conv_umma");
+    return B200_OK;
+}
+
+int run_umma(UmmaP& p, cudaStream_t st) {
+    choose_tile(p.W, p.TW, p.TH);
+    p.HW = p.TW + 2;
+    p.NPIXA = (256 + 2 * p.HW + 2 + 7) / 8 * 8;
+    if (p.NPIXA < (p.TH + 2) * p.HW) p.NPIXA = ((p.TH + 2) * p.HW + 7) / 8 * 8;
+    p.tiles_w = (p.W + p.TW - 1) / p.TW;
+    p.tiles_r = (p.N * (p.H + 2) + p.TH - 1) / p.TH;
+    p.fd_hw.init(p.HW);
+    p.fd_hp2.init(p.H + 2);
+    p.nstages = p.Cin > UKC ? 2 : 1;
+    if (p.Cout <= 16) return launch_umma<16>(p, st);
+    if (p.Cout <= 32) return launch_umma<32>(p, st);
+    if (p.Cout <= 64) return launch_umma<64>(p, st);
+    return launch_umma<128>(p, st);
+}
+
+int umma_supported(const b200_conv_desc* d) {
+    return d && d->stride == 1 && d->kd == 1 && d->kh == 3 && d->kw == 3 && d->pd == 0 && d->ph == 1 && d->pw == 1 &&
+           (d->c0 & 3) == 0 && (d->c1 & 3) == 0 && d->id == 1;
+}
+
+}  // namespace
+
+B200_API int b200_conv_umma_supported(const b200_conv_desc* d, int for_dgrad) {
+    if (!umma_supported(d)) return 0;
+    if (for_dgrad) return (d->cout & 3) == 0;        // dy is the staged operand; dx channel counts are already multiples of 4
+    return d->cout <= 4 || (d->cout & 3) == 0;
+}
+
+B200_API long long b200_conv_umma_packed_floats(int dgrad, int O, int I, int T) {
+    const int rows = dgrad ? O : I, cols = dgrad ? I : O;
+    return (long long)((rows + UKC - 1) / UKC) * T * 4 * round16(cols) * 4;
+}
+
+B200_API int b200_conv_umma_pack_weights(const float* w, float* out, int dgrad, int O, int I, int T, cudaStream_t st) {
+    B200_REQUIRE(w && out && O > 0 && I > 0 && T > 0, "conv_umma_pack_weights: bad arguments");
+    const int rows = dgrad ? O : I, cols = dgrad ? I : O;
+    const int chunks = (rows + UKC - 1) / UKC, colsP = round16(cols);
+    const long long total = (long long)chunks * T * 4 * colsP * 4;
+    int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_umma_weights_kernel<<<blocks, 256, 0, st>>>(w, out, dgrad, O, I, T, rows, cols, colsP, chunks);
+    B200_CHECK_LAUNCH("conv_umma_pack_weights");
+    return B200_OK;
+}
+
+B200_API int b200_conv_umma_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt,
+                                const float* bias, float* dst, int out_nchw, cudaStream_t st) {
+    B200_REQUIRE(b200_conv_umma_supported(d, 0), "conv_umma_fwd: unsupported convolution (needs 2D 3x3 stride 1 pad 1, channels % 4 == 0)");
+    B200_REQUIRE(src0 && wt && dst && (d->c1 == 0 || src1), "conv_umma_fwd: null pointer");
+    B200_REQUIRE(out_nchw || (d->cout & 3) == 0, "conv_umma_fwd: channels-last output needs cout % 4 == 0");
+    UmmaP p;
+    memset(&p, 0, sizeof(p));
+    p.src0 = src0; p.src1 = src1; p.C0 = d->c0; p.C1 = d->c1; p.Cin = d->c0 + d->c1;
+    p.N = d->n; p.H = d->ih; p.W = d->iw;
+    p.wt = wt; p.Cout = d->cout; p.CoutP = round16(d->cout); p.bias = bias;
+    p.dst0 = dst; p.D0 = d->cout; p.D1 = 0; p.out_nchw = out_nchw;
+    return run_umma(p, st);
+}
+
+B200_API int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
+                                  int accumulate, cudaStream_t st) {
+    B200_REQUIRE(b200_conv_umma_supported(d, 1), "conv_umma_dgrad: unsupported convolution");
+    B200_REQUIRE(dy && wt_dgrad && dx0 && (d->c1 == 0 || dx1), "conv_umma_dgrad: null pointer");
+    UmmaP p;
+    memset(&p, 0, sizeof(p));
+    p.src0 = dy; p.C0 = d->cout; p.C1 = 0; p.Cin = d->cout;
+    p.N = d->n; p.H = d->ih; p.W = d->iw;
+    p.wt = wt_dgrad; p.Cout = d->c0 + d->c1; p.CoutP = round16(p.Cout);
+    p.dst0 = dx0; p.dst1 = dx1; p.D0 = d->c0; p.D1 = d->c1; p.accumulate = accumulate;
+    return run_umma(p, st);
+}

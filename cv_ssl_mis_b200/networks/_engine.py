@@ -7,6 +7,8 @@ networks together with the BatchNorm -> activation -> dropout that follows it, e
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -102,11 +104,16 @@ class ConvLayer:
         # production path for 3x3 / 3x3x3 stride-1 convs: shared-memory tile kernels (TF32); the generic implicit
         # GEMM serves everything else and the `exact` (3xTF32) validation mode
         is_conv = self.kind == "conv"
+        # 2D 3x3: tcgen05/TMEM kernel (B200_CONV=tile falls back to the mma.sync tile kernel for A/B comparisons)
+        want_umma = is_conv and not rt.exact and os.environ.get("B200_CONV", "umma") == "umma"
+        self.umma_fwd = want_umma and ops.conv_umma_supported(self.desc, False) and (self.out_nchw or self.cout % 4 == 0)
+        self.umma_dgrad = want_umma and ops.conv_umma_supported(self.desc, True)
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
         self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)
         fwd_mode = PACK_CONV_FWD if is_conv else PACK_DECONV_FWD
-        nfwd = ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T)
+        nfwd = (ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
+                ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
         self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
         self.wp_bwd = None
         if need_grad:
@@ -118,18 +125,23 @@ class ConvLayer:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            nbwd = ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T)
+            nbwd = (ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
+                    ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
         return self
 
     def pack(self, need_dgrad):
         O, I = self.cout, self.cin
-        if self.tile_fwd:
+        if self.umma_fwd:
+            ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
+        elif self.tile_fwd:
             ops.conv_tile_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         else:
             ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
         if need_dgrad and self.wp_bwd is not None:
-            if self.tile_dgrad:
+            if self.umma_dgrad:
+                ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
+            elif self.tile_dgrad:
                 ops.conv_tile_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             else:
                 ops.conv_pack_weights(self.conv.weight, self.wp_bwd, self.bwd_mode, O, I, self.T)
@@ -137,7 +149,9 @@ class ConvLayer:
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
         _lib.tag = self.name
-        if self.tile_fwd:
+        if self.umma_fwd:
+            ops.conv_umma_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
+        elif self.tile_fwd:
             ops.conv_tile_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
         elif self.kind == "conv":
             ops.conv_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw, rt.exact)
@@ -174,7 +188,9 @@ class ConvLayer:
             else:
                 ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
             if dx0 is not None:
-                if self.tile_dgrad:
+                if self.umma_dgrad:
+                    ops.conv_umma_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
+                elif self.tile_dgrad:
                     ops.conv_tile_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
                 elif self.stride == 1:
                     ops.conv_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx, rt.exact)

@@ -127,6 +127,27 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
               _pf(dw), _pf(db), int(accumulate), _st())
 
 
+# tcgen05 kernels (2D 3x3 stride-1 pad-1 forward / data gradient)
+def conv_umma_supported(d, for_dgrad=False) -> bool:
+    return bool(_lib.query("b200_conv_umma_supported", C.byref(d), int(for_dgrad)))
+
+
+def conv_umma_packed_floats(dgrad, O, I, T) -> int:
+    return int(_lib.query("b200_conv_umma_packed_floats", int(dgrad), O, I, T))
+
+
+def conv_umma_pack_weights(w, out, dgrad, O, I, T):
+    _lib.call("b200_conv_umma_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, T, _st())
+
+
+def conv_umma_fwd(d, src0, src1, wt, bias, dst, out_nchw=False):
+    _lib.call("b200_conv_umma_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())
+
+
+def conv_umma_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
+    _lib.call("b200_conv_umma_dgrad", C.byref(d), _pf(dy), _pf(wt_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
+
+
 # ------------------------------------------------------------------ norm / activation / dropout
 def bn_workspace_bytes(M, C_) -> int:
     return int(_lib.query("b200_bn_workspace_bytes", M, C_))

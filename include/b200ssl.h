@@ -92,6 +92,17 @@ long long b200_conv_tile_wgrad_workspace_bytes(const b200_conv_desc* d);
 int b200_conv_tile_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
                          long long workspace_bytes, float* dw, float* db, int accumulate, cudaStream_t stream);
 
+/* tcgen05 (5th-gen tensor core) variant of the 2D 3x3 stride-1 pad-1 forward / data-gradient: tcgen05.mma
+ * kind::tf32 over a shared-memory halo tile, accumulators in TMEM (csrc/conv_umma.cu).  Own weight packing
+ * ([16-channel chunk][tap][4-channel group][cout][4], TF32-rounded). */
+int b200_conv_umma_supported(const b200_conv_desc* d, int for_dgrad);
+long long b200_conv_umma_packed_floats(int dgrad, int O, int I, int T);
+int b200_conv_umma_pack_weights(const float* w, float* out, int dgrad, int O, int I, int T, cudaStream_t stream);
+int b200_conv_umma_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt, const float* bias,
+                       float* dst, int out_nchw, cudaStream_t stream);
+int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
+                         int accumulate, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ BatchNorm(train) + activation + dropout
  * nn.BatchNorm2d/3d + nn.LeakyReLU/ReLU + nn.Dropout/Dropout3d: code/networks/unet.py:38-43 ; code/networks/vnet.py:16-25,177
  * state = [mean | invstd | scale | shift] (4*C floats).  drop_mode: 0 none, 1 per element, 2 per (sample, channel).

@@ -236,6 +236,40 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
     conv_wgrad(d, src0, src1, dy, ws, dw, db, accumulate)
 
 
+# ------------------------------------------------------------------ tcgen05 kernels (own weight packing)
+def conv_umma_supported(d, for_dgrad=False):
+    ok = (d.stride == 1 and d.kd == 1 and d.kh == 3 and d.kw == 3 and d.pd == 0 and d.ph == 1 and d.pw == 1 and
+          d.id == 1 and d.c0 % 4 == 0 and d.c1 % 4 == 0)
+    return bool(ok and (d.cout % 4 == 0 if for_dgrad else (d.cout <= 4 or d.cout % 4 == 0)))
+
+
+def conv_umma_packed_floats(dgrad, O, I, T):
+    rows, cols = (O, I) if dgrad else (I, O)
+    return ((rows + 15) // 16) * T * 4 * _r16(cols) * 4
+
+
+def conv_umma_pack_weights(w, out, dgrad, O, I, T):
+    tmp = torch.empty(conv_tile_packed_floats(dgrad, O, I, T))
+    conv_tile_pack_weights(w, tmp, dgrad, O, I, T)                    # [chunk][tap][colsP][16]
+    rows, cols = (O, I) if dgrad else (I, O)
+    chunks, colsP = (rows + 15) // 16, _r16(cols)
+    out.copy_(tmp.reshape(chunks, T, colsP, 4, 4).permute(0, 1, 3, 2, 4).reshape(-1))    # -> [chunk][tap][kq][colsP][4]
+
+
+def _umma_to_tile(wt, dgrad, O, I, T):
+    rows, cols = (O, I) if dgrad else (I, O)
+    chunks, colsP = (rows + 15) // 16, _r16(cols)
+    return wt.reshape(chunks, T, 4, colsP, 4).permute(0, 1, 3, 2, 4).reshape(-1)
+
+
+def conv_umma_fwd(d, src0, src1, wt, bias, dst, out_nchw=False):
+    conv_tile_fwd(d, src0, src1, _umma_to_tile(wt, False, d.cout, d.c0 + d.c1, 9), bias, dst, out_nchw)
+
+
+def conv_umma_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
+    conv_tile_dgrad(d, dy, _umma_to_tile(wt_dgrad, True, d.cout, d.c0 + d.c1, 9), dx0, dx1, accumulate)
+
+
 # ------------------------------------------------------------------ norm / act / dropout
 def bn_workspace_bytes(M, C):
     return 64

@@ -371,3 +371,60 @@ def test_conv_tile_kernels(case):
         ref.conv_wgrad(desc, x0, x1, dy, None, dw_ref, db_ref)
         torch.testing.assert_close(dw.cpu(), dw_ref, rtol=tol["rtol"], atol=tol["atol"] * max(float(dw_ref.abs().max()), 1.0))
         torch.testing.assert_close(db.cpu(), db_ref, rtol=1e-4, atol=1e-4 * max(float(db_ref.abs().max()), 1.0))
+
+
+UMMA_CASES = [
+    # n, h, w, c0, c1, cout
+    (2, 32, 32, 16, 0, 16),
+    (2, 20, 24, 16, 0, 32),           # ragged tile edges
+    (1, 16, 48, 16, 16, 16),          # virtual concat
+    (2, 16, 16, 64, 0, 64),
+    (1, 16, 16, 128, 128, 128),
+    (3, 16, 16, 256, 0, 256),         # column tiles (blockIdx.y), 16 chunks
+    (2, 32, 16, 16, 0, 4),            # head: cout = 4, NCHW output
+    (1, 8, 8, 32, 0, 48),
+    (1, 64, 256, 16, 0, 16),          # wide image: TW = 30 tiles
+    (2, 40, 72, 32, 0, 32),
+]
+
+
+@pytest.mark.parametrize("case", UMMA_CASES)
+def test_conv_umma_kernels(case):
+    """tcgen05.mma / TMEM convolution against the fp32 reference op."""
+    n, h, w, c0, c1, cout = case
+    g = torch.Generator().manual_seed(sum(case) * 3)
+    desc = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    assert ops.conv_umma_supported(desc)
+    T, cin, M = 9, c0 + c1, n * h * w
+    wgt = rnd(g, cout, cin, 3, 3, scale=(cin * T) ** -0.5)
+    bias, x0, dy = rnd(g, cout), rnd(g, M, c0), rnd(g, M, cout)
+    x1 = rnd(g, M, c1) if c1 else None
+    tol = TOL[False]
+    packs = {}
+    for dg in (False, True):
+        pk = torch.empty(ops.conv_umma_packed_floats(dg, cout, cin, T), device=DEV)
+        ops.conv_umma_pack_weights(cu(wgt), pk, dg, cout, cin, T)
+        pk_ref = torch.empty(ref.conv_umma_packed_floats(dg, cout, cin, T))
+        ref.conv_umma_pack_weights(wgt, pk_ref, dg, cout, cin, T)
+        torch.testing.assert_close(pk.cpu(), pk_ref, rtol=1e-3, atol=0)
+        packs[dg] = (pk, pk_ref)
+    y_ref = torch.empty(M, cout)
+    ref.conv_umma_fwd(desc, x0, x1, packs[False][1], bias, y_ref)
+    if cout % 4 == 0:
+        y = torch.full((M, cout), 5.0, device=DEV)
+        ops.conv_umma_fwd(desc, cu(x0), cu(x1), packs[False][0], cu(bias), y)
+        torch.testing.assert_close(y.cpu(), y_ref, **tol)
+    y2 = torch.empty(n, cout, h * w, device=DEV)
+    ops.conv_umma_fwd(desc, cu(x0), cu(x1), packs[False][0], cu(bias), y2, True)
+    torch.testing.assert_close(y2.cpu(), y_ref.view(n, -1, cout).permute(0, 2, 1), **tol)
+    if ops.conv_umma_supported(desc, True):
+        dx0 = torch.full((M, c0), 3.0, device=DEV)
+        dx1 = torch.full((M, c1), 3.0, device=DEV) if c1 else None
+        ops.conv_umma_dgrad(desc, cu(dy), packs[True][0], dx0, dx1, False)
+        r0, r1 = torch.empty(M, c0), (torch.empty(M, c1) if c1 else None)
+        ref.conv_umma_dgrad(desc, dy, packs[True][1], r0, r1)
+        torch.testing.assert_close(dx0.cpu(), r0, **tol)
+        if c1:
+            torch.testing.assert_close(dx1.cpu(), r1, **tol)
+        ops.conv_umma_dgrad(desc, cu(dy), packs[True][0], dx0, dx1, True)
+        torch.testing.assert_close(dx0.cpu(), 2 * r0, rtol=tol["rtol"], atol=2 * tol["atol"])
