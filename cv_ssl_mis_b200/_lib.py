@@ -64,6 +64,8 @@ SIGNATURES = {
     "b200_conv_umma_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
     "b200_conv_umma_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_umma2_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_umma2_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_bn_workspace_bytes": (_L, [_L, _I]),
     "b200_bn_stats_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _L, _S]),
     "b200_bn_eval_state": (_I, [_I, _P, _P, _F, _P, _P, _P, _S]),
