@@ -391,20 +391,25 @@ B200_API int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, cons
 }
 
 // =====================================================================================================
-// v2: the same convolution, TMA-fed and warp-specialised.
-//   warp 0 (one lane)  producer: per 16-channel chunk, four 4D TMA tiled loads (one per 4-channel group; box =
-//                      4 ch x (TW+2) x (TH+2) x 1 image, out-of-bounds = zero fill = the conv padding) + bulk copies
-//                      of the packed weights, all completing on the stage's "full" mbarrier (expect_tx)
-//   warp 1 (one lane)  MMA issuer: waits "full", issues MB x 9 taps x 2 tcgen05.mma, tcgen05.commit -> "empty"
-//   warps 2-5          epilogue: wait for the accumulator barrier, tcgen05.ld, bias, vector stores
-// Loads run up to `nstages` chunks ahead of the tensor core; nothing on the data path is executed by SIMT lanes.
+// v2: the same convolution, persistent and warp-specialised.
+//   warps 0-3  producers: per 16-channel chunk the halo arrives with coalesced 16-byte cp.async (four lanes cover the
+//              64 bytes of one pixel and scatter them into the four 4-channel planes the UMMA descriptor wants;
+//              zero-fill = conv padding); cp.async.mbarrier.arrive.noinc signals the stage's "full" barrier when a
+//              thread's copies have landed.  One lane adds the packed weights with cp.async.bulk (expect_tx).
+//              (A 4D TMA tiled load of the same box was measured first: its inner extent is only 16 bytes, which
+//              costs ~4 cycles per 16-byte row -- 2.5 us per tile -- so the LSU path is used for the halo.)
+//   warp 4     MMA issuer (one lane): waits "full", issues MB x 9 taps x 2 tcgen05.mma, tcgen05.commit -> "empty";
+//              also owns the TMEM allocation (two accumulator buffers)
+//   warps 5-8  epilogue: wait for the accumulator barrier, tcgen05.ld, bias, vector stores, release the buffer
+// Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the shared-memory ring (up to 8 stages) and the
+// two TMEM buffers run continuously across tiles, so the loads of the next tiles are in flight while the tensor
+// core works and the epilogue drains the previous accumulator.
 // =====================================================================================================
-#include <cuda.h>
-
 namespace {
 
-struct alignas(64) Umma2P {
-    CUtensorMap map0, map1;      // source 0 / source 1 (virtual concat), dims (C, W, H, N)
+struct Umma2P {
+    const float* src0;
+    const float* src1;
     int C0, C1, Cin;
     int N, H, W;
     int TH, TW, HW, MB;          // tile rows / cols, halo width, 128-row accumulator blocks per tile
@@ -425,48 +430,52 @@ struct alignas(64) Umma2P {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n) : "memory");
-}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cpasync_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
+constexpr int PRODUCER_THREADS = 128;
+constexpr int U2_THREADS = 288;          // 4 producer warps + 1 MMA warp + 4 epilogue warps
 
 template <int BN>
-__global__ void __launch_bounds__(192) conv_umma2_kernel(const __grid_constant__ Umma2P p) {
+__global__ void __launch_bounds__(U2_THREADS) conv_umma2_kernel(const Umma2P p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int tile = blockIdx.x;
-    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-    const int th = tile % p.tiles_h;
-    const int n = tile / p.tiles_h;
-    const int w0 = tw * p.TW, h0 = th * p.TH;
     const int n0 = blockIdx.y * BN;
     const int plane_a = p.NPIXA * 16;
     const int halo_bytes = 4 * plane_a;
     const int stage_bytes = halo_bytes + 36 * BN * 16;
     const int nchunks = (p.Cin + UKC - 1) / UKC;
     const int S = p.nstages;
+    const int tiles_img = p.tiles_h * p.tiles_w;
+    const int ntiles = p.N * tiles_img;
+    const int acc_cols = p.MB * BN;                       // columns of one accumulator buffer
     int tmem_cols = 32;
-    while (tmem_cols < p.MB * BN) tmem_cols <<= 1;
+    while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), PRODUCER_THREADS + 1);   // 128 cp.async arrivals + the weight expect_tx
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&acc_bar), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&acc_full[a]), 1);
+            mbar_init(smem_u32(&acc_empty[a]), 4);        // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -477,162 +486,166 @@ __global__ void __launch_bounds__(192) conv_umma2_kernel(const __grid_constant__
     const uint32_t tmem_base = tmem_base_smem;
     const uint32_t smem0 = smem_u32(smem);
 
-    if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t box_bytes = 16u * (uint32_t)p.HW * (uint32_t)(p.TH + 2);
-            const uint32_t tx = 4u * box_bytes + 36u * BN * 16u;
-            for (int chunk = 0; chunk < nchunks; ++chunk) {
-                const int s = chunk % S;
-                if (chunk >= S) mbar_wait(smem_u32(&empty_bar[s]), ((chunk / S) - 1) & 1);
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers
+        const int npix_real = (p.TH + 2) * p.HW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int n = tile / tiles_img, r = tile % tiles_img;
+            const int h0 = (r / p.tiles_w) * p.TH, w0 = (r % p.tiles_w) * p.TW;
+            for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(smem_u32(&empty_bar[s]), ((it / S) - 1) & 1);
                 const uint32_t fb = smem_u32(&full_bar[s]);
-                mbar_expect_tx(fb, tx);
                 const uint32_t st = smem0 + s * stage_bytes;
-                const int ch = chunk * UKC;
-                const CUtensorMap* map = ch < p.C0 ? &p.map0 : &p.map1;
-                const int cb = ch < p.C0 ? ch : ch - p.C0;
-#pragma unroll
-                for (int kq = 0; kq < 4; ++kq) tma_load_4d(st + kq * plane_a, map, fb, cb + kq * 4, w0 - 1, h0 - 1, n);
-                const uint32_t sw = st + halo_bytes;
-                const float* wsrc = p.wt + (size_t)chunk * 36 * p.CoutP * 4;
-                if (BN == p.CoutP) {
-                    bulk_load(sw, wsrc, 36u * BN * 16u, fb);
-                } else {
-                    for (int tk = 0; tk < 36; ++tk) bulk_load(sw + tk * BN * 16, wsrc + ((size_t)tk * p.CoutP + n0) * 4, BN * 16u, fb);
+                if (tid == 0) {
+                    const float* wsrc = p.wt + (size_t)chunk * 36 * p.CoutP * 4;
+                    mbar_expect_tx(fb, 36u * BN * 16u);
+                    if (BN == p.CoutP) {
+                        bulk_load(st + halo_bytes, wsrc, 36u * BN * 16u, fb);
+                    } else {
+                        for (int tk = 0; tk < 36; ++tk)
+                            bulk_load(st + halo_bytes + tk * BN * 16, wsrc + ((size_t)tk * p.CoutP + n0) * 4, BN * 16u, fb);
+                    }
                 }
+                for (int sl = tid; sl < npix_real * 4; sl += PRODUCER_THREADS) {
+                    const int kq = sl & 3, q = sl >> 2;
+                    uint32_t rr, cc;
+                    p.fd_hw.divmod((uint32_t)q, rr, cc);
+                    const int ih = h0 + (int)rr - 1, iw = w0 + (int)cc - 1, ch = chunk * UKC + kq * 4;
+                    const bool ok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W && ch < p.Cin;
+                    const float* src = p.src0;
+                    if (ok) {
+                        const size_t pix = ((size_t)n * p.H + ih) * p.W + iw;
+                        src = ch < p.C0 ? p.src0 + pix * p.C0 + ch : p.src1 + pix * p.C1 + (ch - p.C0);
+                    }
+                    cp16(st + kq * plane_a + q * 16, src, ok);
+                }
+                cpasync_arrive_noinc(fb);                  // arrives once this thread's copies have landed
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-            for (int chunk = 0; chunk < nchunks; ++chunk) {
-                const int s = chunk % S;
-                mbar_wait(smem_u32(&full_bar[s]), (chunk / S) & 1);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+                const int as = tl & 1;
+                // the epilogue must have drained this accumulator buffer (used two tiles ago)
+                if (tl >= 2) mbar_wait(smem_u32(&acc_empty[as]), ((tl >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sh = smem0 + s * stage_bytes, sw = sh + halo_bytes;
+                const uint32_t dcol = tmem_base + as * acc_cols;
+                for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
+                    const int s = it % S;
+                    mbar_wait(smem_u32(&full_bar[s]), (it / S) & 1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) data -> tensor core
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sh = smem0 + s * stage_bytes, sw = sh + halo_bytes;
 #pragma unroll 1
-                for (int b = 0; b < p.MB; ++b) {
+                    for (int b = 0; b < p.MB; ++b) {
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap % 3;
-                        const uint32_t a0 = sh + (uint32_t)(b * 128 + kh * p.HW + kw) * 16;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int kh = tap / 3, kw = tap % 3;
+                            const uint32_t a0 = sh + (uint32_t)(b * 128 + kh * p.HW + kw) * 16;
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t ad = umma_desc(a0 + 2 * ks * plane_a, plane_a, 128);
-                            const uint64_t bd = umma_desc(sw + (uint32_t)((tap * 4 + 2 * ks) * BN) * 16, BN * 16, 128);
-                            umma_tf32(tmem_base + b * BN, ad, bd, idesc, (chunk | tap | ks) != 0);
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t ad = umma_desc(a0 + 2 * ks * plane_a, plane_a, 128);
+                                const uint64_t bd = umma_desc(sw + (uint32_t)((tap * 4 + 2 * ks) * BN) * 16, BN * 16, 128);
+                                umma_tf32(dcol + b * BN, ad, bd, idesc, (chunk | tap | ks) != 0);
+                            }
                         }
                     }
+                    umma_commit(smem_u32(&empty_bar[s]));     // frees the stage when these MMAs retire
                 }
-                umma_commit(smem_u32(&empty_bar[s]));        // frees the stage when these MMAs retire
+                umma_commit(smem_u32(&acc_full[as]));          // accumulator of this tile complete
             }
-            umma_commit(smem_u32(&acc_bar));                  // accumulators complete
         }
     } else {
-        mbar_wait(smem_u32(&acc_bar), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int lslice = (warp & 3) * 32;                   // TMEM lanes this warp may read
+        // ------------------------------------------------------------------ epilogue
+        const int lslice = (warp & 3) * 32;                    // TMEM lanes this warp may read
         const size_t S_img = (size_t)p.H * p.W;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+            const int as = tl & 1;
+            const int n = tile / tiles_img, r = tile % tiles_img;
+            const int h0 = (r / p.tiles_w) * p.TH, w0 = (r % p.tiles_w) * p.TW;
+            mbar_wait(smem_u32(&acc_full[as]), (tl >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int b = 0; b < p.MB; ++b) {
-            const int q = b * 128 + lslice + lane;
-            uint32_t rr, cc;
-            p.fd_hw.divmod((uint32_t)q, rr, cc);
-            const int oh = h0 + (int)rr, ow = w0 + (int)cc;
-            const bool valid = (int)rr < p.TH && (int)cc < p.TW && oh < p.H && ow < p.W;
-            const size_t sp = (size_t)oh * p.W + ow;
-            const size_t pix = (size_t)n * S_img + sp;
+            for (int b = 0; b < p.MB; ++b) {
+                const int q = b * 128 + lslice + lane;
+                uint32_t rr, cc;
+                p.fd_hw.divmod((uint32_t)q, rr, cc);
+                const int oh = h0 + (int)rr, ow = w0 + (int)cc;
+                const bool valid = (int)rr < p.TH && (int)cc < p.TW && oh < p.H && ow < p.W;
+                const size_t sp = (size_t)oh * p.W + ow;
+                const size_t pix = (size_t)n * S_img + sp;
 #pragma unroll 1
-            for (int j = 0; j < BN / 16; ++j) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)lslice << 16) + (uint32_t)(b * BN + j * 16), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int c0 = n0 + j * 16;
-                if (!valid || c0 >= p.Cout) continue;
-                float v[16];
+                for (int j = 0; j < BN / 16; ++j) {
+                    uint32_t rg[16];
+                    tmem_ld16(tmem_base + ((uint32_t)lslice << 16) + (uint32_t)(as * acc_cols + b * BN + j * 16), rg);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int c0 = n0 + j * 16;
+                    if (!valid || c0 >= p.Cout) continue;
+                    float v[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    v[e] = __uint_as_float(r[e]);
-                    if (p.bias && c0 + e < p.Cout) v[e] += __ldg(p.bias + c0 + e);
-                }
-                if (p.out_nchw) {
+                    for (int e = 0; e < 16; ++e) {
+                        v[e] = __uint_as_float(rg[e]);
+                        if (p.bias && c0 + e < p.Cout) v[e] += __ldg(p.bias + c0 + e);
+                    }
+                    if (p.out_nchw) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (c0 + e < p.Cout) {
-                            float* o = p.dst0 + ((size_t)n * p.Cout + c0 + e) * S_img + sp;
-                            *o = p.accumulate ? *o + v[e] : v[e];
+                        for (int e = 0; e < 16; ++e)
+                            if (c0 + e < p.Cout) {
+                                float* o = p.dst0 + ((size_t)n * p.Cout + c0 + e) * S_img + sp;
+                                *o = p.accumulate ? *o + v[e] : v[e];
+                            }
+                    } else {
+#pragma unroll
+                        for (int e4 = 0; e4 < 4; ++e4) {
+                            const int c = c0 + e4 * 4;
+                            if (c >= p.Cout) break;
+                            float* o = c < p.D0 ? p.dst0 + pix * p.D0 + c : p.dst1 + pix * p.D1 + (c - p.D0);
+                            float4 val = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(o);
+                                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(o) = val;
                         }
-                } else {
-#pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        const int c = c0 + e4 * 4;
-                        if (c >= p.Cout) break;
-                        float* o = c < p.D0 ? p.dst0 + pix * p.D0 + c : p.dst1 + pix * p.D1 + (c - p.D0);
-                        float4 val = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-                        if (p.accumulate) {
-                            const float4 old = *reinterpret_cast<const float4*>(o);
-                            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-                        }
-                        *reinterpret_cast<float4*>(o) = val;
                     }
                 }
             }
+            // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// channels-last activation tensor [N][H][W][C] as a 4D TMA map with box (4 channels, HW, BH, 1)
-int make_act_map(CUtensorMap* map, const float* base, int N, int H, int W, int C, int HW, int BH) {
-    EncodeTiledFn enc = get_encode_tiled();
-    if (!enc) { b200_set_error("conv_umma: cuTensorMapEncodeTiled is unavailable"); return B200_ERR_CUDA; }
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {4, (cuuint32_t)HW, (cuuint32_t)BH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { b200_set_error("conv_umma: cuTensorMapEncodeTiled failed (%d)", (int)r); return B200_ERR_CUDA; }
-    return B200_OK;
-}
-
 // tile geometry: maximise the fraction of accumulator rows that are real outputs, prefer more rows per tile
-void choose_tile2(int H, int W, int BN, int nchunks, int& TW, int& TH, int& MB, int& S, int& NPIXA) {
+void choose_tile2(int H, int W, int BN, int& TW, int& TH, int& MB, int& S, int& NPIXA) {
     const int cand[7] = {W, 14, 30, 32, 62, 64, 126};
     double best = -1;
     for (int mb = 1; mb <= 4; ++mb) {
-        if (mb * BN > 512) break;
+        if (2 * mb * BN > 512) break;                      // two TMEM accumulator buffers
         for (int i = 0; i < 7; ++i) {
             const int tw = cand[i] > W ? W : cand[i];
             const int hw = tw + 2;
-            if (hw > 256) continue;
             int th = (mb * 128) / hw;
             if (th < 1) continue;
             if (th > H) th = H;
-            if (th + 2 > 256) th = 254;
             const int npixa = (mb * 128 + 2 * hw + 2 + 7) / 8 * 8;
             const int stage = 4 * npixa * 16 + 36 * BN * 16;
-            int s = nchunks < 3 ? nchunks : 3;
-            while (s > 1 && s * stage > 200 * 1024) --s;
-            if (s * stage > 200 * 1024 || (nchunks > 1 && s < 2)) continue;
+            int s = (200 * 1024) / stage;                     // persistent CTA: use the shared memory for a deep ring
+            if (s > MAX_STAGES) s = MAX_STAGES;
+            if (s < 2) continue;
             const double cover = (double)H * W / ((double)((H + th - 1) / th) * ((W + tw - 1) / tw) * mb * 128);
             const double score = cover + 0.01 * mb;             // tie-break: bigger tiles reuse the weights more
             if (score > best) { best = score; TW = tw; TH = th; MB = mb; S = s; NPIXA = npixa; }
@@ -649,57 +662,46 @@ int launch_umma2(const Umma2P& p, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         attr_bytes = bytes;
     }
-    dim3 grid(p.N * p.tiles_h * p.tiles_w, (p.Cout + BN - 1) / BN);
-    kern<<<grid, 192, bytes, st>>>(p);
+    const int coltiles = (p.Cout + BN - 1) / BN;
+    const int ntiles = p.N * p.tiles_h * p.tiles_w;
+    int gx = b200_num_sms() / coltiles;                       // one persistent CTA per SM in total
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    dim3 grid(gx, coltiles);
+    kern<<<grid, U2_THREADS, bytes, st>>>(p);
     B200_CHECK_LAUNCH("conv_umma2");
     return B200_OK;
 }
 
-int run_umma2(Umma2P& p, const float* src0, const float* src1, cudaStream_t st) {
+int run_umma2(Umma2P& p, cudaStream_t st) {
     const int BN = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : 128));
-    const int nchunks = (p.Cin + UKC - 1) / UKC;
     p.TW = 0;
-    choose_tile2(p.H, p.W, BN, nchunks, p.TW, p.TH, p.MB, p.nstages, p.NPIXA);
+    choose_tile2(p.H, p.W, BN, p.TW, p.TH, p.MB, p.nstages, p.NPIXA);
     if (p.TW == 0) { b200_set_error("conv_umma: no tile geometry fits"); return B200_ERR_ARG; }
     p.HW = p.TW + 2;
     p.tiles_w = (p.W + p.TW - 1) / p.TW;
     p.tiles_h = (p.H + p.TH - 1) / p.TH;
     p.fd_hw.init(p.HW);
-    if (int rc = make_act_map(&p.map0, src0, p.N, p.H, p.W, p.C0, p.HW, p.TH + 2)) return rc;
-    if (p.C1 > 0) {
-        if (int rc = make_act_map(&p.map1, src1, p.N, p.H, p.W, p.C1, p.HW, p.TH + 2)) return rc;
-    } else {
-        p.map1 = p.map0;
-    }
     if (BN == 16) return launch_umma2<16>(p, st);
     if (BN == 32) return launch_umma2<32>(p, st);
     if (BN == 64) return launch_umma2<64>(p, st);
     return launch_umma2<128>(p, st);
 }
 
-bool use_v1() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B200_UMMA_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 }  // namespace
 
-// v2 entry points (TMA + warp specialisation).  When a two-source input is given, the first source's channel
-// count must be a multiple of 16 so a chunk never straddles the two tensor maps.
 B200_API int b200_conv_umma2_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt,
                                  const float* bias, float* dst, int out_nchw, cudaStream_t st) {
     B200_REQUIRE(b200_conv_umma_supported(d, 0), "conv_umma2_fwd: unsupported convolution");
     B200_REQUIRE(src0 && wt && dst && (d->c1 == 0 || src1), "conv_umma2_fwd: null pointer");
     B200_REQUIRE(out_nchw || (d->cout & 3) == 0, "conv_umma2_fwd: channels-last output needs cout % 4 == 0");
-    B200_REQUIRE(d->c1 == 0 || (d->c0 & 15) == 0, "conv_umma2_fwd: concat needs c0 % 16 == 0");
     Umma2P p;
     memset(&p, 0, sizeof(p));
-    p.C0 = d->c0; p.C1 = d->c1; p.Cin = d->c0 + d->c1;
+    p.src0 = src0; p.src1 = src1; p.C0 = d->c0; p.C1 = d->c1; p.Cin = d->c0 + d->c1;
     p.N = d->n; p.H = d->ih; p.W = d->iw;
     p.wt = wt; p.Cout = d->cout; p.CoutP = round16(d->cout); p.bias = bias;
     p.dst0 = dst; p.D0 = d->cout; p.D1 = 0; p.out_nchw = out_nchw;
-    return run_umma2(p, src0, src1, st);
+    return run_umma2(p, st);
 }
 
 B200_API int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
@@ -708,9 +710,9 @@ B200_API int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, con
     B200_REQUIRE(dy && wt_dgrad && dx0 && (d->c1 == 0 || dx1), "conv_umma2_dgrad: null pointer");
     Umma2P p;
     memset(&p, 0, sizeof(p));
-    p.C0 = d->cout; p.C1 = 0; p.Cin = d->cout;
+    p.src0 = dy; p.C0 = d->cout; p.C1 = 0; p.Cin = d->cout;
     p.N = d->n; p.H = d->ih; p.W = d->iw;
     p.wt = wt_dgrad; p.Cout = d->c0 + d->c1; p.CoutP = round16(p.Cout);
     p.dst0 = dx0; p.dst1 = dx1; p.D0 = d->c0; p.D1 = d->c1; p.accumulate = accumulate;
-    return run_umma2(p, dy, nullptr, st);
+    return run_umma2(p, st);
 }

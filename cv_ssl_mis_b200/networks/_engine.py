@@ -106,8 +106,12 @@ class ConvLayer:
         is_conv = self.kind == "conv"
         # 2D 3x3: tcgen05/TMEM kernel (B200_CONV=tile falls back to the mma.sync tile kernel for A/B comparisons)
         want_umma = is_conv and not rt.exact and os.environ.get("B200_CONV", "umma") == "umma"
-        self.umma_fwd = want_umma and ops.conv_umma_supported(self.desc, False) and (self.out_nchw or self.cout % 4 == 0)
-        self.umma_dgrad = want_umma and ops.conv_umma_supported(self.desc, True)
+        # measured (tools/bench_conv.py): with fp32 operands the UMMA is bound by its shared-memory operand reads,
+        # 4(M+N)/(MN) bytes per MAC, so it only beats mma.sync when both channel counts are >= 32
+        wide = self.cout >= 32 and self.cin >= 32
+        self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False)
+                         and (self.out_nchw or self.cout % 4 == 0))
+        self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True)
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
         self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)

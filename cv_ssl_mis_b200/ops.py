@@ -144,7 +144,7 @@ UMMA_V2 = True        # TMA-fed warp-specialised kernel (False: the simpler cp.a
 
 
 def conv_umma_fwd(d, src0, src1, wt, bias, dst, out_nchw=False):
-    if UMMA_V2 and (d.c1 == 0 or d.c0 % 16 == 0):
+    if UMMA_V2:
         _lib.call("b200_conv_umma2_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())
         return
     _lib.call("b200_conv_umma_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())

@@ -102,8 +102,8 @@ int b200_conv_umma_fwd(const b200_conv_desc* d, const float* src0, const float* 
                        float* dst, int out_nchw, cudaStream_t stream);
 int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
                          int accumulate, cudaStream_t stream);
-/* same operation and weight packing, TMA-fed and warp-specialised (producer / MMA issuer / epilogue warps, multi-stage
- * mbarrier pipeline); a two-source input needs c0 % 16 == 0 */
+/* same operation and weight packing, persistent and warp-specialised: cp.async producer warps + cp.async.bulk weights ->
+ * multi-stage mbarrier ring -> one MMA-issuing lane -> double-buffered TMEM accumulators -> epilogue warps */
 int b200_conv_umma2_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt, const float* bias,
                         float* dst, int out_nchw, cudaStream_t stream);
 int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
