@@ -82,8 +82,9 @@ SIGNATURES = {
     "b200_colsum": (_I, [_P, _L, _I, _P, _I, _P, _L, _S]),
     "b200_add": (_I, [_P, _P, _P, _L, _S]),
     "b200_ssl_loss_workspace_bytes": (_L, [_I, _L]),
-    "b200_ssl_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
-    "b200_ssl_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _I, _S]),
+    "b200_ssl_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P, _P, _L, _S]),
+    "b200_ssl_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P, _F, _P, _I, _S]),
+    "b200_mc_softmax_accumulate": (_I, [_P, _P, _I, _I, _I, _L, _I, _I, _S]),
     "b200_sgd_ema_step": (_I, [_P, _P, _P, _P, _L, _P, _I, _S]),
     "b200_ema_update": (_I, [_P, _P, _L, _P, _S]),
     "b200_noise_add": (_I, [_P, _P, _L, _F, _F, _U64, _P, _U32, _S]),

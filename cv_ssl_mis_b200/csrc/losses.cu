@@ -20,7 +20,33 @@ struct LossGeom {
     int nhwc;
     int B, Lb, C;
     long long S;
+    // uncertainty-aware variant (code/train_uncertainty_aware_mean_teacher_3D.py:161-179): sum over T stochastic
+    // teacher passes of softmax probabilities, [U][C][S] in the logits' layout; null => plain mean-teacher MSE
+    const float* mc_psum;
+    float mc_T;
+    const float* mc_thr;    // DEVICE scalar: entropy threshold
 };
+
+// mask = [ -sum_c pbar_c log(pbar_c + 1e-6) < thr ],  pbar = psum / T
+template <int C>
+__device__ __forceinline__ bool mc_mask(const LossGeom& g, long long u, long long s) {
+    float ps[C];
+    if (g.nhwc) {
+        const float* p = g.mc_psum + (u * g.S + s) * g.C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ps[c] = c < g.C ? __ldg(p + c) : 0.f;
+    } else {
+        const float* p = g.mc_psum + u * g.C * g.S + s;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ps[c] = c < g.C ? __ldg(p + (long long)c * g.S) : 0.f;
+    }
+    const float invT = 1.f / g.mc_T;
+    float H = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if (c < g.C) { const float pb = ps[c] * invT; H -= pb * logf(pb + 1e-6f); }
+    return H < __ldg(g.mc_thr);
+}
 
 template <int C>
 __device__ __forceinline__ void load_logits(const float* base, int nhwc, long long n, long long s, long long S, int Crt,
@@ -55,8 +81,8 @@ __device__ __forceinline__ int load_label(const void* labels, int i64, long long
     return i64 ? (int)reinterpret_cast<const long long*>(labels)[idx] : (int)reinterpret_cast<const unsigned char*>(labels)[idx];
 }
 
-// accumulators per block: [0] ce, [1] mse, [2..2+C) I_c, [2+C..) Z_c, [2+2C..) Y_c
-#define SSL_NACC(C) (2 + 3 * (C))
+// accumulators per block: [0] ce, [1] mse, [2..2+C) I_c, [2+C..) Z_c, [2+2C..) Y_c, [2+3C] mask count
+#define SSL_NACC(C) (3 + 3 * (C))
 
 template <int C>
 __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, double* __restrict__ part) {
@@ -90,9 +116,13 @@ __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, dou
             load_logits<C>(g.teacher, g.nhwc, n - g.Lb, s, g.S, g.C, q);
             float lse2;
             softmax_inplace<C>(q, lse2);
+            const bool on = g.mc_psum == nullptr || mc_mask<C>(g, n - g.Lb, s);
+            if (on) {
+                acc[2 + 3 * C] += 1.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (c < g.C) { const float d = p[c] - q[c]; acc[1] += d * d; }
+                for (int c = 0; c < C; ++c) {
+                    if (c < g.C) { const float d = p[c] - q[c]; acc[1] += d * d; }
+                }
             }
         }
     }
@@ -111,9 +141,10 @@ __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, dou
     }
 }
 
-// out: [0] ce  [1] dice  [2] cons  [3] total  [4..4+C) A_c  [4+C..4+2C) B_c   (A/B = dice-gradient coefficients)
+// out: [0] ce  [1] dice  [2] cons  [3] total  [4..4+C) A_c  [4+C..4+2C) B_c  [4+2C] d(cons)/d(p) scale
+//      (A/B = dice-gradient coefficients)
 __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nblk, int Cpad, int C, int Lb, int U,
-                                         long long S, int has_teacher, const float* __restrict__ w_cons,
+                                         long long S, int has_teacher, int mc_mode, const float* __restrict__ w_cons,
                                          float* __restrict__ out) {
     __shared__ double tot[SSL_NACC(SSL_MAXC)];
     const int NA = SSL_NACC(Cpad);
@@ -142,8 +173,16 @@ __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nb
         } else {
             for (int c = 0; c < C; ++c) { out[4 + c] = 0.f; out[4 + C + c] = 0.f; }
         }
-        if (has_teacher && U > 0) cons = (float)(tot[1] / ((double)U * (double)C * (double)S));
         const float w = w_cons ? w_cons[0] : 0.f;
+        float dscale = 0.f;
+        if (has_teacher && U > 0) {
+            // mean over all elements (MT) or sum(mask * dist) / (2 sum(mask) + 1e-16) (UAMT: the reference divides by
+            // 2 * sum(mask) whatever the class count)
+            const double denom = mc_mode ? 2.0 * tot[2 + 3 * Cpad] + 1e-16 : (double)U * (double)C * (double)S;
+            cons = (float)(tot[1] / denom);
+            dscale = (float)(2.0 * (double)w / denom);
+        }
+        out[4 + 2 * C] = dscale;
         out[0] = ce;
         out[1] = dice;
         out[2] = cons;
@@ -161,10 +200,8 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
         A[c] = c < g.C ? lossbuf[4 + c] : 0.f;
         Bc[c] = c < g.C ? lossbuf[4 + g.C + c] : 0.f;
     }
-    const int U = g.B - g.Lb;
-    const float w = (w_cons && g.teacher) ? w_cons[0] : 0.f;
     const float ce_scale = g.Lb > 0 ? 1.f / ((float)g.Lb * (float)g.S) : 0.f;
-    const float mse_scale = U > 0 ? 2.f * w / ((float)U * (float)g.C * (float)g.S) : 0.f;
+    const float mse_scale = g.teacher ? lossbuf[4 + 2 * g.C] : 0.f;
     const long long total = (long long)g.B * g.S;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long n = idx / g.S, s = idx - n * g.S;
@@ -183,7 +220,7 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
 #pragma unroll
             for (int c = 0; c < C; ++c)
                 dz[c] = 0.5f * gscale * (p[c] * (gd[c] - dot) + (p[c] - (c == t ? 1.f : 0.f)) * ce_scale);
-        } else if (g.teacher && mse_scale != 0.f) {
+        } else if (g.teacher && mse_scale != 0.f && (g.mc_psum == nullptr || mc_mask<C>(g, n - g.Lb, s))) {
             float q[C];
             load_logits<C>(g.teacher, g.nhwc, n - g.Lb, s, g.S, g.C, q);
             float lse2;
@@ -226,7 +263,8 @@ B200_API long long b200_ssl_loss_workspace_bytes(int B, long long S) {
 }
 
 static int fill_geom(LossGeom& g, const float* logits, const float* teacher, const void* labels, int label_dtype,
-                     int layout_nhwc, int B, int Lb, int C, long long S, const char* who) {
+                     int layout_nhwc, int B, int Lb, int C, long long S, const float* mc_psum, float mc_T,
+                     const float* mc_thr, const char* who) {
     B200_REQUIRE(logits != nullptr, "%s: null logits", who);
     B200_REQUIRE(B > 0 && Lb >= 0 && Lb <= B && S > 0, "%s: bad batch geometry (B=%d Lb=%d)", who, B, Lb);
     B200_REQUIRE(C >= 2 && C <= SSL_MAXC, "%s: classes must be in [2,%d]", who, SSL_MAXC);
@@ -235,14 +273,19 @@ static int fill_geom(LossGeom& g, const float* logits, const float* teacher, con
     g.logits = logits; g.teacher = teacher; g.labels = labels;
     g.label_i64 = label_dtype == B200_LABEL_I64;
     g.nhwc = layout_nhwc; g.B = B; g.Lb = Lb; g.C = C; g.S = S;
+    B200_REQUIRE(mc_psum == nullptr || (teacher != nullptr && mc_thr != nullptr && mc_T > 0.f),
+                 "%s: the uncertainty mask needs teacher logits, a threshold and T > 0", who);
+    g.mc_psum = mc_psum; g.mc_T = mc_T; g.mc_thr = mc_thr;
     return B200_OK;
 }
 
 B200_API int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
-                               int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, float* lossbuf,
-                               void* workspace, long long workspace_bytes, cudaStream_t st) {
+                               int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons,
+                               const float* mc_psum, float mc_T, const float* mc_thr, float* lossbuf, void* workspace,
+                               long long workspace_bytes, cudaStream_t st) {
     LossGeom g;
-    if (int rc = fill_geom(g, logits, teacher_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, "ssl_loss_fwd")) return rc;
+    if (int rc = fill_geom(g, logits, teacher_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, mc_psum, mc_T, mc_thr,
+                           "ssl_loss_fwd")) return rc;
     B200_REQUIRE(lossbuf && workspace, "ssl_loss_fwd: null output/workspace");
     B200_REQUIRE(workspace_bytes >= b200_ssl_loss_workspace_bytes(B, S), "ssl_loss_fwd: workspace too small");
     const int grid = loss_grid((long long)B * S);
@@ -252,16 +295,19 @@ B200_API int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits,
     else if (Cp == 4) ssl_loss_fwd_kernel<4><<<grid, 256, 0, st>>>(g, part);
     else ssl_loss_fwd_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(g, part);
     B200_CHECK_LAUNCH("ssl_loss_fwd");
-    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(part, grid, Cp, C, Lb, B - Lb, S, teacher_logits != nullptr, w_cons, lossbuf);
+    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(part, grid, Cp, C, Lb, B - Lb, S, teacher_logits != nullptr, mc_psum != nullptr,
+                                                 w_cons, lossbuf);
     B200_CHECK_LAUNCH("ssl_loss_finalize");
     return B200_OK;
 }
 
 B200_API int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
                                int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons,
-                               const float* lossbuf, float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
+                               const float* mc_psum, float mc_T, const float* mc_thr, const float* lossbuf,
+                               float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
     LossGeom g;
-    if (int rc = fill_geom(g, logits, teacher_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, "ssl_loss_bwd")) return rc;
+    if (int rc = fill_geom(g, logits, teacher_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, mc_psum, mc_T, mc_thr,
+                           "ssl_loss_bwd")) return rc;
     B200_REQUIRE(lossbuf && dlogits, "ssl_loss_bwd: null pointer");
     const int grid = loss_grid((long long)B * S);
     const int Cp = cpad_of(C);
@@ -269,5 +315,51 @@ B200_API int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits,
     else if (Cp == 4) ssl_loss_bwd_kernel<4><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc);
     else ssl_loss_bwd_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc);
     B200_CHECK_LAUNCH("ssl_loss_bwd");
+    return B200_OK;
+}
+
+// psum[u] (+)= sum_r softmax(logits[r*U + u])  -- the T stochastic teacher passes of UAMT
+// (code/train_uncertainty_aware_mean_teacher_3D.py:149-163: preds.reshape(T, stride, ...).mean(0), never materialised)
+template <int C>
+__global__ void __launch_bounds__(256) mc_softmax_acc_kernel(const float* __restrict__ logits, float* __restrict__ psum, int R,
+                                                             int U, int Crt, long long S, int nhwc, int init) {
+    const long long total = (long long)U * S;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long u = idx / S, s = idx - u * S;
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int r = 0; r < R; ++r) {
+            float p[C];
+            load_logits<C>(logits, nhwc, (long long)r * U + u, s, S, Crt, p);
+            float lse;
+            softmax_inplace<C>(p, lse);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += p[c];
+        }
+        if (nhwc) {
+            float* o = psum + (u * S + s) * Crt;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (c < Crt) o[c] = init ? acc[c] : o[c] + acc[c];
+        } else {
+            float* o = psum + u * Crt * S + s;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (c < Crt) o[(long long)c * S] = init ? acc[c] : o[(long long)c * S] + acc[c];
+        }
+    }
+}
+
+B200_API int b200_mc_softmax_accumulate(const float* logits, float* psum, int R, int U, int C, long long S, int layout_nhwc,
+                                        int init, cudaStream_t st) {
+    B200_REQUIRE(logits && psum && R > 0 && U > 0 && S > 0, "mc_softmax_accumulate: bad arguments");
+    B200_REQUIRE(C >= 2 && C <= SSL_MAXC, "mc_softmax_accumulate: classes must be in [2,%d]", SSL_MAXC);
+    const int grid = loss_grid((long long)U * S);
+    const int Cp = cpad_of(C);
+    if (Cp == 2) mc_softmax_acc_kernel<2><<<grid, 256, 0, st>>>(logits, psum, R, U, C, S, layout_nhwc, init);
+    else if (Cp == 4) mc_softmax_acc_kernel<4><<<grid, 256, 0, st>>>(logits, psum, R, U, C, S, layout_nhwc, init);
+    else mc_softmax_acc_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(logits, psum, R, U, C, S, layout_nhwc, init);
+    B200_CHECK_LAUNCH("mc_softmax_accumulate");
     return B200_OK;
 }

@@ -239,14 +239,20 @@ def ssl_loss_workspace_bytes(B, S) -> int:
     return int(_lib.query("b200_ssl_loss_workspace_bytes", B, S))
 
 
-def ssl_loss_fwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, ws):
+def ssl_loss_fwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, ws, mc_psum=None, mc_T=0.0, mc_thr=None):
     _lib.call("b200_ssl_loss_fwd", _pf(logits), _pf(teacher), _p(labels), _label_dtype(labels), int(nhwc), B, Lb, C_, S,
-              _pf(w_cons), _pf(lossbuf), _p(ws), ws.numel() * ws.element_size(), _st())
+              _pf(w_cons), _pf(mc_psum), float(mc_T), _pf(mc_thr), _pf(lossbuf), _p(ws), ws.numel() * ws.element_size(), _st())
 
 
-def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, grad_scale, dlogits, dlogits_nhwc,
+                 mc_psum=None, mc_T=0.0, mc_thr=None):
     _lib.call("b200_ssl_loss_bwd", _pf(logits), _pf(teacher), _p(labels), _label_dtype(labels), int(nhwc), B, Lb, C_, S,
-              _pf(w_cons), _pf(lossbuf), grad_scale, _pf(dlogits), int(dlogits_nhwc), _st())
+              _pf(w_cons), _pf(mc_psum), float(mc_T), _pf(mc_thr), _pf(lossbuf), grad_scale, _pf(dlogits),
+              int(dlogits_nhwc), _st())
+
+
+def mc_softmax_accumulate(logits, psum, R, U, C_, S, nhwc=False, init=True):
+    _lib.call("b200_mc_softmax_accumulate", _pf(logits), _pf(psum), R, U, C_, S, int(nhwc), int(init), _st())
 
 
 def sgd_ema_step(params, grads, momentum_buf, ema_params, hparams, zero_grad=False):

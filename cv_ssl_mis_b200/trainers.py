@@ -1,37 +1,45 @@
 """Fused training steps: the inner loops of the reference trainers as fixed launch schedules.
 
-`MeanTeacherTrainer` is code/train_mean_teacher_2D.py:201-238 (and, with `ema_model=None`, the fully
-supervised loop code/train_fully_supervised_2D.py:104-123): noise -> student forward -> teacher forward
-(train mode, no grad) -> CE + Dice + consistency -> student backward -> [grad all-reduce] -> SGD + EMA ->
-poly LR.  Everything between the host->device copy of the batch and the loss read-back is asynchronous on
-one stream, allocates nothing, reads its per-step scalars from a small device array and can therefore be
-replayed as a CUDA graph.
+`MeanTeacherTrainer` covers, with one schedule,
+  * Mean Teacher 2D/3D            code/train_mean_teacher_2D.py:201-238, code/train_mean_teacher_3D.py:134-166
+  * Uncertainty-Aware Mean Teacher code/train_uncertainty_aware_mean_teacher_3D.py:135-189 (2D twin: ..._2D.py:147-201)
+    (`uncertainty_T=8`: T/2 extra stochastic teacher passes on the twice-repeated unlabeled batch, entropy mask)
+  * fully supervised               code/train_fully_supervised_2D.py:104-123                  (`ema_model=None`)
+noise -> student forward -> teacher forward(s) (train mode, no grad) -> CE + Dice + (masked) consistency -> student
+backward -> [grad all-reduce] -> SGD + EMA -> poly LR.  Everything between the host->device copy of the batch and
+the loss read-back is asynchronous on one stream, allocates nothing, reads its per-step scalars from a small device
+array and can therefore be replayed as a CUDA graph.
 """
 from __future__ import annotations
+
+import math
 
 import torch
 
 from . import ops
 from .utils import ramps
 
-HP_LR, HP_MOMENTUM, HP_WD, HP_ALPHA, HP_ONE_MINUS_ALPHA, HP_GRAD_SCALE, HP_WCONS = range(7)
+HP_LR, HP_MOMENTUM, HP_WD, HP_ALPHA, HP_ONE_MINUS_ALPHA, HP_GRAD_SCALE, HP_WCONS, HP_THRESHOLD = range(8)
+NOISE_STREAM = 1000
 
 
 class MeanTeacherTrainer:
     def __init__(self, model, ema_model=None, *, batch_size=24, labeled_bs=12, patch_size=(256, 256), num_classes=4,
                  base_lr=0.01, max_iterations=30000, ema_decay=0.99, consistency=0.1, consistency_rampup=200.0,
-                 momentum=0.9, weight_decay=1e-4, start_iter=0, consistency_gate_iters=1000, noise_seed=2024,
-                 process_group=None, use_cuda_graph=False):
+                 momentum=0.9, weight_decay=1e-4, start_iter=0, consistency_gate_iters=1000, uncertainty_T=0,
+                 label_dtype=None, noise_seed=2024, process_group=None, use_cuda_graph=False):
         self.model, self.ema_model = model, ema_model
         self.B = batch_size
         self.Lb = labeled_bs if ema_model is not None else batch_size
         self.U = self.B - self.Lb
-        self.H, self.W = patch_size
+        self.patch = tuple(patch_size)
         self.C = num_classes
         self.base_lr, self.max_iterations, self.ema_decay = base_lr, max_iterations, ema_decay
         self.consistency, self.consistency_rampup = consistency, consistency_rampup
         self.momentum, self.weight_decay = momentum, weight_decay
         self.gate = consistency_gate_iters
+        self.T = uncertainty_T if ema_model is not None else 0
+        assert self.T % 2 == 0
         self.iter_num = start_iter
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -44,22 +52,32 @@ class MeanTeacherTrainer:
         if self.ema_flat is not None:
             assert self.ema_flat.padded == self.flat.padded
         self.momentum_buf = torch.zeros_like(self.flat.data)
-        # one RNG epoch counter shared by student, teacher and the noise kernel (their seeds/streams differ)
-        self.seed_off = model._rt.seed_off
-        if ema_model is not None:
-            ema_model._rt.seed_off = self.seed_off
-        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(8)
+        # RNG epochs: the student's is bumped once per step (its backward must regenerate the forward's masks), the
+        # teacher's before every teacher forward (each stochastic pass draws fresh noise and dropout)
+        self.s_off = model._rt.seed_off
+        self.t_off = ema_model._rt.seed_off if ema_model is not None else None
+        pin = dev.type == "cuda"
+        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if pin else torch.zeros(8)
         self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
-        S = self.H * self.W
+        S = 1
+        for v in self.patch:
+            S *= v
         self.S = S
-        self.x = torch.empty((self.B, 1, self.H, self.W), dtype=torch.float32, device=dev)
-        self.y = torch.empty((self.B, self.H, self.W), dtype=torch.uint8, device=dev)
-        self.ema_in = torch.empty((self.U, 1, self.H, self.W), dtype=torch.float32, device=dev) if self.U else None
-        self.lossbuf = torch.zeros(4 + 2 * 8, dtype=torch.float32, device=dev)
-        self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(4)
+        if label_dtype is None:
+            label_dtype = torch.uint8 if len(self.patch) == 2 else torch.int64      # dataset.py:425 / brats2019.py:188
+        self.x = torch.empty((self.B, 1, *self.patch), dtype=torch.float32, device=dev)
+        self.y = torch.empty((self.B, *self.patch), dtype=label_dtype, device=dev)
+        self.ema_in = torch.empty((self.U, 1, *self.patch), dtype=torch.float32, device=dev) if self.U else None
+        self.lossbuf = torch.zeros(32, dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if pin else torch.zeros(4)
         self.loss_ws = torch.empty(ops.ssl_loss_workspace_bytes(self.B, S) // 4 + 4, dtype=torch.float32, device=dev)
-        self.s_plan = model._get_plan(self.B, self.H, self.W, True)
-        self.t_plan = ema_model._get_plan(self.U, self.H, self.W, False) if self.U else None
+        self.s_plan = model._get_plan(self.B, *self.patch, True)
+        self.t_plan = ema_model._get_plan(self.U, *self.patch, False) if self.U else None
+        if self.T:
+            self.x_rep = torch.empty((2 * self.U, 1, *self.patch), dtype=torch.float32, device=dev)
+            self.ema_in2 = torch.empty_like(self.x_rep)
+            self.t_plan2 = ema_model._get_plan(2 * self.U, *self.patch, False)
+            self.psum = torch.empty((self.U, self.C, S), dtype=torch.float32, device=dev)
         self.lr = base_lr                     # the reference installs the poly LR *after* each step (:234-236)
         self.use_graph = use_cuda_graph and dev.type == "cuda"
         self.graph = None
@@ -70,6 +88,10 @@ class MeanTeacherTrainer:
         if self.ema_model is None or iter_num < self.gate:
             return 0.0
         return self.consistency * ramps.sigmoid_rampup(iter_num // 150, self.consistency_rampup)
+
+    def uncertainty_threshold(self, iter_num):
+        """code/train_uncertainty_aware_mean_teacher_3D.py:175-176 (ln 2 whatever the class count)"""
+        return (0.75 + 0.25 * ramps.sigmoid_rampup(iter_num, self.max_iterations)) * math.log(2)
 
     def _set_hparams(self):
         it = self.iter_num
@@ -82,24 +104,36 @@ class MeanTeacherTrainer:
         h[HP_ONE_MINUS_ALPHA] = 1 - alpha
         h[HP_GRAD_SCALE] = 1.0 / self.world
         h[HP_WCONS] = self.consistency_weight(it)
+        h[HP_THRESHOLD] = self.uncertainty_threshold(it)
         self.hp.copy_(h, non_blocking=True)
 
     # ---- the device-side schedule (graph-capturable)
     def _device_step(self):
-        self.seed_off += 1
+        self.s_off += 1
         self.model.train()
-        if self.U:
-            ops.noise_add(self.x[self.Lb:], self.ema_in, 0.1, 0.2, self.noise_seed, self.seed_off, 1000)
+        xu = self.x[self.Lb:]
         self.s_plan.forward(self.x, train=True)
-        teacher_logits = None
+        teacher_logits = psum = thr = None
         if self.U:
+            self.t_off += 1
+            ops.noise_add(xu, self.ema_in, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
             self.t_plan.forward(self.ema_in, train=True)          # teacher stays in train mode (Appendix A.1)
             teacher_logits = self.t_plan.logits
+        if self.T:
+            # volume_batch_r = unlabeled.repeat(2, ...); T//2 noisy passes of the 2U batch (:153-160)
+            self.x_rep[:self.U].copy_(xu)
+            self.x_rep[self.U:].copy_(xu)
+            for i in range(self.T // 2):
+                self.t_off += 1
+                ops.noise_add(self.x_rep, self.ema_in2, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
+                self.t_plan2.forward(self.ema_in2, train=True)
+                ops.mc_softmax_accumulate(self.t_plan2.logits, self.psum, 2, self.U, self.C, self.S, False, i == 0)
+            psum, thr = self.psum, self.hp[HP_THRESHOLD:HP_THRESHOLD + 1]
         w = self.hp[HP_WCONS:HP_WCONS + 1]
         ops.ssl_loss_fwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
-                         self.lossbuf, self.loss_ws)
+                         self.lossbuf, self.loss_ws, psum, float(self.T), thr)
         ops.ssl_loss_bwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
-                         self.lossbuf, 1.0, self.s_plan.head.g, True)
+                         self.lossbuf, 1.0, self.s_plan.head.g, True, psum, float(self.T), thr)
         self.s_plan.backward(None)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat.grad, group=self.pg)
@@ -107,7 +141,7 @@ class MeanTeacherTrainer:
                          self.ema_flat.data if self.ema_flat is not None else None, self.hp)
 
     def step(self, images, labels, read_loss=False):
-        """images [B,1,H,W] float32, labels [B,H,W] uint8 -- host (ideally pinned) or device tensors.
+        """images [B,1,*patch] float32, labels [B,*patch] uint8 (2D) / int64 (3D) -- host (ideally pinned) or device.
         Returns the device loss buffer [ce, dice, consistency, total, ...] (or host floats if read_loss)."""
         self._set_hparams()
         self.x.copy_(images, non_blocking=True)
@@ -126,23 +160,23 @@ class MeanTeacherTrainer:
             return self.loss_host.tolist()
         return self.lossbuf
 
+    def _state_tensors(self):
+        ts = [self.flat.data, self.momentum_buf, self.s_off]
+        if self.ema_flat is not None:
+            ts += [self.ema_flat.data, self.t_off]
+        return ts + self._all_buffers()
+
     def _capture(self):
         # warm up once eagerly on a side stream (lazy module loading, allocator), restoring all state after
-        keep = [t.clone() for t in (self.flat.data, self.momentum_buf, self.seed_off)]
-        keep_ema = self.ema_flat.data.clone() if self.ema_flat is not None else None
-        bufs = [b.clone() for b in self._all_buffers()]
+        keep = [t.clone() for t in self._state_tensors()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self._device_step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        for t, k in zip((self.flat.data, self.momentum_buf, self.seed_off), keep):
+        for t, k in zip(self._state_tensors(), keep):
             t.copy_(k)
-        if keep_ema is not None:
-            self.ema_flat.data.copy_(keep_ema)
-        for b, k in zip(self._all_buffers(), bufs):
-            b.copy_(k)
         from . import _lib
         n0 = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()

@@ -150,12 +150,22 @@ int b200_add(const float* a, const float* b, float* c, long long n, cudaStream_t
  * compared with teacher_logits [B-Lb][..] (NULL: no consistency term).  w_cons: DEVICE scalar (consistency weight).
  * lossbuf (>= 4 + 2*C floats): [0] ce [1] dice [2] consistency [3] total, then backward coefficients. */
 long long b200_ssl_loss_workspace_bytes(int B, long long S);
+/* Uncertainty-aware variant (code/train_uncertainty_aware_mean_teacher_3D.py:149-179): pass mc_psum = sum over the T
+ * stochastic teacher passes of softmax probabilities ([B-Lb][..], logits' layout; see b200_mc_softmax_accumulate), mc_T = T
+ * and mc_thr = DEVICE scalar threshold; the consistency term becomes sum(mask*dist) / (2 sum(mask) + 1e-16) with
+ * mask = [entropy(mc_psum / T) < thr].  mc_psum = NULL selects the plain mean over all elements.
+ * lossbuf needs 5 + 2*C floats. */
 int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
-                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, float* lossbuf,
-                      void* workspace, long long workspace_bytes, cudaStream_t stream);
+                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, const float* mc_psum,
+                      float mc_T, const float* mc_thr, float* lossbuf, void* workspace, long long workspace_bytes,
+                      cudaStream_t stream);
 int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
-                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, const float* lossbuf,
-                      float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t stream);
+                      int layout_nhwc, int B, int Lb, int C, long long S, const float* w_cons, const float* mc_psum,
+                      float mc_T, const float* mc_thr, const float* lossbuf, float grad_scale, float* dlogits,
+                      int dlogits_nhwc, cudaStream_t stream);
+/* psum[u] (+)= sum_{r<R} softmax(logits[r*U + u]) : accumulates the MC-dropout teacher passes without materialising them */
+int b200_mc_softmax_accumulate(const float* logits, float* psum, int R, int U, int C, long long S, int layout_nhwc,
+                               int init, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ optimizer / EMA / noise
  * optim.SGD + update_ema_variables + input noise: code/train_mean_teacher_2D.py:124-128,189-190,208-210,230-233

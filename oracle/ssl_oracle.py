@@ -206,3 +206,103 @@ def mt2d_step(student_sd, teacher_sd, bufs, images, labels, noise, iter_num, *, 
                 student_sd[k] = leaf[k]
     return dict(loss=loss.detach(), ce=ce.detach(), dice=dice.detach(), cons=cons.detach(), logits=outputs.detach(),
                 teacher_logits=ema_output, grads=dict(zip(keys, grads)), lr=lr, w=w_eff)
+
+
+# --------------------------------------------------------------------------- VNet (code/networks/vnet.py)
+VNET_STAGES = [1, 2, 3, 3, 3, 3, 3, 2, 1]
+VNET_NAMES = ["one", "two", "three", "four", "five", "six", "seven", "eight", "nine"]
+
+
+def _vnet_stage(h, sd, name, n, train, upd):
+    """ConvBlock, code/networks/vnet.py:5-31: n x [conv3x3x3 -> BatchNorm3d -> ReLU]"""
+    for i in range(n):
+        h = F.conv3d(h, sd[f"{name}.conv.{3 * i}.weight"], sd[f"{name}.conv.{3 * i}.bias"], padding=1)
+        h = F.relu(_bn(h, sd, f"{name}.conv.{3 * i + 1}", train, upd))
+    return h
+
+
+def vnet_forward(sd, x, train=True, drop5=None, drop9=None, update_running=False):
+    """VNet.forward with normalization='batchnorm', code/networks/vnet.py:180-239.
+    drop5 / drop9: optional [B, C] keep-masks of the two Dropout3d(0.5) (None => has_dropout False / eval)."""
+    feats = []
+    h = x
+    for s in range(5):                                                     # encoder :180-200
+        h = _vnet_stage(h, sd, f"block_{VNET_NAMES[s]}", VNET_STAGES[s], train, update_running)
+        if s == 4 and drop5 is not None:
+            h = h * drop5[:, :, None, None, None] / 0.5                    # Dropout3d: whole channels (:195-196)
+        feats.append(h)
+        if s < 4:
+            name = f"block_{VNET_NAMES[s]}_dw"                             # DownsamplingConvBlock :67-91
+            h = F.conv3d(h, sd[name + ".conv.0.weight"], sd[name + ".conv.0.bias"], stride=2)
+            h = F.relu(_bn(h, sd, name + ".conv.1", train, update_running))
+    for k in range(4):                                                     # decoder :202-228
+        name = f"block_{VNET_NAMES[4 + k]}_up"                             # UpsamplingDeconvBlock :94-118
+        h = F.conv_transpose3d(h, sd[name + ".conv.0.weight"], sd[name + ".conv.0.bias"], stride=2)
+        h = F.relu(_bn(h, sd, name + ".conv.1", train, update_running))
+        h = h + feats[3 - k]                                               # additive skips :210,214,218,222
+        h = _vnet_stage(h, sd, f"block_{VNET_NAMES[5 + k]}", VNET_STAGES[5 + k], train, update_running)
+    if drop9 is not None:
+        h = h * drop9[:, :, None, None, None] / 0.5                        # :225-226
+    return F.conv3d(h, sd["out_conv.weight"], sd["out_conv.bias"])
+
+
+def uamt_loss(student_logits, teacher_logits, mc_logits, labels, labeled_bs, n_classes, w_cons, threshold, T=8):
+    """code/train_uncertainty_aware_mean_teacher_3D.py:161-181.
+    mc_logits: list of T//2 tensors [2U, C, ...] (the stochastic teacher passes of the twice-repeated unlabeled batch)."""
+    U = student_logits.shape[0] - labeled_bs
+    preds = torch.cat(mc_logits, 0)                                        # [stride*T, C, ...] with stride = U  (:152-160)
+    preds = torch.softmax(preds, dim=1)
+    preds = preds.reshape(T, U, *preds.shape[1:]).mean(0)                  # :162-163
+    uncertainty = -1.0 * torch.sum(preds * torch.log(preds + 1e-6), dim=1, keepdim=True)   # :164-165
+    sup, ce, dice = supervised_loss(student_logits[:labeled_bs], labels[:labeled_bs], n_classes)
+    dist = softmax_mse_loss(student_logits[labeled_bs:], teacher_logits)   # :173-174
+    mask = (uncertainty < threshold).float()                               # :177
+    cons = torch.sum(mask * dist) / (2 * torch.sum(mask) + 1e-16)          # :178-179
+    return sup + w_cons * cons, ce, dice, cons, mask
+
+
+def uamt3d_step(student_sd, teacher_sd, bufs, images, labels, noises, iter_num, *, labeled_bs, n_classes=2, base_lr=0.01,
+                max_iterations=30000, ema_decay=0.99, consistency=0.1, consistency_rampup=200.0, lr=None, T=8,
+                student_drops=None, teacher_drops=None, forward=vnet_forward):
+    """One iteration of code/train_uncertainty_aware_mean_teacher_3D.py:137-189 on CPU.
+    noises: [noise for ema_inputs (U samples)] + T//2 noises for the repeated batch (2U samples each);
+    student_drops: (drop5, drop9) or None; teacher_drops: list of 1 + T//2 (drop5, drop9) pairs or None."""
+    keys = param_keys(student_sd)
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in student_sd.items()}
+    unlabeled = images[labeled_bs:]
+    sdrop = student_drops or (None, None)
+    outputs = forward(leaf, images, True, sdrop[0], sdrop[1], update_running=True)                 # :145
+    mc = []
+    with torch.no_grad():
+        td = teacher_drops[0] if teacher_drops else (None, None)
+        ema_output = forward(teacher_sd, unlabeled + noises[0], True, td[0], td[1], update_running=True)   # :147-148
+        volume_batch_r = unlabeled.repeat(2, *([1] * (images.dim() - 1)))                        # :151
+        for i in range(T // 2):                                                                    # :155-160
+            td = teacher_drops[1 + i] if teacher_drops else (None, None)
+            mc.append(forward(teacher_sd, volume_batch_r + noises[1 + i], True, td[0], td[1], update_running=True))
+    w = consistency_weight(iter_num, consistency, consistency_rampup)                              # :172
+    threshold = (0.75 + 0.25 * sigmoid_rampup(iter_num, max_iterations)) * np.log(2)               # :175-176
+    loss, ce, dice, cons, mask = uamt_loss(outputs, ema_output, mc, labels, labeled_bs, n_classes, w, threshold, T)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys])
+    if lr is None:
+        lr = base_lr if iter_num == 0 else poly_lr(base_lr, iter_num - 1, max_iterations)
+    with torch.no_grad():
+        params = [student_sd[k] for k in keys]
+        sgd_momentum_step(params, grads, [bufs[k] for k in keys], lr)                              # :183-185
+        ema_update([teacher_sd[k] for k in keys], params, ema_alpha(iter_num, ema_decay))          # :186
+    return dict(loss=loss.detach(), ce=ce.detach(), dice=dice.detach(), cons=cons.detach(), logits=outputs.detach(),
+                teacher_logits=ema_output, mask_frac=float(mask.mean()), grads=dict(zip(keys, grads)), lr=lr, w=w,
+                threshold=float(threshold))
+
+
+def vnet_fixture_inputs(gen_seed, B, Lb, P, T=8):
+    """Replays the torch.Generator calls of tests/golden/make_golden.py:vnet_fixture (inputs, labels, noises)."""
+    g = torch.Generator().manual_seed(gen_seed)
+    x = torch.randn(B, 1, P, P, P, generator=g)
+    low = torch.randint(0, 2, (B, P // 8, P // 8, P // 8), generator=g)
+    y = low.repeat_interleave(8, 1).repeat_interleave(8, 2).repeat_interleave(8, 3).long()
+    U = B - Lb
+    noises = [torch.clamp(torch.randn(U, 1, P, P, P, generator=g) * 0.1, -0.2, 0.2)]
+    for _ in range(T // 2):
+        noises.append(torch.clamp(torch.randn(2 * U, 1, P, P, P, generator=g) * 0.1, -0.2, 0.2))
+    return x, y, noises

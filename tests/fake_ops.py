@@ -389,7 +389,7 @@ def _to_ncs(t, nhwc, n, C, S):
     return t.reshape(n, S, C).permute(0, 2, 1) if nhwc else t.reshape(n, C, S)
 
 
-def _ssl_loss(logits, teacher, labels, nhwc, B, Lb, C, S, w):
+def _ssl_loss(logits, teacher, labels, nhwc, B, Lb, C, S, w, mc_psum=None, mc_T=0.0, mc_thr=None):
     from oracle import ssl_oracle as O
     lg = _to_ncs(logits, nhwc, B, C, S)
     tl = _to_ncs(teacher, nhwc, B - Lb, C, S) if teacher is not None else None
@@ -400,24 +400,42 @@ def _ssl_loss(logits, teacher, labels, nhwc, B, Lb, C, S, w):
         sup = ce = dice = torch.zeros(())
     cons = torch.zeros(())
     if tl is not None and B > Lb:
-        cons = torch.mean((torch.softmax(lg[Lb:], 1) - torch.softmax(tl, 1)) ** 2)
+        dist = (torch.softmax(lg[Lb:], 1) - torch.softmax(tl, 1)) ** 2
+        if mc_psum is None:
+            cons = torch.mean(dist)
+        else:
+            pbar = _to_ncs(mc_psum, nhwc, B - Lb, C, S) / mc_T
+            unc = -torch.sum(pbar * torch.log(pbar + 1e-6), dim=1, keepdim=True)
+            mask = (unc < float(mc_thr[0])).float()
+            cons = torch.sum(mask * dist) / (2 * torch.sum(mask) + 1e-16)
     return sup + w * cons, ce, dice, cons
 
 
-def ssl_loss_fwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, ws):
+def ssl_loss_fwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, ws, mc_psum=None, mc_T=0.0, mc_thr=None):
     w = float(w_cons[0]) if w_cons is not None else 0.0
-    tot, ce, dice, cons = _ssl_loss(logits.detach(), teacher, labels, nhwc, B, Lb, C, S, w)
+    tot, ce, dice, cons = _ssl_loss(logits.detach(), teacher, labels, nhwc, B, Lb, C, S, w, mc_psum, mc_T, mc_thr)
     lossbuf[0], lossbuf[1], lossbuf[2], lossbuf[3] = ce, dice, cons, tot
 
 
-def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, grad_scale, dlogits, dlogits_nhwc,
+                 mc_psum=None, mc_T=0.0, mc_thr=None):
     w = float(w_cons[0]) if (w_cons is not None and teacher is not None) else 0.0
     with torch.enable_grad():
         lg = logits.detach().clone().requires_grad_(True)
-        tot, *_ = _ssl_loss(lg, teacher, labels, nhwc, B, Lb, C, S, w)
+        tot, *_ = _ssl_loss(lg, teacher, labels, nhwc, B, Lb, C, S, w, mc_psum, mc_T, mc_thr)
         (g,) = torch.autograd.grad(tot * grad_scale, lg)
     g = _to_ncs(g, nhwc, B, C, S)
     dlogits.copy_((g.permute(0, 2, 1) if dlogits_nhwc else g).reshape(dlogits.shape))
+
+
+def mc_softmax_accumulate(logits, psum, R, U, C, S, nhwc=False, init=True):
+    lg = _to_ncs(logits, nhwc, R * U, C, S)
+    acc = torch.softmax(lg, 1).reshape(R, U, C, S).sum(0)
+    acc = (acc.permute(0, 2, 1) if nhwc else acc).reshape(psum.shape)
+    if init:
+        psum.copy_(acc)
+    else:
+        psum += acc
 
 
 def sgd_ema_step(params, grads, momentum_buf, ema_params, hparams, zero_grad=False):

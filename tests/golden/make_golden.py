@@ -188,3 +188,89 @@ if __name__ == "__main__":
     losses_fixture()
     ramps_fixture()
     mt_step_fixture()
+
+
+def vnet_fixture():
+    """VNet (batchnorm, has_dropout) forward/backward + one UAMT iteration restated from
+    code/train_uncertainty_aware_mean_teacher_3D.py:137-189 over the reference's own VNet/DiceLoss/softmax_mse/ramps."""
+    from networks.vnet import VNet as RefVNet
+    from cv_ssl_mis_b200.networks.vnet import VNet as OurVNet
+    seed = 2468
+    torch.manual_seed(seed)
+    model = RefVNet(n_channels=1, n_classes=2, normalization='batchnorm', has_dropout=True)
+    ema_model = RefVNet(n_channels=1, n_classes=2, normalization='batchnorm', has_dropout=True)
+    torch.manual_seed(seed)
+    ours = OurVNet(n_channels=1, n_classes=2, normalization='batchnorm', has_dropout=True)
+    sd_ref, sd_ours = model.state_dict(), ours.state_dict()
+    assert list(sd_ref.keys()) == list(sd_ours.keys()), "VNet state_dict key schema differs from the reference"
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_ours[k]), k
+    assert [tuple(p.shape) for p in model.parameters()] == [tuple(p.shape) for p in ours.parameters()]
+    for p in ema_model.parameters():
+        p.detach_()
+    init_ck = (checksum(sd_ref), checksum(ema_model.state_dict()))
+    model.dropout.p = 0.0                 # Dropout3d off (masks cannot be shared with torch's RNG); BN stays in train mode
+    ema_model.dropout.p = 0.0
+    model.train(); ema_model.train()
+    g = torch.Generator().manual_seed(11)
+    B, Lb, P = 4, 2, 32
+    volume_batch = torch.randn(B, 1, P, P, P, generator=g)
+    low = torch.randint(0, 2, (B, P // 8, P // 8, P // 8), generator=g)
+    label_batch = low.repeat_interleave(8, 1).repeat_interleave(8, 2).repeat_interleave(8, 3).long()
+    base_lr, max_iterations, ema_decay, consistency, consistency_rampup = 0.01, 30000, 0.99, 0.1, 200.0
+    optimizer = torch.optim.SGD(model.parameters(), lr=base_lr, momentum=0.9, weight_decay=0.0001)
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(2)
+    iter_num = 3000
+    unlabeled_volume_batch = volume_batch[Lb:]                                                    # :139
+    noises = [torch.clamp(torch.randn(unlabeled_volume_batch.shape, generator=g) * 0.1, -0.2, 0.2)]   # :141-142
+    ema_inputs = unlabeled_volume_batch + noises[0]
+    outputs = model(volume_batch)                                                                 # :145
+    outputs_soft = torch.softmax(outputs, dim=1)
+    with torch.no_grad():
+        ema_output = ema_model(ema_inputs)                                                        # :148
+    T = 8
+    _, _, d, w, h = unlabeled_volume_batch.shape
+    volume_batch_r = unlabeled_volume_batch.repeat(2, 1, 1, 1, 1)                                 # :151
+    stride = volume_batch_r.shape[0] // 2
+    preds = torch.zeros([stride * T, 2, d, w, h])
+    for i in range(T // 2):                                                                       # :155-160
+        nz = torch.clamp(torch.randn(volume_batch_r.shape, generator=g) * 0.1, -0.2, 0.2)
+        noises.append(nz)
+        with torch.no_grad():
+            preds[2 * stride * i:2 * stride * (i + 1)] = ema_model(volume_batch_r + nz)
+    preds = torch.softmax(preds, dim=1)
+    preds = preds.reshape(T, stride, 2, d, w, h)
+    preds = torch.mean(preds, dim=0)
+    uncertainty = -1.0 * torch.sum(preds * torch.log(preds + 1e-6), dim=1, keepdim=True)          # :164-165
+    loss_ce = ce_loss(outputs[:Lb], label_batch[:Lb])                                             # :167-168
+    loss_dice = dice_loss(outputs_soft[:Lb], label_batch[:Lb].unsqueeze(1))
+    supervised_loss = 0.5 * (loss_dice + loss_ce)
+    consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :172
+    consistency_dist = ref_losses.softmax_mse_loss(outputs[Lb:], ema_output)                      # :173-174
+    threshold = (0.75 + 0.25 * ref_ramps.sigmoid_rampup(iter_num, max_iterations)) * np.log(2)    # :175-176
+    mask = (uncertainty < threshold).float()
+    consistency_loss = torch.sum(mask * consistency_dist) / (2 * torch.sum(mask) + 1e-16)         # :178-179
+    loss = supervised_loss + consistency_weight * consistency_loss
+    optimizer.zero_grad()
+    loss.backward()
+    grad_norm = {n: float(p.grad.norm()) for n, p in model.named_parameters()}
+    optimizer.step()
+    update_ema_variables(model, ema_model, ema_decay, iter_num)                                   # :186
+    # inputs/noises are regenerated by the tests from the same generator calls (vnet_inputs below); logits are
+    # stored subsampled (every 4th voxel) plus their mean/abs-mean to keep the fixture small
+    sub = lambda t: t[:, :, ::4, ::4, ::4].clone()
+    stat = lambda t: (float(t.mean()), float(t.abs().mean()))
+    torch.save(dict(seed=seed, init_ck=init_ck, keys=list(sd_ref.keys()), labeled_bs=Lb, iter_num=iter_num, gen_seed=11,
+                    B=B, P=P, logits_sub=sub(outputs.detach()), logits_stat=stat(outputs.detach()),
+                    teacher_sub=sub(ema_output), teacher_stat=stat(ema_output),
+                    loss=loss.detach(), ce=loss_ce.detach(), dice=loss_dice.detach(), cons=consistency_loss.detach(),
+                    mask_frac=float(mask.mean()), threshold=float(threshold), w=consistency_weight, grad_norm=grad_norm,
+                    w_out=model.out_conv.weight.detach().clone(), t_out=ema_model.out_conv.weight.detach().clone(),
+                    student_ck=checksum(model.state_dict()), teacher_ck=checksum(ema_model.state_dict())),
+               os.path.join(HERE, "vnet_uamt.pt"))
+    print("vnet_uamt: loss", float(loss), "cons", float(consistency_loss), "mask frac", float(mask.mean()))
+
+
+if __name__ == "__main__":
+    vnet_fixture()

@@ -117,3 +117,82 @@ def test_mean_teacher_trainer_matches_oracle(fake):
                 torch.testing.assert_close(td_now[k], t_sd[k], rtol=2e-3, atol=1e-5, msg=lambda m, k=k: f"teacher {k}: {m}")
     assert tr.iter_num == 1002
     assert abs(tr.lr - O.poly_lr(0.01, 1001, 30000)) < 1e-15
+
+
+def vnet_drops(seed, B, nf=16):
+    """(drop5, drop9) channel keep-masks [B, C] of one VNet forward (rng streams 0 and 1, Dropout3d p = 0.5)."""
+    d5 = torch.from_numpy(philox.keep_mask(seed, 0, B, 16 * nf, 0.5, 2, 1)).reshape(B, 16 * nf)
+    d9 = torch.from_numpy(philox.keep_mask(seed, 1, B, nf, 0.5, 2, 1)).reshape(B, nf)
+    return d5, d9
+
+
+def test_vnet_plan_matches_oracle(fake):
+    from cv_ssl_mis_b200.networks import vnet as vnet_mod
+    torch.manual_seed(13)
+    net = vnet_mod.VNet(1, 2, has_dropout=True)
+    B, P = 2, 32                      # 16^3 would leave 2 samples per channel in the deepest BatchNorm: ill-conditioned
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 1, P, P, P, generator=g)
+    y = torch.randint(0, 2, (B, P, P, P), generator=g)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    FlatParams(net, "cpu")
+    rt = Runtime("cpu", seed=55)
+    plan = vnet_mod.VNetPlan(net, rt, B, P, P, P, True)
+    logits = plan.forward(x, train=True).view(B, 2, P, P, P)
+    keys = O.param_keys(sd0)
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v.clone()) for k, v in sd0.items()}
+    d5, d9 = vnet_drops(55, B)
+    ref = O.vnet_forward(leaf, x, True, d5, d9, update_running=True)
+    torch.testing.assert_close(logits, ref, rtol=1e-3, atol=2e-4)      # 30 BatchNorms deep, 16 samples in the deepest
+    loss, _, _ = O.supervised_loss(ref, y, 2)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys] + [ref])
+    plan.backward(grads[-1].permute(0, 2, 3, 4, 1).reshape(B * P ** 3, 2).contiguous())
+    named = dict(net.named_parameters())
+    for k, gr in zip(keys, grads[:-1]):
+        rel = float((named[k].grad - gr).norm() / (gr.norm() + 1e-12))
+        # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (only round-off remains)
+        # the fp32 oracle itself sits 0.5-1.2% from an fp64 run on this tiny batch (30 BatchNorm backward passes)
+        assert rel < 5e-2 or float(gr.norm()) < 1e-5, (k, rel)
+    sd1 = net.state_dict()
+    for k in sd1:
+        if "running" in k:
+            torch.testing.assert_close(sd1[k], leaf[k], rtol=1e-5, atol=1e-6)
+
+
+def test_uamt_trainer_matches_oracle(fake):
+    from cv_ssl_mis_b200.networks import vnet as vnet_mod
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(31)
+    student, teacher = vnet_mod.VNet(1, 2, has_dropout=True, seed=301), vnet_mod.VNet(1, 2, has_dropout=True, seed=402)
+    for p in teacher.parameters():
+        p.detach_()
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    t_sd = {k: v.clone() for k, v in teacher.state_dict().items()}
+    B, Lb, P, T = 4, 2, 32, 8
+    U = B - Lb
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(P, P, P), num_classes=2,
+                            start_iter=2000, consistency_gate_iters=0, uncertainty_T=T, noise_seed=777)
+    tr.lr = O.poly_lr(0.01, 1999, 30000)
+    bufs = {k: torch.zeros_like(s_sd[k]) for k in O.param_keys(s_sd)}
+    g = torch.Generator().manual_seed(9)
+    t_epoch = 0
+    for step in range(2):
+        it = 2000 + step
+        x = torch.randn(B, 1, P, P, P, generator=g)
+        y = torch.randint(0, 2, (B, P, P, P), generator=g)
+        lossbuf = tr.step(x, y).clone()
+        noises, tdrops = [], []
+        for k in range(1 + T // 2):                           # teacher RNG epoch advances before every teacher forward
+            t_epoch += 1
+            nb = U if k == 0 else 2 * U
+            noises.append(torch.from_numpy(philox.clamp_noise(777 + t_epoch, 1000, nb * P ** 3)).reshape(nb, 1, P, P, P))
+            tdrops.append(vnet_drops(402 + t_epoch, nb))
+        r = O.uamt3d_step(s_sd, t_sd, bufs, x, y, noises, it, labeled_bs=Lb, T=T,
+                          student_drops=vnet_drops(301 + step + 1, B), teacher_drops=tdrops)
+        torch.testing.assert_close(lossbuf[3], r["loss"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(lossbuf[2], r["cons"], rtol=1e-3, atol=1e-6)
+        sd_now, td_now = student.state_dict(), teacher.state_dict()
+        for k in s_sd:
+            if s_sd[k].dtype.is_floating_point:
+                torch.testing.assert_close(sd_now[k], s_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"student {k}: {m}")
+                torch.testing.assert_close(td_now[k], t_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"teacher {k}: {m}")

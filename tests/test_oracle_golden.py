@@ -95,3 +95,33 @@ def test_mt_step(golden):
         torch.testing.assert_close(student["encoder.in_conv.conv_conv.0.weight"], s["w_in"], rtol=1e-4, atol=1e-6)
         assert abs(checksum(student) - s["student_ck"]) < 1e-5 * s["student_ck"]
         assert abs(checksum(teacher) - s["teacher_ck"]) < 1e-5 * s["teacher_ck"]
+
+
+def test_vnet_uamt_step(golden):
+    """oracle.vnet_forward + oracle.uamt3d_step against one UAMT iteration driven through the reference's own VNet."""
+    from cv_ssl_mis_b200.networks.vnet import VNet
+    g = golden("vnet_uamt.pt")
+    torch.manual_seed(g["seed"])
+    student = VNet(1, 2, has_dropout=True).state_dict()
+    teacher = VNet(1, 2, has_dropout=True).state_dict()
+    assert list(student.keys()) == g["keys"]
+    if abs(checksum(student) - g["init_ck"][0]) > 1e-6 * g["init_ck"][0] or abs(checksum(teacher) - g["init_ck"][1]) > 1e-6 * g["init_ck"][1]:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    student = {k: v.clone() for k, v in student.items()}
+    teacher = {k: v.clone() for k, v in teacher.items()}
+    x, y, noises = O.vnet_fixture_inputs(g["gen_seed"], g["B"], g["labeled_bs"], g["P"])
+    bufs = {k: torch.zeros_like(student[k]) for k in O.param_keys(student)}
+    r = O.uamt3d_step(student, teacher, bufs, x, y, noises, g["iter_num"], labeled_bs=g["labeled_bs"], lr=0.01)
+    sub = lambda t: t[:, :, ::4, ::4, ::4]
+    torch.testing.assert_close(sub(r["logits"]), g["logits_sub"], rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(sub(r["teacher_logits"]), g["teacher_sub"], rtol=2e-4, atol=2e-5)
+    assert abs(float(r["logits"].abs().mean()) - g["logits_stat"][1]) < 1e-4 * g["logits_stat"][1]
+    torch.testing.assert_close(r["loss"], g["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(r["cons"], g["cons"], rtol=1e-3, atol=1e-6)
+    assert abs(r["mask_frac"] - g["mask_frac"]) < 1e-4 and abs(r["threshold"] - g["threshold"]) < 1e-12 and r["w"] == g["w"]
+    for k, gr in r["grads"].items():
+        assert abs(float(gr.norm()) - g["grad_norm"][k]) <= 5e-3 * g["grad_norm"][k] + 1e-7, k
+    torch.testing.assert_close(student["out_conv.weight"], g["w_out"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(teacher["out_conv.weight"], g["t_out"], rtol=1e-4, atol=1e-6)
+    assert abs(checksum(student) - g["student_ck"]) < 1e-5 * g["student_ck"]
+    assert abs(checksum(teacher) - g["teacher_ck"]) < 1e-5 * g["teacher_ck"]
