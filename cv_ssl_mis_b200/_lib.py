@@ -66,6 +66,11 @@ SIGNATURES = {
     "b200_conv_umma_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_pack_batch": (_I, [_P, _I, _I, _S]),
+    "b200_conv_c1_supported": (_I, [_D]),
+    "b200_conv_c1_fwd": (_I, [_D, _P, _P, _P, _P, _S]),
+    "b200_conv_c1_wgrad_workspace_bytes": (_L, [_D]),
+    "b200_conv_c1_wgrad": (_I, [_D, _P, _P, _P, _L, _P, _P, _I, _S]),
     "b200_bn_workspace_bytes": (_L, [_L, _I]),
     "b200_bn_stats_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _L, _S]),
     "b200_bn_eval_state": (_I, [_I, _P, _P, _F, _P, _P, _P, _S]),
@@ -91,7 +96,8 @@ SIGNATURES = {
 }
 
 # entry points whose int return value is NOT a status code
-_NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported"}
+_NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported",
+               "b200_conv_c1_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

@@ -112,6 +112,7 @@ class ConvLayer:
         self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False)
                          and (self.out_nchw or self.cout % 4 == 0))
         self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True)
+        self.c1 = is_conv and not rt.exact and ops.conv_c1_supported(self.desc)       # first layer: FFMA kernels
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
         self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)
@@ -123,7 +124,8 @@ class ConvLayer:
         if need_grad:
             if is_conv:
                 self.bwd_mode = PACK_CONV_DGRAD if self.stride == 1 else PACK_CONV_DGRAD_D2S
-                rt.need_scratch(ops.conv_tile_wgrad_workspace_bytes(self.desc) if self.tile_wgrad
+                rt.need_scratch(ops.conv_c1_wgrad_workspace_bytes(self.desc) if self.c1 else
+                                ops.conv_tile_wgrad_workspace_bytes(self.desc) if self.tile_wgrad
                                 else ops.conv_wgrad_workspace_bytes(self.desc))
             else:
                 self.bwd_mode = PACK_DECONV_DGRAD
@@ -133,6 +135,26 @@ class ConvLayer:
                     ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
         return self
+
+    def pack_jobs(self, need_dgrad):
+        """(weight, packed buffer, kind, mode, O, I, T) tuples for the one-launch packer (ops.conv_pack_batch)."""
+        O, I, T, w = self.cout, self.cin, self.T, self.conv.weight
+        jobs = []
+        if not self.c1:
+            if self.umma_fwd:
+                jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
+            elif self.tile_fwd:
+                jobs.append((w, self.wp_fwd, 1, 0, O, I, T))
+            else:
+                jobs.append((w, self.wp_fwd, 0, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, T))
+        if need_dgrad and self.wp_bwd is not None:
+            if self.umma_dgrad:
+                jobs.append((w, self.wp_bwd, 2, 1, O, I, T))
+            elif self.tile_dgrad:
+                jobs.append((w, self.wp_bwd, 1, 1, O, I, T))
+            else:
+                jobs.append((w, self.wp_bwd, 0, self.bwd_mode, O, I, T))
+        return jobs
 
     def pack(self, need_dgrad):
         O, I = self.cout, self.cin
@@ -153,7 +175,9 @@ class ConvLayer:
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
         _lib.tag = self.name
-        if self.umma_fwd:
+        if self.c1:
+            ops.conv_c1_fwd(self.desc, src0, self.conv.weight, self.conv.bias, self.y)
+        elif self.umma_fwd:
             ops.conv_umma_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
         elif self.tile_fwd:
             ops.conv_tile_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
@@ -187,7 +211,9 @@ class ConvLayer:
         dy = self.g
         bias_grad = conv.bias.grad if conv.bias is not None else None
         if self.kind == "conv":
-            if self.tile_wgrad:
+            if self.c1:
+                ops.conv_c1_wgrad(self.desc, src0, dy, rt.scratch, conv.weight.grad, bias_grad, False)
+            elif self.tile_wgrad:
                 ops.conv_tile_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False)
             else:
                 ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
@@ -206,3 +232,19 @@ class ConvLayer:
                 ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch)
             if dx0 is not None:
                 ops.deconv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
+
+
+class PackTable:
+    """Device-side job table so that all weight packings of a plan run as ONE kernel launch per forward."""
+
+    def __init__(self, layers, need_dgrad, device):
+        self.jobs_py = [j for l in layers for j in l.pack_jobs(need_dgrad)]
+        rows = [[w.data_ptr(), out.data_ptr(), kind, mode, O, I, T, out.numel()] for (w, out, kind, mode, O, I, T) in self.jobs_py]
+        self.table = torch.tensor(rows, dtype=torch.int64, device=device)
+        self.ptrs = [w.data_ptr() for (w, *_rest) in self.jobs_py]
+
+    def run(self):
+        # parameters may have been re-homed (e.g. .cuda() after planning): the table stores raw pointers
+        assert self.ptrs == [w.data_ptr() for (w, *_r) in self.jobs_py], "parameters moved after planning"
+        _lib.tag = "pack"
+        ops.conv_pack_batch(self.table, len(self.jobs_py), 16, self.jobs_py)

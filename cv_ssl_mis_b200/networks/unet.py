@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._engine import ConvLayer, FlatParams, Runtime
+from ._engine import ConvLayer, FlatParams, PackTable, Runtime
 
 FT_CHNS = [16, 32, 64, 128, 256]
 DROPOUT = [0.05, 0.1, 0.2, 0.3, 0.5]
@@ -107,6 +107,7 @@ class UNetPlan:
         for l in self.layers:                 # profiling tags: gradient-carrying (student) vs forward-only (teacher) plan
             l.name = ("S." if need_grad else "T.") + l.name
         rt.alloc_scratch()
+        self.packer = PackTable(self.layers, need_grad, dev)
         self.in_flight = False
 
     @property
@@ -116,8 +117,7 @@ class UNetPlan:
     def forward(self, x, train=True):
         """x: [B,1,H,W] (== channels-last for one channel) or [B*H*W, in_chns] channels-last."""
         rt, B = self.rt, self.B
-        for l in self.layers:
-            l.pack(self.need_grad)
+        self.packer.run()
         self.x_in = x
         src = x
         h, w = self.H, self.W

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._engine import ConvLayer, FlatParams, Runtime
+from ._engine import ConvLayer, FlatParams, PackTable, Runtime
 
 STAGES = [1, 2, 3, 3, 3, 3, 3, 2, 1]           # block_one .. block_nine
 
@@ -85,6 +85,7 @@ class VNetPlan:
         self.head = ConvLayer(net.out_conv, dims=3, out_nchw=True, name="out").plan(rt, B, D, H, W, nf, 0, need_grad)
         self.layers = [l for st in self.stages for l in st] + self.down + self.up + [self.head]
         rt.alloc_scratch()
+        self.packer = PackTable(self.layers, need_grad, dev)
         self.in_flight = False
 
     @property
@@ -93,8 +94,7 @@ class VNetPlan:
 
     def forward(self, x, train=True):
         rt = self.rt
-        for l in self.layers:
-            l.pack(self.need_grad)
+        self.packer.run()
         self.x_in = x
         cur = x
         for s in range(5):

@@ -157,6 +157,29 @@ def conv_umma_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
     _lib.call("b200_conv_umma_dgrad", C.byref(d), _pf(dy), _pf(wt_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
 
 
+# batched packing / first-layer kernels
+def conv_pack_batch(jobs_dev, njobs, blocks_per_job=16, jobs_py=None):
+    """jobs_dev: int64 [njobs, 8] device table (see include/b200ssl.h); jobs_py is only used by the CPU test stand-in."""
+    _lib.call("b200_conv_pack_batch", _p(jobs_dev), njobs, blocks_per_job, _st())
+
+
+def conv_c1_supported(d) -> bool:
+    return bool(_lib.query("b200_conv_c1_supported", C.byref(d)))
+
+
+def conv_c1_fwd(d, x, w, bias, y):
+    _lib.call("b200_conv_c1_fwd", C.byref(d), _pf(x), _pf(w), _pf(bias), _pf(y), _st())
+
+
+def conv_c1_wgrad_workspace_bytes(d) -> int:
+    return int(_lib.query("b200_conv_c1_wgrad_workspace_bytes", C.byref(d)))
+
+
+def conv_c1_wgrad(d, x, dy, ws, dw, db, accumulate=False):
+    _lib.call("b200_conv_c1_wgrad", C.byref(d), _pf(x), _pf(dy), _p(ws), ws.numel() * ws.element_size(), _pf(dw), _pf(db),
+              int(accumulate), _st())
+
+
 # ------------------------------------------------------------------ norm / activation / dropout
 def bn_workspace_bytes(M, C_) -> int:
     return int(_lib.query("b200_bn_workspace_bytes", M, C_))

@@ -109,6 +109,17 @@ int b200_conv_umma2_fwd(const b200_conv_desc* d, const float* src0, const float*
 int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
                           int accumulate, cudaStream_t stream);
 
+/* One-launch weight packing for a whole network.  jobs_dev: DEVICE array of njobs x 8 int64:
+ * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma), mode (generic: B200_PACK_*; tile/umma: dgrad flag), O, I, T, total]. */
+int b200_conv_pack_batch(const long long* jobs_dev, int njobs, int blocks_per_job, cudaStream_t stream);
+/* First layer of the CNNs (Cin = 1, 3x3 / 3x3x3 stride 1 pad 1, Cout in {16, 32}): HBM-bound FFMA kernels working on the
+ * framework weight layout directly (code/networks/unet.py:37 with in_chns = 1, code/networks/vnet.py:152). */
+int b200_conv_c1_supported(const b200_conv_desc* d);
+int b200_conv_c1_fwd(const b200_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t stream);
+long long b200_conv_c1_wgrad_workspace_bytes(const b200_conv_desc* d);
+int b200_conv_c1_wgrad(const b200_conv_desc* d, const float* x, const float* dy, float* workspace, long long workspace_bytes,
+                       float* dw, float* db, int accumulate, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ BatchNorm(train) + activation + dropout
  * nn.BatchNorm2d/3d + nn.LeakyReLU/ReLU + nn.Dropout/Dropout3d: code/networks/unet.py:38-43 ; code/networks/vnet.py:16-25,177
  * state = [mean | invstd | scale | shift] (4*C floats).  drop_mode: 0 none, 1 per element, 2 per (sample, channel).

@@ -270,6 +270,35 @@ def conv_umma_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
     conv_tile_dgrad(d, dy, _umma_to_tile(wt_dgrad, True, d.cout, d.c0 + d.c1, 9), dx0, dx1, accumulate)
 
 
+# ------------------------------------------------------------------ batched packing / first layer
+def conv_pack_batch(jobs_dev, njobs, blocks_per_job=16, jobs_py=None):
+    for (w, out, kind, mode, O, I, T) in jobs_py:
+        if kind == 0:
+            conv_pack_weights(w, out, mode, O, I, T)
+        elif kind == 1:
+            conv_tile_pack_weights(w, out, bool(mode), O, I, T)
+        else:
+            conv_umma_pack_weights(w, out, bool(mode), O, I, T)
+
+
+def conv_c1_supported(d):
+    return bool(d.c0 == 1 and d.c1 == 0 and d.stride == 1 and d.kh == 3 and d.kw == 3 and d.ph == 1 and d.pw == 1 and
+                ((d.kd == 1 and d.pd == 0) or (d.kd == 3 and d.pd == 1)) and d.cout in (16, 32))
+
+
+def conv_c1_fwd(d, x, w, bias, y):
+    r = F.conv3d(_input(d, x.reshape(-1, 1), None), w.detach().reshape(d.cout, 1, d.kd, d.kh, d.kw), bias, **_kw(d))
+    y.copy_(_ncdhw_to_cl(r).reshape(y.shape))
+
+
+def conv_c1_wgrad_workspace_bytes(d):
+    return 64
+
+
+def conv_c1_wgrad(d, x, dy, ws, dw, db, accumulate=False):
+    conv_wgrad(d, x.reshape(-1, 1), None, dy, ws, dw, db, accumulate)
+
+
 # ------------------------------------------------------------------ norm / act / dropout
 def bn_workspace_bytes(M, C):
     return 64

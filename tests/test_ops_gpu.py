@@ -430,3 +430,26 @@ def test_conv_umma_kernels(case, v2, monkeypatch):
             torch.testing.assert_close(dx1.cpu(), r1, **tol)
         ops.conv_umma_dgrad(desc, cu(dy), packs[True][0], dx0, dx1, True)
         torch.testing.assert_close(dx0.cpu(), 2 * r0, rtol=tol["rtol"], atol=2 * tol["atol"])
+
+
+@pytest.mark.parametrize("case", [(2, 1, 20, 24, 16), (3, 1, 32, 32, 32), (1, 6, 10, 12, 16), (2, 4, 8, 8, 32)])
+def test_first_layer_kernels(case):
+    n, d, h, w, cout = case
+    dims = 3 if d > 1 else 2
+    g = torch.Generator().manual_seed(sum(case))
+    desc = ops.conv_desc(n, d, h, w, 1, 0, cout, 3, 1, 1, dims)
+    assert ops.conv_c1_supported(desc)
+    T, M = 3 ** dims, n * d * h * w
+    wgt, bias = rnd(g, cout, 1, *([3] * dims), scale=0.3), rnd(g, cout)
+    x, dy = rnd(g, M, 1), rnd(g, M, cout)
+    y, y_ref = torch.empty(M, cout, device=DEV), torch.empty(M, cout)
+    ops.conv_c1_fwd(desc, cu(x), cu(wgt), cu(bias), y)
+    ref.conv_c1_fwd(desc, x, wgt, bias, y_ref)
+    torch.testing.assert_close(y.cpu(), y_ref, rtol=1e-5, atol=1e-5)            # FFMA: fp32-exact
+    ws = torch.empty(ops.conv_c1_wgrad_workspace_bytes(desc) // 4 + 4, device=DEV)
+    dw, db = torch.empty_like(cu(wgt)), torch.empty(cout, device=DEV)
+    ops.conv_c1_wgrad(desc, cu(x), cu(dy), ws, dw, db)
+    dw_ref, db_ref = torch.empty_like(wgt), torch.empty(cout)
+    ref.conv_c1_wgrad(desc, x, dy, None, dw_ref, db_ref)
+    torch.testing.assert_close(dw.cpu(), dw_ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db.cpu(), db_ref, rtol=1e-4, atol=1e-4)
