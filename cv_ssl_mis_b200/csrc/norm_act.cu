@@ -109,28 +109,34 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- finalize forward statistics
-// one warp per channel: lanes stride over the per-block partials (fixed order -> deterministic)
+// one 256-thread block per channel: every thread takes <= 3 of the per-block partials, so the dependent-load depth
+// is ~3 instead of nblk/32 (these finalize kernels were 10 us each -- pure latency -- with a warp per channel);
+// fixed summation order -> deterministic.  Valid in thread 0 after the call.
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblk, int C, int c, double& s0,
                                                 double& s1) {
-    const int lane = threadIdx.x & 31;
+    __shared__ double sh[2][8];
     double a = 0, b = 0;
-    for (int k = lane; k < nblk; k += 32) {
+    for (int k = threadIdx.x; k < nblk; k += 256) {
         a += part[(size_t)k * 2 * C + c];
         b += part[(size_t)k * 2 * C + C + c];
     }
-    s0 = warp_sum_d(a);
-    s1 = warp_sum_d(b);
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    s0 = s1 = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) { s0 += sh[0][w]; s1 += sh[1][w]; }
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ state) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
+    const int c = blockIdx.x;
     double s, ss;
     reduce_partials(part, nblk, C, c, s, ss);
-    if ((threadIdx.x & 31) == 0) {
+    if (threadIdx.x == 0) {
         const double mean = s / (double)M;
         double var = ss / (double)M - mean * mean;
         if (var < 0) var = 0;
@@ -166,11 +172,10 @@ __global__ void bn_eval_state_kernel(int C, const float* __restrict__ gamma, con
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, long long M, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ coef) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
+    const int c = blockIdx.x;
     double s, sx;
     reduce_partials(part, nblk, C, c, s, sx);
-    if ((threadIdx.x & 31) == 0) {
+    if (threadIdx.x == 0) {
         if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
         if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
         coef[c] = (float)(s / (double)M);
@@ -297,7 +302,7 @@ B200_API int b200_bn_stats_fwd(const float* y, long long M, int C, const float* 
     const size_t smem = (size_t)RP * 2 * C * sizeof(double);
     bn_reduce_kernel<0><<<grid, 256, smem, st>>>(y, nullptr, nullptr, M, C, 0.f, 0.f, 0, 0ull, 0u, 1, part, nullptr);
     B200_CHECK_LAUNCH("bn_stats_fwd");
-    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, grid, M, C, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_kernel<<<C, 256, 0, st>>>(part, grid, M, C, gamma, beta, eps, momentum, running_mean,
                                                         running_var, state);
     B200_CHECK_LAUNCH("bn_finalize");
     return B200_OK;
@@ -342,7 +347,7 @@ B200_API int b200_bn_act_bwd(const float* y, const float* da, const float* state
     const size_t smem = (size_t)RP * 2 * C * sizeof(double);
     bn_reduce_kernel<1><<<grid, 256, smem, st>>>(y, da, state, M, C, slope, p_drop, drop_mode, seed, stream, spatial, part, seed_offset_dev);
     B200_CHECK_LAUNCH("bn_act_bwd_reduce");
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, grid, M, C, dgamma, dbeta, accumulate, coef);
+    bn_bwd_finalize_kernel<<<C, 256, 0, st>>>(part, grid, M, C, dgamma, dbeta, accumulate, coef);
     B200_CHECK_LAUNCH("bn_bwd_finalize");
     const long long total4 = M * (C >> 2);
     bn_act_bwd_kernel<<<ew_grid(total4), 256, 0, st>>>(y, da, state, coef, dy, total4, C, slope, p_drop, drop_mode, seed,
