@@ -9,7 +9,7 @@
 // ---------------------------------------------------------------------------------------------------- batched packing
 // job layout (8 x int64): [0] src ptr [1] dst ptr [2] kind (0 generic, 1 tile, 2 umma) [3] mode (generic pack mode or
 // dgrad flag) [4] O [5] I [6] T [7] total output floats
-__device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind, int mode, int O, int I, int T, long long idx) {
+__device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind, int mode, int O, int I, int T, int idx) {
     if (kind == 0) {
         int rows, cols;
         switch (mode) {
@@ -21,7 +21,7 @@ __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind
         }
         (void)rows;
         const int ldn = (cols + 3) / 4 * 4;
-        const int r = (int)(idx / ldn), c = (int)(idx % ldn);
+        const int r = idx / ldn, c = idx % ldn;
         if (c >= cols) return 0.f;
         switch (mode) {
             case B200_PACK_CONV_FWD: { int tap = r / I, i = r % I; return w[((size_t)c * I + i) * T + tap]; }
@@ -36,18 +36,18 @@ __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind
     const int colsP = (cols + 15) / 16 * 16;
     int row, col, tap;
     if (kind == 1) {            // [chunk][tap][colsP][16]
-        const int kk = (int)(idx % 16);
-        long long r = idx / 16;
-        col = (int)(r % colsP); r /= colsP;
-        tap = (int)(r % T);
-        row = (int)(r / T) * 16 + kk;
+        const int kk = idx & 15;
+        int r = idx >> 4;
+        col = r % colsP; r /= colsP;
+        tap = r % T;
+        row = (r / T) * 16 + kk;
     } else {                    // [chunk][tap][kq][colsP][4]
-        const int j = (int)(idx & 3);
-        long long r = idx >> 2;
-        col = (int)(r % colsP); r /= colsP;
-        const int kq = (int)(r & 3); r >>= 2;
-        tap = (int)(r % T);
-        row = (int)(r / T) * 16 + kq * 4 + j;
+        const int j = idx & 3;
+        int r = idx >> 2;
+        col = r % colsP; r /= colsP;
+        const int kq = r & 3; r >>= 2;
+        tap = r % T;
+        row = (r / T) * 16 + kq * 4 + j;
     }
     if (row >= rows || col >= cols) return 0.f;
     const float v = dgrad ? w[((size_t)row * I + col) * T + (T - 1 - tap)] : w[((size_t)col * I + row) * T + tap];
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const long long* __rest
     const float* w = reinterpret_cast<const float*>(j[0]);
     float* out = reinterpret_cast<float*>(j[1]);
     const int kind = (int)j[2], mode = (int)j[3], O = (int)j[4], I = (int)j[5], T = (int)j[6];
-    const long long total = j[7];
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    const int total = (int)j[7];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
         out[idx] = pack_elem(w, kind, mode, O, I, T, idx);
 }
 
@@ -128,23 +128,26 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const C1P p) {
     }
 }
 
-// dw[co][tap] = sum_pixels dy[p][co] * x[p + tap]; threads = (pixel lane, co); deterministic two-stage reduction
+// dw[co][tap] = sum_pixels dy[p][co] * x[p + tap].  Thread = (pixel lane, group of 4 output channels): one 16-byte dy
+// load and T cached x loads feed 4T FMAs per pixel; deterministic two-stage reduction (block partials, then the
+// generic split reducer).
 template <int COUT, int KD>
 __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const C1P p) {
-    constexpr int T = KD * 9, PL = 256 / COUT;
-    __shared__ float red[256];
-    const int co = threadIdx.x % COUT, pl = threadIdx.x / COUT;
-    float acc[T], cs = 0.f;
+    constexpr int T = KD * 9, CQ = COUT / 4, PL = 256 / CQ;
+    extern __shared__ float red[];                         // [PL][T + 1][COUT] would be too big: reduce tap by tap
+    const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
+    float acc[T][4], cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int t = 0; t < T; ++t) acc[t] = 0.f;
+    for (int t = 0; t < T; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+#pragma unroll 2
     for (long long m = (long long)blockIdx.x * PL + pl; m < p.M; m += (long long)gridDim.x * PL) {
         long long r = m;
         const int w = (int)(r % p.W); r /= p.W;
         const int h = (int)(r % p.H); r /= p.H;
         const int d = (int)(r % p.D);
         const long long n = r / p.D;
-        const float g = __ldg(p.dy + m * COUT + co);
-        cs += g;
+        const float4 g = ldg4_stream(p.dy + m * COUT + cq * 4);
+        cs[0] += g.x; cs[1] += g.y; cs[2] += g.z; cs[3] += g.w;
 #pragma unroll
         for (int kd = 0; kd < KD; ++kd)
 #pragma unroll
@@ -154,14 +157,17 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const C1P p) {
                     const int id = d + kd - (KD == 3 ? 1 : 0), ih = h + kh - 1, iw = w + kw - 1;
                     const bool ok = (unsigned)id < (unsigned)p.D && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
                     const float xv = ok ? __ldg(p.x + ((n * p.D + id) * p.H + ih) * p.W + iw) : 0.f;
-                    acc[(kd * 3 + kh) * 3 + kw] = fmaf(g, xv, acc[(kd * 3 + kh) * 3 + kw]);
+                    const int t = (kd * 3 + kh) * 3 + kw;
+                    acc[t][0] = fmaf(g.x, xv, acc[t][0]); acc[t][1] = fmaf(g.y, xv, acc[t][1]);
+                    acc[t][2] = fmaf(g.z, xv, acc[t][2]); acc[t][3] = fmaf(g.w, xv, acc[t][3]);
                 }
     }
     float* out = p.part + (size_t)blockIdx.x * T * COUT;
-#pragma unroll 1
-    for (int t = 0; t <= T; ++t) {
+#pragma unroll
+    for (int t = 0; t <= T; ++t) {                         // fully unrolled: acc[] stays in registers
         __syncthreads();
-        red[threadIdx.x] = t < T ? acc[t] : cs;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red[pl * COUT + cq * 4 + e] = t < T ? acc[t < T ? t : 0][e] : cs[e];
         __syncthreads();
         if (threadIdx.x < COUT) {
             float v = 0.f;
@@ -225,10 +231,11 @@ B200_API int b200_conv_c1_wgrad(const b200_conv_desc* d, const float* x, const f
     const int T = d->kd * 9, grid = c1_wg_blocks();
     p.x = x; p.dy = dy; p.part = workspace;
     p.part_colsum = db ? workspace + (size_t)grid * T * d->cout : nullptr;
-    if (d->cout == 16 && d->kd == 1) conv_c1_wgrad_kernel<16, 1><<<grid, 256, 0, st>>>(p);
-    else if (d->cout == 32 && d->kd == 1) conv_c1_wgrad_kernel<32, 1><<<grid, 256, 0, st>>>(p);
-    else if (d->cout == 16) conv_c1_wgrad_kernel<16, 3><<<grid, 256, 0, st>>>(p);
-    else conv_c1_wgrad_kernel<32, 3><<<grid, 256, 0, st>>>(p);
+    const size_t smem = (size_t)(256 / (d->cout / 4)) * d->cout * sizeof(float);      // [PL][COUT]
+    if (d->cout == 16 && d->kd == 1) conv_c1_wgrad_kernel<16, 1><<<grid, 256, smem, st>>>(p);
+    else if (d->cout == 32 && d->kd == 1) conv_c1_wgrad_kernel<32, 1><<<grid, 256, smem, st>>>(p);
+    else if (d->cout == 16) conv_c1_wgrad_kernel<16, 3><<<grid, 256, smem, st>>>(p);
+    else conv_c1_wgrad_kernel<32, 3><<<grid, 256, smem, st>>>(p);
     B200_CHECK_LAUNCH("conv_c1_wgrad");
     // partial layout [split][k = tap (Cin = 1)][Cout] == the generic reducer's [splits][K][NG] with A = 1
     return b200_wgrad_reduce_launch(p.part, p.part_colsum, grid, T, d->cout, 1, T, dw, db, accumulate, st);

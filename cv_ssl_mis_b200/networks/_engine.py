@@ -247,4 +247,4 @@ class PackTable:
         # parameters may have been re-homed (e.g. .cuda() after planning): the table stores raw pointers
         assert self.ptrs == [w.data_ptr() for (w, *_r) in self.jobs_py], "parameters moved after planning"
         _lib.tag = "pack"
-        ops.conv_pack_batch(self.table, len(self.jobs_py), 16, self.jobs_py)
+        ops.conv_pack_batch(self.table, len(self.jobs_py), 48, self.jobs_py)
