@@ -90,6 +90,20 @@ SIGNATURES = {
     "b200_ssl_loss_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P, _P, _L, _S]),
     "b200_ssl_loss_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _F, _P, _P, _F, _P, _I, _S]),
     "b200_mc_softmax_accumulate": (_I, [_P, _P, _I, _I, _I, _L, _I, _I, _S]),
+    "b200_ct_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
+    "b200_ct_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _F, _P, _I, _S]),
+    "b200_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
+    "b200_layernorm_workspace_bytes": (_L, [_L, _I]),
+    "b200_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _S]),
+    "b200_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _L, _S]),
+    "b200_gelu_fwd": (_I, [_P, _P, _L, _S]),
+    "b200_gelu_bwd": (_I, [_P, _P, _P, _L, _I, _S]),
+    "b200_window_attn_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "b200_window_attn_workspace_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "b200_window_attn_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _L, _S]),
+    "b200_add_droppath": (_I, [_P, _P, _P, _I, _L, _F, _U64, _P, _U32, _S]),
+    "b200_patch_merge_gather": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
+    "b200_patch_embed_gather": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
     "b200_sgd_ema_step": (_I, [_P, _P, _P, _P, _L, _P, _I, _S]),
     "b200_ema_update": (_I, [_P, _P, _L, _P, _S]),
     "b200_noise_add": (_I, [_P, _P, _L, _F, _F, _U64, _P, _U32, _S]),

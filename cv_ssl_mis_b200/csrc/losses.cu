@@ -25,6 +25,10 @@ struct LossGeom {
     const float* mc_psum;
     float mc_T;
     const float* mc_thr;    // DEVICE scalar: entropy threshold
+    // cross-teaching variant (code/train_cross_teaching_between_cnn_transformer_2D.py:238-246): `teacher` holds the OTHER
+    // model's logits for all B samples (its own layout); the unlabeled term is Dice against their argmax
+    int pseudo;
+    int teacher_nhwc;
 };
 
 // mask = [ -sum_c pbar_c log(pbar_c + 1e-6) < thr ],  pbar = psum / T
@@ -81,12 +85,22 @@ __device__ __forceinline__ int load_label(const void* labels, int i64, long long
     return i64 ? (int)reinterpret_cast<const long long*>(labels)[idx] : (int)reinterpret_cast<const unsigned char*>(labels)[idx];
 }
 
-// accumulators per block: [0] ce, [1] mse, [2..2+C) I_c, [2+C..) Z_c, [2+2C..) Y_c, [2+3C] mask count
+// accumulators per block: [0] ce, [1] mse, [2..2+C) I_c, [2+C..) Z_c, [2+2C..) Y_c, [2+3C] mask count,
+// pseudo-label mode only: [3+3C..) I'_c, [3+4C..) Z'_c, [3+5C..) Y'_c over the unlabeled samples
 #define SSL_NACC(C) (3 + 3 * (C))
+#define SSL_NACC_PSEUDO(C) (3 + 6 * (C))
 
 template <int C>
+__device__ __forceinline__ int argmax_first(const float (&q)[C]) {
+    int t = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c) t = q[c] > q[t] ? c : t;
+    return t;
+}
+
+template <int C, int PSEUDO>
 __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, double* __restrict__ part) {
-    constexpr int NA = SSL_NACC(C);
+    constexpr int NA = PSEUDO ? SSL_NACC_PSEUDO(C) : SSL_NACC(C);
     float acc[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.f;
@@ -109,6 +123,20 @@ __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, dou
                     acc[0] += lse - raw[c];
                     acc[2 + c] += p[c];
                     acc[2 + 2 * C + c] += 1.f;
+                }
+            }
+        } else if (PSEUDO) {
+            float q[C];
+            load_logits<C>(g.teacher, g.teacher_nhwc, n, s, g.S, g.C, q);
+            float lse2;
+            softmax_inplace<C>(q, lse2);
+            const int t = argmax_first<C>(q);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                acc[(PSEUDO ? 3 + 4 * C : 0) + c] += p[c] * p[c];
+                if (c == t) {
+                    acc[(PSEUDO ? 3 + 3 * C : 0) + c] += p[c];
+                    acc[(PSEUDO ? 3 + 5 * C : 0) + c] += 1.f;
                 }
             }
         } else if (g.teacher) {
@@ -141,19 +169,33 @@ __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, dou
     }
 }
 
+// batch Dice over one accumulator triple; writes the gradient coefficients A_c, B_c scaled by `gw`
+__device__ double dice_from_sums(const double* I, const double* Z, const double* Y, int C, double gw, float* A, float* Bc) {
+    const double smooth = 1e-5;
+    double dsum = 0;
+    for (int c = 0; c < C; ++c) {
+        const double D = Z[c] + Y[c] + smooth;
+        dsum += 1.0 - (2.0 * I[c] + smooth) / D;
+        A[c] = (float)(gw * 2.0 * (2.0 * I[c] + smooth) / ((double)C * D * D));
+        Bc[c] = (float)(gw * 2.0 / ((double)C * D));
+    }
+    return dsum / (double)C;
+}
+
 // out: [0] ce  [1] dice  [2] cons  [3] total  [4..4+C) A_c  [4+C..4+2C) B_c  [4+2C] d(cons)/d(p) scale
-//      (A/B = dice-gradient coefficients)
+//      (A/B = dice-gradient coefficients); pseudo-label mode: [2] = Dice against the pseudo labels and
+//      [5+2C..5+3C) A'_c, [5+3C..5+4C) B'_c = its gradient coefficients, already multiplied by w
 __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nblk, int Cpad, int C, int Lb, int U,
-                                         long long S, int has_teacher, int mc_mode, const float* __restrict__ w_cons,
-                                         float* __restrict__ out) {
-    __shared__ double tot[SSL_NACC(SSL_MAXC)];
-    const int NA = SSL_NACC(Cpad);
+                                         long long S, int has_teacher, int mc_mode, int pseudo,
+                                         const float* __restrict__ w_cons, float* __restrict__ out) {
+    __shared__ double tot[SSL_NACC_PSEUDO(SSL_MAXC)];
+    const int NA = pseudo ? SSL_NACC_PSEUDO(Cpad) : SSL_NACC(Cpad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;      // one warp per accumulator
-    if (warp < NA) {
+    for (int a = warp; a < NA; a += 32) {
         double s = 0;
-        for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * NA + warp];
+        for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * NA + a];
         s = warp_sum_d(s);
-        if (lane == 0) tot[warp] = s;
+        if (lane == 0) tot[a] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -175,7 +217,13 @@ __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nb
         }
         const float w = w_cons ? w_cons[0] : 0.f;
         float dscale = 0.f;
-        if (has_teacher && U > 0) {
+        if (pseudo) {
+            if (U > 0)
+                cons = (float)dice_from_sums(tot + 3 + 3 * Cpad, tot + 3 + 4 * Cpad, tot + 3 + 5 * Cpad, C, (double)w,
+                                             out + 5 + 2 * C, out + 5 + 3 * C);
+            else
+                for (int c = 0; c < 2 * C; ++c) out[5 + 2 * C + c] = 0.f;
+        } else if (has_teacher && U > 0) {
             // mean over all elements (MT) or sum(mask * dist) / (2 sum(mask) + 1e-16) (UAMT: the reference divides by
             // 2 * sum(mask) whatever the class count)
             const double denom = mc_mode ? 2.0 * tot[2 + 3 * Cpad] + 1e-16 : (double)U * (double)C * (double)S;
@@ -190,18 +238,20 @@ __global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nb
     }
 }
 
-template <int C>
+template <int C, int PSEUDO>
 __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, const float* __restrict__ lossbuf,
                                                            const float* __restrict__ w_cons, float gscale,
                                                            float* __restrict__ dlogits, int out_nhwc) {
-    float A[C], Bc[C];
+    float A[C], Bc[C], A2[C], B2[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         A[c] = c < g.C ? lossbuf[4 + c] : 0.f;
         Bc[c] = c < g.C ? lossbuf[4 + g.C + c] : 0.f;
+        A2[c] = PSEUDO && c < g.C ? lossbuf[5 + 2 * g.C + c] : 0.f;
+        B2[c] = PSEUDO && c < g.C ? lossbuf[5 + 3 * g.C + c] : 0.f;
     }
     const float ce_scale = g.Lb > 0 ? 1.f / ((float)g.Lb * (float)g.S) : 0.f;
-    const float mse_scale = g.teacher ? lossbuf[4 + 2 * g.C] : 0.f;
+    const float mse_scale = g.teacher && !PSEUDO ? lossbuf[4 + 2 * g.C] : 0.f;
     const long long total = (long long)g.B * g.S;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long n = idx / g.S, s = idx - n * g.S;
@@ -220,6 +270,20 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
 #pragma unroll
             for (int c = 0; c < C; ++c)
                 dz[c] = 0.5f * gscale * (p[c] * (gd[c] - dot) + (p[c] - (c == t ? 1.f : 0.f)) * ce_scale);
+        } else if (PSEUDO) {
+            float q[C];
+            load_logits<C>(g.teacher, g.teacher_nhwc, n, s, g.S, g.C, q);
+            float lse2;
+            softmax_inplace<C>(q, lse2);
+            const int t = argmax_first<C>(q);
+            float gd[C], dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                gd[c] = A2[c] * p[c] - (c == t ? B2[c] : 0.f);
+                dot += gd[c] * p[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) dz[c] = gscale * p[c] * (gd[c] - dot);
         } else if (g.teacher && mse_scale != 0.f && (g.mc_psum == nullptr || mc_mask<C>(g, n - g.Lb, s))) {
             float q[C];
             load_logits<C>(g.teacher, g.nhwc, n - g.Lb, s, g.S, g.C, q);
@@ -259,7 +323,7 @@ static inline int loss_grid(long long total) {
 static inline int cpad_of(int C) { return C <= 2 ? 2 : (C <= 4 ? 4 : SSL_MAXC); }
 
 B200_API long long b200_ssl_loss_workspace_bytes(int B, long long S) {
-    return (long long)loss_grid((long long)B * S) * SSL_NACC(SSL_MAXC) * sizeof(double);
+    return (long long)loss_grid((long long)B * S) * SSL_NACC_PSEUDO(SSL_MAXC) * sizeof(double);
 }
 
 static int fill_geom(LossGeom& g, const float* logits, const float* teacher, const void* labels, int label_dtype,
@@ -276,7 +340,22 @@ static int fill_geom(LossGeom& g, const float* logits, const float* teacher, con
     B200_REQUIRE(mc_psum == nullptr || (teacher != nullptr && mc_thr != nullptr && mc_T > 0.f),
                  "%s: the uncertainty mask needs teacher logits, a threshold and T > 0", who);
     g.mc_psum = mc_psum; g.mc_T = mc_T; g.mc_thr = mc_thr;
+    g.pseudo = 0; g.teacher_nhwc = layout_nhwc;
     return B200_OK;
+}
+
+template <int PSEUDO>
+static void launch_loss_fwd(const LossGeom& g, int Cp, int grid, double* part, cudaStream_t st) {
+    if (Cp == 2) ssl_loss_fwd_kernel<2, PSEUDO><<<grid, 256, 0, st>>>(g, part);
+    else if (Cp == 4) ssl_loss_fwd_kernel<4, PSEUDO><<<grid, 256, 0, st>>>(g, part);
+    else ssl_loss_fwd_kernel<SSL_MAXC, PSEUDO><<<grid, 256, 0, st>>>(g, part);
+}
+template <int PSEUDO>
+static void launch_loss_bwd(const LossGeom& g, int Cp, int grid, const float* lossbuf, const float* w_cons, float gs,
+                            float* dlogits, int dl_nhwc, cudaStream_t st) {
+    if (Cp == 2) ssl_loss_bwd_kernel<2, PSEUDO><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, gs, dlogits, dl_nhwc);
+    else if (Cp == 4) ssl_loss_bwd_kernel<4, PSEUDO><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, gs, dlogits, dl_nhwc);
+    else ssl_loss_bwd_kernel<SSL_MAXC, PSEUDO><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, gs, dlogits, dl_nhwc);
 }
 
 B200_API int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits, const void* labels, int label_dtype,
@@ -291,12 +370,10 @@ B200_API int b200_ssl_loss_fwd(const float* logits, const float* teacher_logits,
     const int grid = loss_grid((long long)B * S);
     double* part = reinterpret_cast<double*>(workspace);
     const int Cp = cpad_of(C);
-    if (Cp == 2) ssl_loss_fwd_kernel<2><<<grid, 256, 0, st>>>(g, part);
-    else if (Cp == 4) ssl_loss_fwd_kernel<4><<<grid, 256, 0, st>>>(g, part);
-    else ssl_loss_fwd_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(g, part);
+    launch_loss_fwd<0>(g, Cp, grid, part, st);
     B200_CHECK_LAUNCH("ssl_loss_fwd");
     ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(part, grid, Cp, C, Lb, B - Lb, S, teacher_logits != nullptr, mc_psum != nullptr,
-                                                 w_cons, lossbuf);
+                                                 0, w_cons, lossbuf);
     B200_CHECK_LAUNCH("ssl_loss_finalize");
     return B200_OK;
 }
@@ -311,10 +388,43 @@ B200_API int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits,
     B200_REQUIRE(lossbuf && dlogits, "ssl_loss_bwd: null pointer");
     const int grid = loss_grid((long long)B * S);
     const int Cp = cpad_of(C);
-    if (Cp == 2) ssl_loss_bwd_kernel<2><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc);
-    else if (Cp == 4) ssl_loss_bwd_kernel<4><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc);
-    else ssl_loss_bwd_kernel<SSL_MAXC><<<grid, 256, 0, st>>>(g, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc);
+    launch_loss_bwd<0>(g, Cp, grid, lossbuf, w_cons, grad_scale, dlogits, dlogits_nhwc, st);
     B200_CHECK_LAUNCH("ssl_loss_bwd");
+    return B200_OK;
+}
+
+// Cross-teaching loss of ONE model (code/train_cross_teaching_between_cnn_transformer_2D.py:229-247):
+//   0.5 (CE + Dice)(logits[:Lb], y) + w * Dice(softmax(logits[Lb:]), argmax softmax(other[Lb:]))
+// lossbuf (>= 5 + 4C floats): [0] ce [1] dice [2] pseudo-label dice [3] total, then gradient coefficients
+B200_API int b200_ct_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                              const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* w_cons,
+                              float* lossbuf, void* workspace, long long workspace_bytes, cudaStream_t st) {
+    LossGeom g;
+    if (int rc = fill_geom(g, logits, other_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, nullptr, 0.f, nullptr,
+                           "ct_loss_fwd")) return rc;
+    B200_REQUIRE(other_logits && lossbuf && workspace && w_cons, "ct_loss_fwd: null pointer");
+    B200_REQUIRE(workspace_bytes >= b200_ssl_loss_workspace_bytes(B, S), "ct_loss_fwd: workspace too small");
+    g.pseudo = 1; g.teacher_nhwc = other_nhwc;
+    const int grid = loss_grid((long long)B * S);
+    const int Cp = cpad_of(C);
+    launch_loss_fwd<1>(g, Cp, grid, reinterpret_cast<double*>(workspace), st);
+    B200_CHECK_LAUNCH("ct_loss_fwd");
+    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<double*>(workspace), grid, Cp, C, Lb, B - Lb, S, 1, 0, 1, w_cons,
+                                                 lossbuf);
+    B200_CHECK_LAUNCH("ct_loss_finalize");
+    return B200_OK;
+}
+
+B200_API int b200_ct_loss_bwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                              const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf,
+                              float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
+    LossGeom g;
+    if (int rc = fill_geom(g, logits, other_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, nullptr, 0.f, nullptr,
+                           "ct_loss_bwd")) return rc;
+    B200_REQUIRE(other_logits && lossbuf && dlogits, "ct_loss_bwd: null pointer");
+    g.pseudo = 1; g.teacher_nhwc = other_nhwc;
+    launch_loss_bwd<1>(g, cpad_of(C), loss_grid((long long)B * S), lossbuf, nullptr, grad_scale, dlogits, dlogits_nhwc, st);
+    B200_CHECK_LAUNCH("ct_loss_bwd");
     return B200_OK;
 }
 

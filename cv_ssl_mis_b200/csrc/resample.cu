@@ -216,10 +216,10 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, in
 }
 
 // c = a + b (VNet additive skips, code/networks/vnet.py:210,214,218,222)
-__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                  float* __restrict__ c, long long total4) {
+// c may alias a (in-place accumulate of a gradient), so a / c carry no __restrict__
+__global__ void __launch_bounds__(256) add_kernel(const float* a, const float* __restrict__ b, float* c, long long total4) {
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
-        const float4 x = ldg4(a + q * 4), y = ldg4(b + q * 4);
+        const float4 x = *reinterpret_cast<const float4*>(a + q * 4), y = ldg4(b + q * 4);
         stg4(c + q * 4, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w));
     }
 }

@@ -114,6 +114,10 @@ class UNetPlan:
     def logits(self):            # [B, C, H*W] view of the head output (NCHW)
         return self.head.y
 
+    @property
+    def g_logits(self):          # channels-last d(loss)/d(logits), [B*H*W, C]
+        return self.head.g
+
     def forward(self, x, train=True):
         """x: [B,1,H,W] (== channels-last for one channel) or [B*H*W, in_chns] channels-last."""
         rt, B = self.rt, self.B

@@ -247,6 +247,57 @@ def add(a, b, c):
     _lib.call("b200_add", _pf(a), _pf(b), _pf(c), a.numel(), _st())
 
 
+# ------------------------------------------------------------------ Swin-UNet token ops
+def layernorm_workspace_bytes(M, C_) -> int:
+    return int(_lib.query("b200_layernorm_workspace_bytes", M, C_))
+
+
+def layernorm_fwd(x, gamma, beta, y, stats, M, C_, eps=1e-5):
+    _lib.call("b200_layernorm_fwd", _pf(x), _pf(gamma), _pf(beta), _pf(y), _pf(stats), M, C_, eps, _st())
+
+
+def layernorm_bwd(x, stats, gamma, dy, dx, dgamma, dbeta, M, C_, ws, accumulate_dx=False):
+    _lib.call("b200_layernorm_bwd", _pf(x), _pf(stats), _pf(gamma), _pf(dy), _pf(dx), _pf(dgamma), _pf(dbeta),
+              int(accumulate_dx), M, C_, _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def gelu_fwd(x, y):
+    _lib.call("b200_gelu_fwd", _pf(x), _pf(y), x.numel(), _st())
+
+
+def gelu_bwd(x, dy, dx, accumulate=False):
+    _lib.call("b200_gelu_bwd", _pf(x), _pf(dy), _pf(dx), x.numel(), int(accumulate), _st())
+
+
+def window_attn_fwd(qkv, table, out, B, H, W, C_, heads, ws, shift):
+    _lib.call("b200_window_attn_fwd", _pf(qkv), _pf(table), _pf(out), B, H, W, C_, heads, ws, shift, _st())
+
+
+def window_attn_workspace_bytes(B, H, W, heads, ws) -> int:
+    return int(_lib.query("b200_window_attn_workspace_bytes", B, H, W, heads, ws))
+
+
+def window_attn_bwd(qkv, table, dout, dqkv, dtable, B, H, W, C_, heads, ws, shift, wsp):
+    _lib.call("b200_window_attn_bwd", _pf(qkv), _pf(table), _pf(dout), _pf(dqkv), _pf(dtable), B, H, W, C_, heads, ws, shift,
+              _p(wsp), wsp.numel() * wsp.element_size(), _st())
+
+
+def add_droppath(x, branch, out, B, per_sample, p_drop=0.0, seed=0, seed_off=None, rng_stream=0):
+    _lib.call("b200_add_droppath", _pf(x), _pf(branch), _pf(out), B, per_sample, p_drop, seed, _p(seed_off), rng_stream, _st())
+
+
+def patch_merge_gather(x, y, B, H, W, C_, inverse=False, accumulate=False):
+    _lib.call("b200_patch_merge_gather", _pf(x), _pf(y), B, H, W, C_, int(inverse), int(accumulate), _st())
+
+
+def pixel_shuffle(x, y, B, H, W, C_, p, inverse=False):
+    _lib.call("b200_pixel_shuffle", _pf(x), _pf(y), B, H, W, C_, p, int(inverse), _st())
+
+
+def patch_embed_gather(x, y, B, H, W, patch, repeat_channels):
+    _lib.call("b200_patch_embed_gather", _pf(x), _pf(y), B, H, W, patch, repeat_channels, _st())
+
+
 # ------------------------------------------------------------------ loss / optimizer / noise
 def _label_dtype(labels):
     if labels is None:
@@ -272,6 +323,16 @@ def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C_, S, w_cons, lossbuf, g
     _lib.call("b200_ssl_loss_bwd", _pf(logits), _pf(teacher), _p(labels), _label_dtype(labels), int(nhwc), B, Lb, C_, S,
               _pf(w_cons), _pf(mc_psum), float(mc_T), _pf(mc_thr), _pf(lossbuf), grad_scale, _pf(dlogits),
               int(dlogits_nhwc), _st())
+
+
+def ct_loss_fwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C_, S, w_cons, lossbuf, ws):
+    _lib.call("b200_ct_loss_fwd", _pf(logits), int(nhwc), _pf(other), int(other_nhwc), _p(labels), _label_dtype(labels), B, Lb,
+              C_, S, _pf(w_cons), _pf(lossbuf), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def ct_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C_, S, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+    _lib.call("b200_ct_loss_bwd", _pf(logits), int(nhwc), _pf(other), int(other_nhwc), _p(labels), _label_dtype(labels), B, Lb,
+              C_, S, _pf(lossbuf), grad_scale, _pf(dlogits), int(dlogits_nhwc), _st())
 
 
 def mc_softmax_accumulate(logits, psum, R, U, C_, S, nhwc=False, init=True):

@@ -1,5 +1,7 @@
 """Fused training steps: the inner loops of the reference trainers as fixed launch schedules.
 
+`CrossTeachingTrainer` is the CNN <-> Transformer iteration of
+code/train_cross_teaching_between_cnn_transformer_2D.py:221-262 (two students, no EMA).
 `MeanTeacherTrainer` covers, with one schedule,
   * Mean Teacher 2D/3D            code/train_mean_teacher_2D.py:201-238, code/train_mean_teacher_3D.py:134-166
   * Uncertainty-Aware Mean Teacher code/train_uncertainty_aware_mean_teacher_3D.py:135-189 (2D twin: ..._2D.py:147-201)
@@ -187,3 +189,123 @@ class MeanTeacherTrainer:
     def _all_buffers(self):
         mods = [self.model] + ([self.ema_model] if self.ema_model is not None else [])
         return [b for m in mods for b in m.buffers() if b.dtype.is_floating_point]
+
+
+def _plan_for(model, B, patch, need_grad):
+    """UNet-style plans are keyed by (B, H, W), the Swin-UNet's by B alone (its token grid is fixed by its config)."""
+    if getattr(model, "plan_key_is_batch", False):
+        return model._get_plan(B, need_grad)
+    return model._get_plan(B, *patch, need_grad)
+
+
+class CrossTeachingTrainer:
+    """Cross Teaching between CNN and Transformer (code/train_cross_teaching_between_cnn_transformer_2D.py:221-262).
+
+    Per iteration: both models see the whole batch; each is trained with 0.5 (CE + Dice) on the labeled half plus
+    w * Dice against the argmax pseudo labels of the OTHER model on the unlabeled half; two independent SGD steps.
+    The reference bumps iter_num before recomputing the poly LR (:257-259), so iteration k runs with poly_lr(k)."""
+
+    def __init__(self, model1, model2, *, batch_size=16, labeled_bs=8, patch_size=(224, 224), num_classes=4, base_lr=0.01,
+                 max_iterations=30000, consistency=0.1, consistency_rampup=200.0, momentum=0.9, weight_decay=1e-4,
+                 start_iter=0, label_dtype=torch.uint8, process_group=None, use_cuda_graph=False):
+        self.models = (model1, model2)
+        self.B, self.Lb, self.patch, self.C = batch_size, labeled_bs, tuple(patch_size), num_classes
+        self.base_lr, self.max_iterations = base_lr, max_iterations
+        self.consistency, self.consistency_rampup = consistency, consistency_rampup
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.iter_num = start_iter
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.flats = [m.materialize() for m in self.models]
+        dev = self.dev = self.flats[0].data.device
+        self.momentum_bufs = [torch.zeros_like(f.data) for f in self.flats]
+        self.offs = [m._rt.seed_off for m in self.models]
+        pin = dev.type == "cuda"
+        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if pin else torch.zeros(8)
+        self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.S = self.patch[0] * self.patch[1]
+        self.x = torch.empty((self.B, 1, *self.patch), dtype=torch.float32, device=dev)
+        self.y = torch.empty((self.B, *self.patch), dtype=label_dtype, device=dev)
+        # per model: [ce, dice, pseudo-label dice, total, coefficients...]
+        self.lossbufs = [torch.zeros(40, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory() if pin else torch.zeros(8)
+        self.loss_ws = torch.empty(ops.ssl_loss_workspace_bytes(self.B, self.S) // 4 + 4, dtype=torch.float32, device=dev)
+        self.plans = [_plan_for(m, self.B, self.patch, True) for m in self.models]
+        self.lr = base_lr * (1.0 - start_iter / max_iterations) ** 0.9
+        self.use_graph = use_cuda_graph and dev.type == "cuda"
+        self.graph = None
+        self.kernel_launches_per_step = None
+
+    def consistency_weight(self, iter_num):
+        """:117-119 with the iter_num // 150 argument of :229-230 (no warm-up gate in this trainer)"""
+        return self.consistency * ramps.sigmoid_rampup(iter_num // 150, self.consistency_rampup)
+
+    def _set_hparams(self):
+        h = self.hp_host
+        h[HP_LR] = self.lr
+        h[HP_MOMENTUM] = self.momentum
+        h[HP_WD] = self.weight_decay
+        h[HP_ALPHA], h[HP_ONE_MINUS_ALPHA] = 1.0, 0.0
+        h[HP_GRAD_SCALE] = 1.0 / self.world
+        h[HP_WCONS] = self.consistency_weight(self.iter_num)
+        self.hp.copy_(h, non_blocking=True)
+
+    def _device_step(self):
+        for m, off in zip(self.models, self.offs):
+            off += 1
+            m.train()
+        p1, p2 = self.plans
+        p1.forward(self.x, train=True)                                     # :224-228
+        p2.forward(self.x, train=True)
+        w = self.hp[HP_WCONS:HP_WCONS + 1]
+        for mine, other, lb in ((p1, p2, self.lossbufs[0]), (p2, p1, self.lossbufs[1])):
+            ops.ct_loss_fwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, w, lb, self.loss_ws)
+            ops.ct_loss_bwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, lb, 1.0,
+                            mine.g_logits, True)
+        for plan, flat, mom in zip(self.plans, self.flats, self.momentum_bufs):
+            plan.backward(None)                                            # :252-255 (loss = model1_loss + model2_loss)
+            if self.world > 1:
+                torch.distributed.all_reduce(flat.grad, group=self.pg)
+            ops.sgd_ema_step(flat.data, flat.grad, mom, None, self.hp)     # :257-258
+
+    def step(self, images, labels, read_loss=False):
+        """images [B,1,H,W] float32, labels [B,H,W] uint8.  Returns the two device loss buffers, or with read_loss the
+        host floats [ce1, dice1, pseudo1, model1_loss, ce2, dice2, pseudo2, model2_loss]."""
+        self._set_hparams()
+        self.x.copy_(images, non_blocking=True)
+        self.y.copy_(labels, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._device_step()
+        self.iter_num += 1                                                 # :257
+        self.lr = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9    # :259
+        if read_loss:
+            self.loss_host[:4].copy_(self.lossbufs[0][:4], non_blocking=True)
+            self.loss_host[4:].copy_(self.lossbufs[1][:4], non_blocking=True)
+            torch.cuda.current_stream().synchronize() if self.dev.type == "cuda" else None
+            return self.loss_host.tolist()
+        return self.lossbufs
+
+    def _state_tensors(self):
+        ts = [f.data for f in self.flats] + self.momentum_bufs + self.offs
+        return ts + [b for m in self.models for b in m.buffers() if b.dtype.is_floating_point]
+
+    def _capture(self):
+        keep = [t.clone() for t in self._state_tensors()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._device_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, k in zip(self._state_tensors(), keep):
+            t.copy_(k)
+        from . import _lib
+        n0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self._device_step()
+        self.kernel_launches_per_step = _lib.launch_count - n0

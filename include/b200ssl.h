@@ -178,6 +178,48 @@ int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits, const vo
 int b200_mc_softmax_accumulate(const float* logits, float* psum, int R, int U, int C, long long S, int layout_nhwc,
                                int init, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ Swin-UNet token ops
+ * code/networks/swin_transformer_unet_skip_expand_decoder_sys.py: nn.LayerNorm (:204,211,...), nn.GELU in Mlp (:19-25),
+ * WindowAttention + roll/partition/reverse of SwinTransformerBlock (:115-150,244-288), DropPath residual (:284-286),
+ * PatchMerging gather (:336-341), PatchEmbed im2col (:573).  Tokens are rows of [B*H*W][C] in natural order. */
+long long b200_layernorm_workspace_bytes(long long M, int C);
+int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, long long M, int C,
+                       float eps, cudaStream_t stream);
+int b200_layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, float* dx, float* dgamma,
+                       float* dbeta, int accumulate_dx, long long M, int C, float* workspace, long long workspace_bytes,
+                       cudaStream_t stream);
+int b200_gelu_fwd(const float* x, float* y, long long n, cudaStream_t stream);
+int b200_gelu_bwd(const float* x, const float* dy, float* dx, long long n, int accumulate, cudaStream_t stream);
+/* qkv [B*H*W][3C] (q | k | v, head-major inside each), head dim 32, window ws (ws*ws <= 49), cyclic shift `shift` */
+int b200_window_attn_fwd(const float* qkv, const float* bias_table, float* out, int B, int H, int W, int C, int heads,
+                         int ws, int shift, cudaStream_t stream);
+long long b200_window_attn_workspace_bytes(int B, int H, int W, int heads, int ws);
+int b200_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv, float* dbias_table,
+                         int B, int H, int W, int C, int heads, int ws, int shift, float* workspace,
+                         long long workspace_bytes, cudaStream_t stream);
+/* out = x + branch * keep[b] / (1 - p), keep ~ Bernoulli(1 - p) per sample (Philox); x may be NULL (treated as 0) */
+int b200_add_droppath(const float* x, const float* branch, float* out, int B, long long per_sample, float p_drop,
+                      unsigned long long seed, const unsigned long long* seed_offset_dev, unsigned rng_stream,
+                      cudaStream_t stream);
+/* inverse = 0: y[B][H/2][W/2][4C] gathered from x[B][H][W][C]; inverse = 1: x is the gathered gradient, y the input gradient */
+int b200_patch_merge_gather(const float* x, float* y, int B, int H, int W, int C, int inverse, int accumulate,
+                            cudaStream_t stream);
+/* PatchExpand rearrange 'b h w (p1 p2 c) -> b (h p1) (w p2) c' (…_sys.py:378-379,405-407): x [B][H][W][p*p*C] ->
+ * y [B][H*p][W*p][C]; inverse = 1 maps a gradient laid out like y back to x's layout */
+int b200_pixel_shuffle(const float* x, float* y, int B, int H, int W, int C, int p, int inverse, cudaStream_t stream);
+int b200_patch_embed_gather(const float* x, float* y, int B, int H, int W, int patch, int repeat_channels, cudaStream_t stream);
+
+/* Cross-teaching loss of ONE model (code/train_cross_teaching_between_cnn_transformer_2D.py:229-247):
+ *   0.5 (CE + Dice)(logits[:Lb], labels) + w * Dice(softmax(logits[Lb:]), argmax softmax(other_logits[Lb:]))
+ * other_logits holds all B samples of the other model in its own layout.  lossbuf (>= 5 + 4C floats):
+ * [0] ce [1] dice [2] pseudo-label dice [3] total, then the gradient coefficients read by b200_ct_loss_bwd. */
+int b200_ct_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc, const void* labels,
+                     int label_dtype, int B, int Lb, int C, long long S, const float* w_cons_dev, float* lossbuf,
+                     void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b200_ct_loss_bwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc, const void* labels,
+                     int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf, float grad_scale,
+                     float* dlogits, int dlogits_nhwc, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ optimizer / EMA / noise
  * optim.SGD + update_ema_variables + input noise: code/train_mean_teacher_2D.py:124-128,189-190,208-210,230-233
  * hparams_dev (DEVICE, 6 floats): [0] lr [1] momentum [2] weight_decay [3] ema_alpha [4] 1-ema_alpha [5] grad_scale */

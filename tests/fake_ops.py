@@ -409,6 +409,140 @@ def add(a, b, c):
     c.copy_(a + b)
 
 
+# ------------------------------------------------------------------ Swin-UNet token ops
+def layernorm_workspace_bytes(M, C):
+    return 64
+
+
+def layernorm_fwd(x, gamma, beta, y, stats, M, C, eps=1e-5):
+    v = x.reshape(M, C)
+    mean = v.mean(1, keepdim=True)
+    var = v.var(1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + eps)
+    y.copy_(((v - mean) * rstd * gamma.detach() + beta.detach()).reshape(y.shape))
+    if stats is not None:
+        stats.view(M, 2)[:, 0] = mean[:, 0]
+        stats.view(M, 2)[:, 1] = rstd[:, 0]
+
+
+def layernorm_bwd(x, stats, gamma, dy, dx, dgamma, dbeta, M, C, ws, accumulate_dx=False):
+    v, g = x.reshape(M, C), dy.reshape(M, C)
+    mean, rstd = stats.view(M, 2)[:, 0:1], stats.view(M, 2)[:, 1:2]
+    xh = (v - mean) * rstd
+    gg = g * gamma.detach()
+    r = rstd * (gg - gg.mean(1, keepdim=True) - xh * (gg * xh).mean(1, keepdim=True))
+    _store(dx, r, accumulate_dx)
+    dgamma.copy_((g * xh).sum(0))
+    dbeta.copy_(g.sum(0))
+
+
+def gelu_fwd(x, y):
+    y.copy_(F.gelu(x))
+
+
+def gelu_bwd(x, dy, dx, accumulate=False):
+    with torch.enable_grad():
+        xi = x.detach().clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(F.gelu(xi), xi, dy)
+    _store(dx, g, accumulate)
+
+
+def _window_attention(qkv, table, B, H, W, C, heads, ws, shift):
+    """Reference formulation (roll / partition / attention / reverse / roll) on a [B*H*W, 3C] qkv matrix."""
+    hd, N = C // heads, ws * ws
+    x = qkv.reshape(B, H, W, 3 * C)
+    if shift > 0:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    xw = x.view(B, H // ws, ws, W // ws, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = xw[0] * hd ** -0.5, xw[1], xw[2]
+    attn = q @ k.transpose(-2, -1)
+    ch = torch.arange(ws)
+    coords = torch.stack(torch.meshgrid([ch, ch], indexing="ij")).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0) + (ws - 1)
+    index = rel[:, :, 0] * (2 * ws - 1) + rel[:, :, 1]
+    attn = attn + table[index.view(-1)].view(N, N, heads).permute(2, 0, 1).unsqueeze(0)
+    if shift > 0:
+        img = torch.zeros(1, H, W, 1)
+        cnt = 0
+        for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                img[:, hs, wsl, :] = cnt
+                cnt += 1
+        mw = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, N)
+        am = mw.unsqueeze(1) - mw.unsqueeze(2)
+        am = am.masked_fill(am != 0, -100.0).masked_fill(am == 0, 0.0)
+        nW = am.shape[0]
+        attn = (attn.view(-1, nW, heads, N, N) + am.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
+    attn = attn.softmax(-1)
+    o = (attn @ v).transpose(1, 2).reshape(-1, ws, ws, C)
+    o = o.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    return o.reshape(B * H * W, C)
+
+
+def window_attn_fwd(qkv, table, out, B, H, W, C, heads, ws, shift):
+    out.copy_(_window_attention(qkv.detach(), table.detach(), B, H, W, C, heads, ws, shift).reshape(out.shape))
+
+
+def window_attn_workspace_bytes(B, H, W, heads, ws):
+    return 64
+
+
+def window_attn_bwd(qkv, table, dout, dqkv, dtable, B, H, W, C, heads, ws, shift, wsp):
+    with torch.enable_grad():
+        q = qkv.detach().clone().requires_grad_(True)
+        t = table.detach().clone().requires_grad_(True)
+        o = _window_attention(q, t, B, H, W, C, heads, ws, shift)
+        gq, gt = torch.autograd.grad(o, [q, t], dout.reshape(o.shape))
+    dqkv.copy_(gq.reshape(dqkv.shape))
+    dtable.copy_(gt.reshape(dtable.shape))
+
+
+def _droppath_scale(B, p_drop, seed, seed_off, rng_stream):
+    if p_drop == 0:
+        return torch.ones(B)
+    s = seed + (int(seed_off.item()) if seed_off is not None else 0)
+    w0 = philox.philox4x32_10(s, rng_stream, np.arange(B, dtype=np.uint64))[0]
+    u = (w0 >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.from_numpy((u >= np.float32(p_drop)).astype(np.float32)) / (1.0 - p_drop)
+
+
+def add_droppath(x, branch, out, B, per_sample, p_drop=0.0, seed=0, seed_off=None, rng_stream=0):
+    sc = _droppath_scale(B, p_drop, seed, seed_off, rng_stream).reshape(B, 1)
+    r = branch.reshape(B, -1) * sc
+    if x is not None:
+        r = r + x.reshape(B, -1)
+    out.copy_(r.reshape(out.shape))
+
+
+def patch_merge_gather(x, y, B, H, W, C, inverse=False, accumulate=False):
+    if not inverse:
+        v = x.reshape(B, H, W, C)
+        g = torch.cat([v[:, 0::2, 0::2], v[:, 1::2, 0::2], v[:, 0::2, 1::2], v[:, 1::2, 1::2]], -1)
+        y.copy_(g.reshape(y.shape))
+    else:
+        g = x.reshape(B, H // 2, W // 2, 4, C)
+        r = torch.zeros(B, H, W, C)
+        r[:, 0::2, 0::2], r[:, 1::2, 0::2], r[:, 0::2, 1::2], r[:, 1::2, 1::2] = g[..., 0, :], g[..., 1, :], g[..., 2, :], g[..., 3, :]
+        _store(y, r, accumulate)
+
+
+def pixel_shuffle(x, y, B, H, W, C, p, inverse=False):
+    if not inverse:
+        v = x.reshape(B, H, W, p, p, C).permute(0, 1, 3, 2, 4, 5)
+        y.copy_(v.reshape(y.shape))
+    else:
+        v = x.reshape(B, H, p, W, p, C).permute(0, 1, 3, 2, 4, 5)
+        y.copy_(v.reshape(y.shape))
+
+
+def patch_embed_gather(x, y, B, H, W, patch, repeat_channels):
+    v = x.reshape(B, 1, H, W).repeat(1, repeat_channels, 1, 1)
+    cols = F.unfold(v, kernel_size=patch, stride=patch)                  # [B, C*P*P, L]
+    y.copy_(cols.transpose(1, 2).reshape(y.shape))
+
+
 # ------------------------------------------------------------------ loss / optimizer / noise
 def ssl_loss_workspace_bytes(B, S):
     return 64
@@ -453,6 +587,32 @@ def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, gr
         lg = logits.detach().clone().requires_grad_(True)
         tot, *_ = _ssl_loss(lg, teacher, labels, nhwc, B, Lb, C, S, w, mc_psum, mc_T, mc_thr)
         (g,) = torch.autograd.grad(tot * grad_scale, lg)
+    g = _to_ncs(g, nhwc, B, C, S)
+    dlogits.copy_((g.permute(0, 2, 1) if dlogits_nhwc else g).reshape(dlogits.shape))
+
+
+def _ct_loss(lg, other, lab, Lb, C, w):
+    from oracle import ssl_oracle as O
+    sup, ce, dice = O.supervised_loss(lg[:Lb], lab, C)
+    pseudo = torch.argmax(torch.softmax(other[Lb:], 1), dim=1)
+    ps = O.dice_loss_multiclass(torch.softmax(lg[Lb:], 1), pseudo.unsqueeze(1), C)
+    return sup + w * ps, ce, dice, ps
+
+
+def ct_loss_fwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, w_cons, lossbuf, ws):
+    w = float(w_cons[0])
+    lg, ot = _to_ncs(logits.detach(), nhwc, B, C, S), _to_ncs(other.detach(), other_nhwc, B, C, S)
+    tot, ce, dice, ps = _ct_loss(lg, ot, labels.reshape(-1, S)[:Lb], Lb, C, w)
+    lossbuf[0], lossbuf[1], lossbuf[2], lossbuf[3], lossbuf[4] = ce, dice, ps, tot, w
+
+
+def ct_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+    w = float(lossbuf[4])
+    with torch.enable_grad():
+        raw = logits.detach().clone().requires_grad_(True)
+        tot, *_ = _ct_loss(_to_ncs(raw, nhwc, B, C, S), _to_ncs(other.detach(), other_nhwc, B, C, S),
+                           labels.reshape(-1, S)[:Lb], Lb, C, w)
+        (g,) = torch.autograd.grad(tot * grad_scale, raw)
     g = _to_ncs(g, nhwc, B, C, S)
     dlogits.copy_((g.permute(0, 2, 1) if dlogits_nhwc else g).reshape(dlogits.shape))
 

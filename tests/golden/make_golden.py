@@ -183,13 +183,6 @@ def mt_step_fixture():
     print("mt_step: losses", [float(s["loss"]) for s in steps], "cons", [float(s["cons"]) for s in steps])
 
 
-if __name__ == "__main__":
-    unet_fixture()
-    losses_fixture()
-    ramps_fixture()
-    mt_step_fixture()
-
-
 def vnet_fixture():
     """VNet (batchnorm, has_dropout) forward/backward + one UAMT iteration restated from
     code/train_uncertainty_aware_mean_teacher_3D.py:137-189 over the reference's own VNet/DiceLoss/softmax_mse/ramps."""
@@ -272,5 +265,162 @@ def vnet_fixture():
     print("vnet_uamt: loss", float(loss), "cons", float(consistency_loss), "mask frac", float(mask.mean()))
 
 
+def _install_timm_shim(keep_source):
+    """timm is not installed here (nor vendored by the reference).  Shim `timm.models.layers` with the three names the
+    reference imports (…_sys.py:6): to_2tuple, trunc_normal_ (== torch.nn.init.trunc_normal_, same algorithm) and
+    DropPath restated from timm's published drop_path(): per-sample Bernoulli(1 - p) keep, divided by the keep
+    probability, identity in eval mode.  The keep draws come from `keep_source(module_index, call_index, batch)` so the
+    CUDA path's Philox draws can be replayed through the reference's own block code."""
+    import types
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    layers = types.ModuleType("timm.models.layers")
+
+    class DropPath(torch.nn.Module):
+        count = 0
+
+        def __init__(self, drop_prob=0.0):
+            super().__init__()
+            self.drop_prob, self.index, self.calls = drop_prob, DropPath.count, 0
+            DropPath.count += 1
+
+        def forward(self, x):
+            call, self.calls = self.calls, self.calls + 1
+            if self.drop_prob == 0.0 or not self.training:
+                return x
+            keep = keep_source(self.index, call, x.shape[0], self.drop_prob)
+            return x * (keep / (1.0 - self.drop_prob)).view(-1, *([1] * (x.dim() - 1)))
+
+    layers.DropPath = DropPath
+    layers.to_2tuple = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+    layers.trunc_normal_ = torch.nn.init.trunc_normal_
+    timm.models, models.layers = models, layers
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+    return DropPath
+
+
+SWIN_SMALL = dict(img_size=64, patch_size=4, in_chans=3, embed_dim=32, depths=(2, 2, 2, 2), num_heads=(1, 2, 4, 8),
+                  window_size=4, mlp_ratio=4.0, qkv_bias=True, drop_path_rate=0.2, patch_norm=True)
+
+
+def swin_fixture():
+    """Swin-UNet forward/backward and one Cross-Teaching iteration (code/train_cross_teaching_between_cnn_transformer_2D.py
+    :221-259) driven through the reference's own SwinUnet / UNet / DiceLoss / ramps / torch.optim.SGD.
+
+    Small geometry (64x64 slices, window 4 -> stages 16^2/8^2 shifted, 4^2 and 2^2 unshifted, heads 1/2/4/8 of dim 32) so
+    that it runs in seconds; DropPath 0.2 with injected Philox keep draws (seed 4242, stream 3000 + 2 * block + call)."""
+    from types import SimpleNamespace as NS
+    from oracle import philox
+    from cv_ssl_mis_b200.networks.swin_unet import SwinUnet as OurSwin, DROPPATH_STREAM
+    dp_seed = 4242 + 1                      # Runtime seed 4242, one seed bump before the forward
+
+    def keep_source(index, call, batch, p):
+        w0 = philox.philox4x32_10(dp_seed, DROPPATH_STREAM + 2 * index + (call % 2), np.arange(batch, dtype=np.uint64))[0]
+        u = (w0 >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        return torch.from_numpy((u >= np.float32(p)).astype(np.float32))
+
+    DropPath = _install_timm_shim(keep_source)
+    from networks.vision_transformer import SwinUnet as RefSwin
+    c = SWIN_SMALL
+    config = NS(DATA=NS(IMG_SIZE=c["img_size"]),
+                MODEL=NS(DROP_RATE=0.0, DROP_PATH_RATE=c["drop_path_rate"], PRETRAIN_CKPT=None,
+                         SWIN=NS(PATCH_SIZE=c["patch_size"], IN_CHANS=c["in_chans"], EMBED_DIM=c["embed_dim"],
+                                 DEPTHS=list(c["depths"]), NUM_HEADS=list(c["num_heads"]), WINDOW_SIZE=c["window_size"],
+                                 MLP_RATIO=c["mlp_ratio"], QKV_BIAS=True, QK_SCALE=False, APE=False, PATCH_NORM=True)),
+                TRAIN=NS(USE_CHECKPOINT=False))
+    seed = 1357
+    torch.manual_seed(seed)
+    model1 = RefUNet(in_chns=1, class_num=4)
+    DropPath.count = 0
+    model2 = RefSwin(config, img_size=c["img_size"], num_classes=4)
+    # DropPath draw ids follow the BLOCK index in construction order (rate-0 blocks hold nn.Identity, not DropPath)
+    sysm = model2.swin_unet
+    all_blocks = [b for l in sysm.layers for b in l.blocks] + [b for l in list(sysm.layers_up)[1:] for b in l.blocks]
+    for bi, blk in enumerate(all_blocks):
+        if isinstance(blk.drop_path, DropPath):
+            blk.drop_path.index = bi
+    torch.manual_seed(seed)
+    ours1 = OurUNet(1, 4)
+    ours2 = OurSwin(config, img_size=c["img_size"], num_classes=4)
+    sd_ref, sd_ours = model2.state_dict(), ours2.state_dict()
+    assert list(sd_ref.keys()) == list(sd_ours.keys()), "SwinUnet state_dict key schema differs from the reference"
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_ours[k]), k
+    assert [tuple(p.shape) for p in model2.parameters()] == [tuple(p.shape) for p in ours2.parameters()]
+    for k in model1.state_dict():
+        assert torch.equal(model1.state_dict()[k], ours1.state_dict()[k]), k
+    # give LayerNorm / bias / rel-pos-bias parameters non-trivial values (their init is 1 / 0 / ~N(0, .02)):
+    # seeded perturbation that the tests replay
+    g = torch.Generator().manual_seed(97)
+    with torch.no_grad():
+        for k, p in model2.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif k.endswith("relative_position_bias_table"):
+                p.add_(0.5 * torch.randn(p.shape, generator=g))
+    init_ck = (checksum(model1.state_dict()), checksum(model2.state_dict()))
+    no_dropout(model1)
+    model1.train(); model2.train()
+    g = torch.Generator().manual_seed(31)
+    B, Lb, P = 4, 2, c["img_size"]
+    volume_batch = torch.rand(B, 1, P, P, generator=g)
+    label_batch = blocky_labels(g, B, P, P, 4)
+    base_lr, max_iterations, iter_num = 0.01, 30000, 24000
+    args = NS(labeled_bs=Lb, consistency=0.1, consistency_rampup=200.0)
+    optimizer1 = torch.optim.SGD(model1.parameters(), lr=base_lr, momentum=0.9, weight_decay=0.0001)     # :200-203
+    optimizer2 = torch.optim.SGD(model2.parameters(), lr=base_lr, momentum=0.9, weight_decay=0.0001)
+    lr0 = base_lr * (1.0 - iter_num / max_iterations) ** 0.9            # installed by the previous iteration (:258-262)
+    for opt in (optimizer1, optimizer2):
+        for pg in opt.param_groups:
+            pg['lr'] = lr0
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(4)
+
+    def get_current_consistency_weight(epoch):                                                           # :117-119
+        return args.consistency * ref_ramps.sigmoid_rampup(epoch, args.consistency_rampup)
+
+    outputs1 = model1(volume_batch)                                                                      # :224-225
+    outputs_soft1 = torch.softmax(outputs1, dim=1)
+    outputs2 = model2(volume_batch)                                                                      # :227-228
+    outputs_soft2 = torch.softmax(outputs2, dim=1)
+    consistency_weight = get_current_consistency_weight(iter_num // 150)                                 # :229-230
+    loss1 = 0.5 * (ce_loss(outputs1[:args.labeled_bs], label_batch[:args.labeled_bs].long()) + dice_loss(
+        outputs_soft1[:args.labeled_bs], label_batch[:args.labeled_bs].unsqueeze(1)))                    # :232-233
+    loss2 = 0.5 * (ce_loss(outputs2[:args.labeled_bs], label_batch[:args.labeled_bs].long()) + dice_loss(
+        outputs_soft2[:args.labeled_bs], label_batch[:args.labeled_bs].unsqueeze(1)))                    # :234-235
+    pseudo_outputs1 = torch.argmax(outputs_soft1[args.labeled_bs:].detach(), dim=1, keepdim=False)       # :237-240
+    pseudo_outputs2 = torch.argmax(outputs_soft2[args.labeled_bs:].detach(), dim=1, keepdim=False)
+    pseudo_supervision1 = dice_loss(outputs_soft1[args.labeled_bs:], pseudo_outputs2.unsqueeze(1))       # :242-245
+    pseudo_supervision2 = dice_loss(outputs_soft2[args.labeled_bs:], pseudo_outputs1.unsqueeze(1))
+    model1_loss = loss1 + consistency_weight * pseudo_supervision1                                       # :247-248
+    model2_loss = loss2 + consistency_weight * pseudo_supervision2
+    loss = model1_loss + model2_loss                                                                     # :250
+    optimizer1.zero_grad()
+    optimizer2.zero_grad()
+    loss.backward()                                                                                      # :255
+    gn1 = {n: float(p.grad.norm()) for n, p in model1.named_parameters()}
+    gn2 = {n: float(p.grad.norm()) for n, p in model2.named_parameters()}
+    table_grad = model2.swin_unet.layers[0].blocks[1].attn.relative_position_bias_table.grad.clone()
+    optimizer1.step()                                                                                    # :257-258
+    optimizer2.step()
+    stat = lambda t: (float(t.mean()), float(t.abs().mean()))
+    torch.save(dict(seed=seed, perturb_seed=97, gen_seed=31, dp_seed=4242, init_ck=init_ck, keys=list(sd_ref.keys()),
+                    cfg=c, B=B, labeled_bs=Lb, iter_num=iter_num, lr=lr0, w=consistency_weight,
+                    logits1_sub=outputs1.detach()[:, :, ::4, ::4].clone(), logits1_stat=stat(outputs1.detach()),
+                    logits2_sub=outputs2.detach()[:, :, ::2, ::2].clone(), logits2_stat=stat(outputs2.detach()),
+                    loss=loss.detach(), model1_loss=model1_loss.detach(), model2_loss=model2_loss.detach(),
+                    ps1=pseudo_supervision1.detach(), ps2=pseudo_supervision2.detach(), loss1=loss1.detach(),
+                    loss2=loss2.detach(), grad_norm1=gn1, grad_norm2=gn2, table_grad=table_grad,
+                    out_w2=model2.swin_unet.output.weight.detach().clone(),
+                    qkv_w2=model2.swin_unet.layers[1].blocks[1].attn.qkv.weight.detach()[:8].clone(),
+                    ck1=checksum(model1.state_dict()), ck2=checksum(model2.state_dict())),
+               os.path.join(HERE, "swin_ct.pt"))
+    print("swin_ct: loss", float(loss), "m1", float(model1_loss), "m2", float(model2_loss), "w", consistency_weight,
+          "ps", float(pseudo_supervision1), float(pseudo_supervision2))
+
+
 if __name__ == "__main__":
-    vnet_fixture()
+    fixtures = dict(unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
+                    vnet=vnet_fixture, swin=swin_fixture)
+    for name in (sys.argv[1:] or list(fixtures)):
+        fixtures[name]()

@@ -196,3 +196,105 @@ def test_uamt_trainer_matches_oracle(fake):
             if s_sd[k].dtype.is_floating_point:
                 torch.testing.assert_close(sd_now[k], s_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"student {k}: {m}")
                 torch.testing.assert_close(td_now[k], t_sd[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"teacher {k}: {m}")
+
+
+# ------------------------------------------------------------------ Swin-UNet / Cross-Teaching
+SWIN_SMALL = dict(img_size=64, embed_dim=32, num_heads=(1, 2, 4, 8), window_size=4, drop_path_rate=0.2)
+
+
+@pytest.mark.parametrize("drop_path", [0.0, 0.3])
+def test_swin_plan_matches_oracle(fake, drop_path):
+    """Forward/backward tape (aliasing residual gradients, pooled buffers, accumulate flags) against autograd."""
+    from oracle import swin_oracle as SO
+    from tests import swin_common as SC
+    from cv_ssl_mis_b200.networks import swin_unet as S
+    torch.manual_seed(5)
+    net = S.SwinUnet(dict(SWIN_SMALL, drop_path_rate=drop_path), num_classes=4, seed=99)
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd0 = SC.swin_sd(net)
+    B = 2
+    x = torch.randn(B, 1, 64, 64, generator=g)
+    y = torch.randint(0, 4, (B, 64, 64), generator=g)
+    net.materialize()
+    plan = net._get_plan(B, True)
+    net._bump_seed()
+    logits = plan.forward(x, train=True).view(B, 4, 64, 64)
+    cfg = SO.swin_config(sd0, 64, 4, drop_path)
+    keys = [k for k, v in sd0.items() if v.dtype.is_floating_point and not k.endswith("attn_mask")]
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd0.items()}
+    keeps = SC.drop_keeps(99 + 1, B, cfg["depths"], drop_path) if drop_path > 0 else None
+    ref = SO.swin_unet_forward(leaf, x, cfg, True, keeps)
+    torch.testing.assert_close(logits, ref, rtol=1e-4, atol=1e-5)
+    loss, _, _ = O.supervised_loss(ref, y, 4)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys] + [ref])
+    plan.backward(grads[-1].permute(0, 2, 3, 1).reshape(-1, 4).contiguous())
+    named = dict(net.swin_unet.named_parameters())
+    for k, gr in zip(keys, grads[:-1]):
+        torch.testing.assert_close(named[k].grad, gr, rtol=2e-3, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
+    # eval mode: DropPath is the identity
+    with torch.no_grad():
+        ev = net._get_plan(B, False).forward(x, train=False).view(B, 4, 64, 64)
+        torch.testing.assert_close(ev, SO.swin_unet_forward(sd0, x, cfg, False), rtol=1e-4, atol=1e-5)
+
+
+def test_swin_autograd_bridge(fake):
+    """`loss.backward()` through SwinUnet.forward, as the reference trainers call it."""
+    from oracle import swin_oracle as SO
+    from tests import swin_common as SC
+    from cv_ssl_mis_b200.networks import swin_unet as S
+    torch.manual_seed(2)
+    net = S.SwinUnet(dict(SWIN_SMALL, drop_path_rate=0.0), num_classes=3)
+    sd0 = SC.swin_sd(net)
+    x = torch.randn(1, 1, 64, 64)
+    out = net(x)
+    out.square().mean().backward()
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd0.items()}
+    ref = SO.swin_unet_forward(leaf, x, SO.swin_config(sd0, 64, 4, 0.0), True)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    (gw,) = torch.autograd.grad(ref.square().mean(), leaf["layers.2.blocks.0.mlp.fc1.weight"])
+    torch.testing.assert_close(net.swin_unet.layers[2].blocks[0].mlp.fc1.weight.grad, gw, rtol=2e-3, atol=1e-8)
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 1, 32, 32))
+
+
+def test_cross_teaching_trainer_matches_oracle(fake):
+    """Two iterations of CrossTeachingTrainer vs oracle.ct2d_step (losses, both models' weights, LR schedule)."""
+    from oracle import swin_oracle as SO
+    from tests import swin_common as SC
+    from cv_ssl_mis_b200.networks import swin_unet as S
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+    torch.manual_seed(31)
+    m1 = unet_mod.UNet(1, 4, seed=11)
+    m2 = S.SwinUnet(dict(SWIN_SMALL), num_classes=4, seed=22)
+    sd1 = {k: v.clone() for k, v in m1.state_dict().items()}
+    sd2 = SC.swin_sd(m2)
+    B, Lb, P = 4, 2, 64
+    it0 = 23999
+    tr = CrossTeachingTrainer(m1, m2, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it0)
+    cfg = SO.swin_config(sd2, P, 4, 0.2)
+    bufs1 = {k: torch.zeros_like(sd1[k]) for k in O.param_keys(sd1)}
+    bufs2 = {k: torch.zeros_like(v) for k, v in sd2.items() if v.dtype.is_floating_point}
+    g = torch.Generator().manual_seed(9)
+    for step in range(2):
+        it = it0 + step
+        x = torch.rand(B, 1, P, P, generator=g)
+        y = SC.blocky_labels(g, B, P, P, 4)
+        got = tr.step(x, y, read_loss=True)
+        off = step + 1
+        r = SO.ct2d_step(sd1, sd2, bufs1, bufs2, x, y, it, cfg, labeled_bs=Lb, masks1=unet_masks(11 + off, B, P, P),
+                         drop_keep=SC.drop_keeps(22 + off, B, cfg["depths"], 0.2))
+        want = [r["ce1"], r["dice1"], r["ps1"], r["model1_loss"], r["ce2"], r["dice2"], r["ps2"], r["model2_loss"]]
+        torch.testing.assert_close(torch.tensor(got), torch.stack(want), rtol=1e-4, atol=1e-5)
+        now1, now2 = m1.state_dict(), SC.swin_sd(m2)
+        for k in sd1:
+            if sd1[k].dtype.is_floating_point:
+                torch.testing.assert_close(now1[k], sd1[k], rtol=2e-3, atol=1e-5, msg=lambda m, k=k: f"unet {k}: {m}")
+        for k in sd2:
+            if sd2[k].dtype.is_floating_point:
+                torch.testing.assert_close(now2[k], sd2[k], rtol=2e-3, atol=1e-6, msg=lambda m, k=k: f"swin {k}: {m}")
+    assert tr.iter_num == it0 + 2
+    assert abs(tr.lr - O.poly_lr(0.01, it0 + 2, 30000)) < 1e-15

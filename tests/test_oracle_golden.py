@@ -125,3 +125,41 @@ def test_vnet_uamt_step(golden):
     torch.testing.assert_close(teacher["out_conv.weight"], g["t_out"], rtol=1e-4, atol=1e-6)
     assert abs(checksum(student) - g["student_ck"]) < 1e-5 * g["student_ck"]
     assert abs(checksum(teacher) - g["teacher_ck"]) < 1e-5 * g["teacher_ck"]
+
+
+def test_swin_cross_teaching_step(golden):
+    """oracle/swin_oracle.py (Swin-UNet forward + the Cross-Teaching iteration) against the reference's own
+    SwinUnet / UNet / DiceLoss / SGD run (tests/golden/swin_ct.pt), DropPath draws replayed from Philox."""
+    from oracle import swin_oracle as SO
+    from tests import swin_common as SC
+    g = golden("swin_ct.pt")
+    unet, swin = SC.build_models(g)
+    assert list(swin.state_dict().keys()) == g["keys"]
+    ck = (checksum(unet.state_dict()), checksum(swin.state_dict()))
+    if any(abs(a - b) > 1e-6 * b for a, b in zip(ck, g["init_ck"])):
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    x, y = SC.build_inputs(g)
+    c = g["cfg"]
+    sd1, sd2 = {k: v.clone() for k, v in unet.state_dict().items()}, SC.swin_sd(swin)
+    cfg = SO.swin_config(sd2, c["img_size"], c["window_size"], c["drop_path_rate"], c["patch_size"])
+    assert cfg["depths"] == list(c["depths"]) and cfg["heads"] == list(c["num_heads"])
+    keeps = SC.drop_keeps(g["dp_seed"] + 1, g["B"], cfg["depths"], c["drop_path_rate"])
+    bufs1 = {k: torch.zeros_like(sd1[k]) for k in O.param_keys(sd1)}
+    bufs2 = {k: torch.zeros_like(v) for k, v in sd2.items() if v.dtype.is_floating_point}
+    r = SO.ct2d_step(sd1, sd2, bufs1, bufs2, x, y, g["iter_num"], cfg, labeled_bs=g["labeled_bs"], drop_keep=keeps)
+    assert abs(r["lr"] - g["lr"]) < 1e-12 and abs(r["w"] - g["w"]) < 1e-12
+    torch.testing.assert_close(r["logits1"][:, :, ::4, ::4], g["logits1_sub"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(r["logits2"][:, :, ::2, ::2], g["logits2_sub"], rtol=1e-4, atol=2e-5)
+    for k in ("loss", "model1_loss", "model2_loss", "ps1", "ps2"):
+        torch.testing.assert_close(r[k], g[k], rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+    for k, gr in r["grads1"].items():
+        assert abs(float(gr.norm()) - g["grad_norm1"][k]) <= 2e-3 * g["grad_norm1"][k] + 1e-7, k
+    for k, gr in r["grads2"].items():
+        ref = g["grad_norm2"]["swin_unet." + k]
+        assert abs(float(gr.norm()) - ref) <= 2e-3 * ref + 1e-7, k
+    torch.testing.assert_close(r["grads2"]["layers.0.blocks.1.attn.relative_position_bias_table"], g["table_grad"],
+                               rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(sd2["output.weight"], g["out_w2"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(sd2["layers.1.blocks.1.attn.qkv.weight"][:8], g["qkv_w2"], rtol=1e-5, atol=1e-7)
+    assert abs(checksum(sd1) - g["ck1"]) <= 1e-6 * g["ck1"]
+    assert abs(checksum({"swin_unet." + k: v for k, v in sd2.items()}) - g["ck2"]) <= 1e-6 * g["ck2"]

@@ -1,0 +1,290 @@
+"""Swin-UNet kernels, the Swin-UNet itself and the Cross-Teaching step on the GPU (through the C ABI), against the
+plain-torch references in tests/fake_ops.py, the oracle, and the reference-generated fixture tests/golden/swin_ct.pt."""
+import numpy as np
+import pytest
+import torch
+
+from cv_ssl_mis_b200 import ops
+from cv_ssl_mis_b200.networks import unet as unet_mod
+from cv_ssl_mis_b200.networks import swin_unet as S
+from cv_ssl_mis_b200.networks.net_factory import net_factory
+from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+from oracle import ssl_oracle as O, swin_oracle as SO
+from tests import fake_ops as ref, swin_common as SC
+from tests.test_host_logic import unet_masks
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return None if t is None else t.to(DEV).contiguous()
+
+
+def scratch(nbytes):
+    return torch.empty(nbytes // 4 + 4, device=DEV)
+
+
+@pytest.mark.parametrize("MC", [(37, 32), (1000, 96), (333, 192), (64, 384), (50, 768), (9, 1536), (20, 128), (17, 100)])
+def test_layernorm(MC):
+    M, C = MC
+    g = torch.Generator().manual_seed(M + C)
+    x, dy = torch.randn(M, C, generator=g) * 2 + 0.5, torch.randn(M, C, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    y, st = torch.empty(M, C, device=DEV), torch.empty(2 * M, device=DEV)
+    ops.layernorm_fwd(cu(x), cu(gamma), cu(beta), y, st, M, C)
+    yr, sr = torch.empty(M, C), torch.empty(2 * M)
+    ref.layernorm_fwd(x, gamma, beta, yr, sr, M, C)
+    torch.testing.assert_close(y.cpu(), yr, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(st.cpu(), sr, rtol=1e-5, atol=1e-5)
+    ws = scratch(ops.layernorm_workspace_bytes(M, C))
+    for acc in (False, True):
+        base = torch.randn(M, C, generator=g)
+        dx, dg, db = cu(base.clone()), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        ops.layernorm_bwd(cu(x), st, cu(gamma), cu(dy), dx, dg, db, M, C, ws, acc)
+        dxr, dgr, dbr = base.clone(), torch.empty(C), torch.empty(C)
+        ref.layernorm_bwd(x, sr, gamma, dy, dxr, dgr, dbr, M, C, None, acc)
+        torch.testing.assert_close(dx.cpu(), dxr, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(dg.cpu(), dgr, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(db.cpu(), dbr, rtol=1e-4, atol=1e-4)
+
+
+def test_gelu():
+    g = torch.Generator().manual_seed(3)
+    x, dy, base = (torch.randn(4096 + 4, generator=g) * 3 for _ in range(3))
+    y = torch.empty_like(x, device=DEV)
+    ops.gelu_fwd(cu(x), y)
+    torch.testing.assert_close(y.cpu(), torch.nn.functional.gelu(x), rtol=1e-5, atol=1e-6)
+    for acc in (False, True):
+        dx, dxr = cu(base.clone()), base.clone()
+        ops.gelu_bwd(cu(x), cu(dy), dx, acc)
+        ref.gelu_bwd(x, dy, dxr, acc)
+        torch.testing.assert_close(dx.cpu(), dxr, rtol=1e-5, atol=1e-6)
+
+
+ATTN_CASES = [  # B, H, W, heads, ws, shift
+    (2, 14, 14, 3, 7, 0), (2, 14, 14, 3, 7, 3), (1, 28, 14, 2, 7, 3), (3, 7, 7, 4, 7, 0), (2, 16, 16, 1, 4, 2),
+    (2, 8, 8, 2, 4, 0), (2, 2, 2, 8, 2, 0), (1, 6, 9, 1, 3, 1), (1, 56, 56, 3, 7, 3),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_window_attention(case):
+    """roll + window partition + scaled QK^T + relative-position bias + shift mask (-100) + softmax + PV + reverse, and
+    its backward incl. the bias-table gradient, vs the reference formulation (…_sys.py:115-150, 244-280) in torch."""
+    B, H, W, heads, ws, shift = case
+    C, M = heads * 32, B * H * W
+    g = torch.Generator().manual_seed(sum(case))
+    qkv = torch.randn(M, 3 * C, generator=g)
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    dout = torch.randn(M, C, generator=g)
+    out = torch.empty(M, C, device=DEV)
+    ops.window_attn_fwd(cu(qkv), cu(table), out, B, H, W, C, heads, ws, shift)
+    outr = torch.empty(M, C)
+    ref.window_attn_fwd(qkv, table, outr, B, H, W, C, heads, ws, shift)
+    torch.testing.assert_close(out.cpu(), outr, rtol=1e-4, atol=2e-5)
+    dqkv, dtab = torch.empty(M, 3 * C, device=DEV), torch.empty_like(table, device=DEV)
+    wsp = scratch(ops.window_attn_workspace_bytes(B, H, W, heads, ws))
+    ops.window_attn_bwd(cu(qkv), cu(table), cu(dout), dqkv, dtab, B, H, W, C, heads, ws, shift, wsp)
+    dqr, dtr = torch.empty(M, 3 * C), torch.empty_like(table)
+    ref.window_attn_bwd(qkv, table, dout, dqr, dtr, B, H, W, C, heads, ws, shift, None)
+    torch.testing.assert_close(dqkv.cpu(), dqr, rtol=1e-3, atol=5e-5)
+    torch.testing.assert_close(dtab.cpu(), dtr, rtol=1e-3, atol=1e-4)
+
+
+def test_droppath_gathers_and_shuffle():
+    g = torch.Generator().manual_seed(8)
+    B, H, W, C = 5, 8, 12, 32
+    x, br = torch.randn(B * H * W, C, generator=g), torch.randn(B * H * W, C, generator=g)
+    off = torch.tensor([3], dtype=torch.int64)
+    for p in (0.0, 0.4):
+        out, outr = torch.empty_like(x, device=DEV), torch.empty_like(x)
+        ops.add_droppath(cu(x), cu(br), out, B, H * W * C, p, 77, cu(off), 3005)
+        ref.add_droppath(x, br, outr, B, H * W * C, p, 77, off, 3005)
+        assert torch.equal(out.cpu(), outr) or torch.allclose(out.cpu(), outr, rtol=1e-6, atol=1e-7)
+        ops.add_droppath(None, cu(br), out, B, H * W * C, p, 77, cu(off), 3005)
+        ref.add_droppath(None, br, outr, B, H * W * C, p, 77, off, 3005)
+        torch.testing.assert_close(out.cpu(), outr, rtol=1e-6, atol=1e-7)
+    # PatchMerging gather and its transpose
+    y, yr = torch.empty(B * H * W // 4, 4 * C, device=DEV), torch.empty(B * H * W // 4, 4 * C)
+    ops.patch_merge_gather(cu(x), y, B, H, W, C)
+    ref.patch_merge_gather(x, yr, B, H, W, C)
+    assert torch.equal(y.cpu(), yr)
+    for acc in (False, True):
+        dx, dxr = cu(br.clone()), br.clone()
+        ops.patch_merge_gather(y, dx, B, H, W, C, True, acc)
+        ref.patch_merge_gather(yr, dxr, B, H, W, C, True, acc)
+        assert torch.equal(dx.cpu(), dxr)
+    # PatchExpand rearrange, p = 2 and 4, and inverse
+    for p in (2, 4):
+        c = 8
+        e = torch.randn(B * H * W, p * p * c, generator=g)
+        s, sr = torch.empty(B * H * W * p * p, c, device=DEV), torch.empty(B * H * W * p * p, c)
+        ops.pixel_shuffle(cu(e), s, B, H, W, c, p)
+        ref.pixel_shuffle(e, sr, B, H, W, c, p)
+        assert torch.equal(s.cpu(), sr)
+        back = torch.empty_like(e, device=DEV)
+        ops.pixel_shuffle(s, back, B, H, W, c, p, True)
+        assert torch.equal(back.cpu(), e)
+    # patch-embedding im2col of the channel-repeated slice
+    img = torch.randn(B, 1, 16, 24, generator=g)
+    cols, colsr = torch.empty(B * 4 * 6, 48, device=DEV), torch.empty(B * 4 * 6, 48)
+    ops.patch_embed_gather(cu(img), cols, B, 16, 24, 4, 3)
+    ref.patch_embed_gather(img, colsr, B, 16, 24, 4, 3)
+    assert torch.equal(cols.cpu(), colsr)
+
+
+@pytest.mark.parametrize("layouts", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("C", [2, 4])
+def test_cross_teaching_loss(layouts, C):
+    """0.5 (CE + Dice) + w * Dice vs the other model's argmax pseudo labels: values and d/d(logits)."""
+    nhwc, other_nhwc = layouts
+    g = torch.Generator().manual_seed(12 + C)
+    B, Lb, S = 6, 2, 40 * 24
+    logits = torch.randn(B, C, S, generator=g) * 2
+    other = torch.randn(B, C, S, generator=g) * 2
+    y = torch.randint(0, C, (B, S), generator=g).to(torch.uint8)
+    w = torch.tensor([0.37])
+    lay = lambda t, f: t.permute(0, 2, 1).contiguous() if f else t
+    lg, ot = lay(logits, nhwc), lay(other, other_nhwc)
+    lb, lbr = torch.zeros(40, device=DEV), torch.zeros(40)
+    ws = scratch(ops.ssl_loss_workspace_bytes(B, S))
+    ops.ct_loss_fwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, cu(w), lb, ws)
+    ref.ct_loss_fwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, w, lbr, None)
+    torch.testing.assert_close(lb[:4].cpu(), lbr[:4], rtol=1e-5, atol=1e-6)
+    for out_nhwc in (False, True):
+        d, dr = torch.empty(B * C * S, device=DEV), torch.empty(B * C * S)
+        ops.ct_loss_bwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, lb, 0.5, d, out_nhwc)
+        ref.ct_loss_bwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, lbr, 0.5, dr, out_nhwc)
+        torch.testing.assert_close(d.cpu(), dr, rtol=1e-4, atol=1e-9)
+
+
+# ------------------------------------------------------------------ the network
+def test_swin_cross_teaching_matches_reference_fixture(golden, monkeypatch):
+    """One Cross-Teaching iteration of the reference's own UNet + SwinUnet (tests/golden/swin_ct.pt): logits of both models,
+    all loss terms, per-parameter gradient norms and updated weights, computed here by the CUDA path (3xTF32 mode)."""
+    monkeypatch.setattr(unet_mod, "DROPOUT", [0.0] * 5)
+    g = golden("swin_ct.pt")
+    unet, swin = SC.build_models(g, unet_seed=1, swin_seed=g["dp_seed"])
+    ck = (SC.checksum(unet.state_dict()), SC.checksum(swin.state_dict()))
+    if any(abs(a - b) > 1e-6 * b for a, b in zip(ck, g["init_ck"])):
+        pytest.skip("torch RNG stream differs from the fixture's")
+    unet._exact = swin._exact = True
+    unet, swin = unet.cuda(), swin.cuda()
+    x, y = SC.build_inputs(g)
+    P, B = g["cfg"]["img_size"], g["B"]
+    tr = CrossTeachingTrainer(unet, swin, batch_size=B, labeled_bs=g["labeled_bs"], patch_size=(P, P), num_classes=4,
+                              start_iter=g["iter_num"])
+    assert abs(tr.lr - g["lr"]) < 1e-12
+    # run the schedule by hand up to the optimizer so that the gradients can be inspected
+    tr._set_hparams()
+    tr.x.copy_(x)
+    tr.y.copy_(y)
+    p1, p2 = tr.plans
+    for m, off in zip(tr.models, tr.offs):
+        off += 1
+        m.train()
+    p1.forward(tr.x, True)
+    p2.forward(tr.x, True)
+    torch.testing.assert_close(p1.logits.view(B, 4, P, P)[:, :, ::4, ::4].cpu(), g["logits1_sub"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(p2.logits.view(B, 4, P, P)[:, :, ::2, ::2].cpu(), g["logits2_sub"], rtol=1e-3, atol=1e-4)
+    w = tr.hp[6:7]
+    for mine, other, lb in ((p1, p2, tr.lossbufs[0]), (p2, p1, tr.lossbufs[1])):
+        ops.ct_loss_fwd(mine.logits, False, other.logits, False, tr.y, B, tr.Lb, 4, P * P, w, lb, tr.loss_ws)
+        ops.ct_loss_bwd(mine.logits, False, other.logits, False, tr.y, B, tr.Lb, 4, P * P, lb, 1.0, mine.g_logits, True)
+        mine.backward(None)
+    l1, l2 = tr.lossbufs[0].cpu(), tr.lossbufs[1].cpu()
+    torch.testing.assert_close(l1[3], g["model1_loss"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(l2[3], g["model2_loss"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(l1[2], g["ps1"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(l2[2], g["ps2"], rtol=1e-4, atol=1e-5)
+    for n, p in swin.named_parameters():
+        want = g["grad_norm2"][n]
+        assert abs(float(p.grad.norm()) - want) <= 5e-3 * want + 1e-7, (n, float(p.grad.norm()), want)
+    for n, p in unet.named_parameters():
+        want = g["grad_norm1"][n]
+        assert abs(float(p.grad.norm()) - want) <= 1e-2 * want + 1e-6, (n, float(p.grad.norm()), want)
+    torch.testing.assert_close(swin.swin_unet.layers[0].blocks[1].attn.relative_position_bias_table.grad.cpu(), g["table_grad"],
+                               rtol=5e-3, atol=1e-6)
+    for flat, mom in zip(tr.flats, tr.momentum_bufs):
+        ops.sgd_ema_step(flat.data, flat.grad, mom, None, tr.hp)
+    torch.testing.assert_close(swin.swin_unet.output.weight.detach().cpu(), g["out_w2"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(swin.swin_unet.layers[1].blocks[1].attn.qkv.weight.detach()[:8].cpu(), g["qkv_w2"], rtol=1e-4, atol=1e-6)
+    assert abs(SC.checksum(swin.state_dict()) - g["ck2"]) <= 1e-5 * g["ck2"]
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_swin_unet_tiny224_matches_oracle(exact):
+    """The real configuration (Swin-tiny-lite, 224x224, window 7, DropPath 0.2) through `net_factory`, forward + backward
+    via autograd, against the CPU oracle with the same Philox DropPath draws."""
+    torch.manual_seed(3)
+    net = S.SwinUnet(None, img_size=224, num_classes=4, seed=501, exact=exact)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    sd0 = SC.swin_sd(net)
+    assert sum(p.numel() for p in net.parameters()) == 27168420
+    net = net.cuda()
+    B = 2
+    x = torch.rand(B, 1, 224, 224, generator=g)
+    y = torch.randint(0, 4, (B, 224, 224), generator=g)
+    logits = net(x.cuda())
+    cfg = SO.swin_config(sd0, 224, 7, 0.2)
+    keys = [k for k, v in sd0.items() if v.dtype.is_floating_point and not k.endswith("attn_mask")]
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd0.items()}
+    ref_logits = SO.swin_unet_forward(leaf, x, cfg, True, SC.drop_keeps(501 + 1, B, cfg["depths"], 0.2))
+    tol = dict(rtol=1e-3, atol=2e-4) if exact else dict(rtol=3e-2, atol=2e-2)
+    torch.testing.assert_close(logits.cpu(), ref_logits.detach(), **tol)
+    loss, _, _ = O.supervised_loss(logits, y.cuda(), 4)
+    loss.backward()
+    rloss, _, _ = O.supervised_loss(ref_logits, y, 4)
+    grads = torch.autograd.grad(rloss, [leaf[k] for k in keys])
+    named = dict(net.swin_unet.named_parameters())
+    gtol = 5e-3 if exact else 5e-2
+    for k, gr in zip(keys, grads):
+        got = named[k].grad.cpu()
+        err = float((got - gr).norm()) / (float(gr.norm()) + 1e-12)
+        assert err < gtol, (k, err)
+
+
+def test_net_factory_vit_seg_and_eval():
+    net = net_factory("ViT_Seg", in_chns=1, class_num=4)
+    assert isinstance(net, S.SwinUnet) and next(net.parameters()).is_cuda
+    net.eval()
+    x = torch.rand(1, 1, 224, 224, device=DEV)
+    with torch.no_grad():
+        a, b = net(x), net(x)
+    assert a.shape == (1, 4, 224, 224) and torch.equal(a, b)             # eval: DropPath off, deterministic
+    assert net_factory("no_such_net") is None
+
+
+def test_cross_teaching_trainer_graph_matches_oracle(monkeypatch):
+    """CrossTeachingTrainer (CUDA-graph replay) vs oracle.ct2d_step for three iterations at a small geometry."""
+    torch.manual_seed(31)
+    cfgd = dict(img_size=64, embed_dim=32, num_heads=(1, 2, 4, 8), window_size=4, drop_path_rate=0.2)
+    m1, m2 = unet_mod.UNet(1, 4, seed=11, exact=True), S.SwinUnet(cfgd, num_classes=4, seed=22, exact=True)
+    sd1, sd2 = {k: v.clone() for k, v in m1.state_dict().items()}, SC.swin_sd(m2)
+    m1, m2 = m1.cuda(), m2.cuda()
+    B, Lb, P, it0 = 4, 2, 64, 23999
+    tr = CrossTeachingTrainer(m1, m2, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it0,
+                              use_cuda_graph=True)
+    cfg = SO.swin_config(sd2, P, 4, 0.2)
+    bufs1 = {k: torch.zeros_like(sd1[k]) for k in O.param_keys(sd1)}
+    bufs2 = {k: torch.zeros_like(v) for k, v in sd2.items() if v.dtype.is_floating_point}
+    g = torch.Generator().manual_seed(9)
+    for step in range(3):
+        x = torch.rand(B, 1, P, P, generator=g)
+        y = SC.blocky_labels(g, B, P, P, 4)
+        got = tr.step(x, y, read_loss=True)
+        off = step + 1
+        r = SO.ct2d_step(sd1, sd2, bufs1, bufs2, x, y, it0 + step, cfg, labeled_bs=Lb, masks1=unet_masks(11 + off, B, P, P),
+                         drop_keep=SC.drop_keeps(22 + off, B, cfg["depths"], 0.2))
+        want = [r["ce1"], r["dice1"], r["ps1"], r["model1_loss"], r["ce2"], r["dice2"], r["ps2"], r["model2_loss"]]
+        torch.testing.assert_close(torch.tensor(got), torch.stack(want), rtol=2e-3, atol=2e-4)
+    now2 = SC.swin_sd(m2)
+    for k in sd2:
+        if sd2[k].dtype.is_floating_point:
+            torch.testing.assert_close(now2[k].cpu(), sd2[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"swin {k}: {m}")
+    assert tr.kernel_launches_per_step and tr.kernel_launches_per_step > 100
