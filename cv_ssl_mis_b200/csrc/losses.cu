@@ -185,7 +185,7 @@ __device__ double dice_from_sums(const double* I, const double* Z, const double*
 // out: [0] ce  [1] dice  [2] cons  [3] total  [4..4+C) A_c  [4+C..4+2C) B_c  [4+2C] d(cons)/d(p) scale
 //      (A/B = dice-gradient coefficients); pseudo-label mode: [2] = Dice against the pseudo labels and
 //      [5+2C..5+3C) A'_c, [5+3C..5+4C) B'_c = its gradient coefficients, already multiplied by w
-__global__ void ssl_loss_finalize_kernel(const double* __restrict__ part, int nblk, int Cpad, int C, int Lb, int U,
+__global__ void __launch_bounds__(1024) ssl_loss_finalize_kernel(const double* __restrict__ part, int nblk, int Cpad, int C, int Lb, int U,
                                          long long S, int has_teacher, int mc_mode, int pseudo,
                                          const float* __restrict__ w_cons, float* __restrict__ out) {
     __shared__ double tot[SSL_NACC_PSEUDO(SSL_MAXC)];
