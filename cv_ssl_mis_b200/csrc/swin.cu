@@ -357,27 +357,41 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinP p) {
     }
 }
 
-// dtable[idx][head] = sum over (image-windows, (i,j) with bias_index(i,j) == idx) of dS
-__global__ void __launch_bounds__(256) window_bias_grad_kernel(const float* __restrict__ part, int nBW, int heads, int ws,
-                                                               float* __restrict__ dtable, int accumulate) {
-    const int N = ws * ws, T = (2 * ws - 1) * (2 * ws - 1);
+// dtable[idx][head] = sum over (image-windows, (i,j) with bias_index(i,j) == idx) of dS, in two deterministic steps:
+// (1) coalesced column sums of part[nBW][heads*49*49] over row chunks -> part2[chunk][heads*49*49];
+// (2) one block per table entry: for every row i the matching column j follows from the entry's (dh, dw) directly.
+#define WA_BIAS_CHUNKS 32
+__global__ void __launch_bounds__(256) window_bias_colsum_kernel(const float* __restrict__ part, int nBW, int cols,
+                                                                 int rows_per_chunk, float* __restrict__ part2) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    const int w0 = blockIdx.y * rows_per_chunk, w1 = min(nBW, w0 + rows_per_chunk);
+    float s = 0.f;
+    for (int w = w0; w < w1; ++w) s += __ldg(part + (size_t)w * cols + col);
+    part2[(size_t)blockIdx.y * cols + col] = s;
+}
+__global__ void __launch_bounds__(64) window_bias_grad_kernel(const float* __restrict__ part2, int chunks, int heads, int ws,
+                                                              float* __restrict__ dtable, int accumulate) {
+    const int N = ws * ws;
     const int entry = blockIdx.x;                          // idx * heads + head
-    if (entry >= T * heads) return;
     const int idx = entry / heads, head = entry % heads;
-    __shared__ double sh[8];
+    const int dh = idx / (2 * ws - 1) - (ws - 1), dw = idx % (2 * ws - 1) - (ws - 1);   // (row_i - row_j, col_i - col_j)
+    const int cols = heads * (WA_MAXN * WA_MAXN);
+    __shared__ double sh[2];
     double s = 0;
-    // (i, j) pairs mapping to this table entry
-    for (int ij = 0; ij < N * N; ++ij) {
-        if (wa_bias_index(ws, ij / N, ij % N) != idx) continue;
-        for (int w = threadIdx.x; w < nBW; w += blockDim.x)
-            s += part[((size_t)w * heads + head) * (WA_MAXN * WA_MAXN) + ij];
+    const int i = threadIdx.x;
+    if (i < N) {
+        const int jr = i / ws - dh, jc = i % ws - dw;
+        if (jr >= 0 && jr < ws && jc >= 0 && jc < ws) {
+            const int ij = i * N + jr * ws + jc;
+            for (int c = 0; c < chunks; ++c) s += (double)part2[(size_t)c * cols + head * (WA_MAXN * WA_MAXN) + ij];
+        }
     }
     s = warp_sum_d(s);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double tot = 0;
-        for (int w = 0; w < 8; ++w) tot += sh[w];
+        const double tot = sh[0] + sh[1];
         dtable[entry] = accumulate ? dtable[entry] + (float)tot : (float)tot;
     }
 }
@@ -405,7 +419,9 @@ B200_API int b200_window_attn_fwd(const float* qkv, const float* bias_table, flo
 }
 
 B200_API long long b200_window_attn_workspace_bytes(int B, int H, int W, int heads, int ws) {
-    return (long long)B * (H / ws) * (W / ws) * heads * WA_MAXN * WA_MAXN * sizeof(float);
+    const long long nBW = (long long)B * (H / ws) * (W / ws);
+    const long long chunks = nBW < WA_BIAS_CHUNKS ? nBW : WA_BIAS_CHUNKS;
+    return (nBW + chunks) * heads * WA_MAXN * WA_MAXN * (long long)sizeof(float);
 }
 
 B200_API int b200_window_attn_bwd(const float* qkv, const float* bias_table, const float* dout, float* dqkv,
@@ -421,7 +437,12 @@ B200_API int b200_window_attn_bwd(const float* qkv, const float* bias_table, con
     window_attn_kernel<true><<<B * nW * heads, 128, 0, st>>>(p);
     B200_CHECK_LAUNCH("window_attn_bwd");
     const int T = (2 * ws - 1) * (2 * ws - 1);
-    window_bias_grad_kernel<<<T * heads, 256, 0, st>>>(workspace, B * nW, heads, ws, dbias_table, 0);
+    const int nBW = B * nW, chunks = nBW < WA_BIAS_CHUNKS ? nBW : WA_BIAS_CHUNKS;
+    const int cols = heads * WA_MAXN * WA_MAXN, rows_per_chunk = (nBW + chunks - 1) / chunks;
+    float* part2 = workspace + (size_t)nBW * cols;
+    window_bias_colsum_kernel<<<dim3((cols + 255) / 256, chunks), 256, 0, st>>>(workspace, nBW, cols, rows_per_chunk, part2);
+    B200_CHECK_LAUNCH("window_bias_colsum");
+    window_bias_grad_kernel<<<T * heads, 64, 0, st>>>(part2, chunks, heads, ws, dbias_table, 0);
     B200_CHECK_LAUNCH("window_bias_grad");
     return B200_OK;
 }
