@@ -92,6 +92,11 @@ SIGNATURES = {
     "b200_mc_softmax_accumulate": (_I, [_P, _P, _I, _I, _I, _L, _I, _I, _S]),
     "b200_ct_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
     "b200_ct_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _F, _P, _I, _S]),
+    "b200_linear_supported": (_I, [_L, _I, _I, _I]),
+    "b200_linear_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _L, _I, _S]),
+    "b200_linear_dgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _L, _I, _S]),
+    "b200_linear_wgrad_workspace_bytes": (_L, [_L, _I, _I]),
+    "b200_linear_wgrad": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _L, _L, _I, _S]),
     "b200_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "b200_layernorm_workspace_bytes": (_L, [_L, _I]),
     "b200_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _S]),
@@ -111,7 +116,7 @@ SIGNATURES = {
 
 # entry points whose int return value is NOT a status code
 _NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported",
-               "b200_conv_c1_supported"}
+               "b200_conv_c1_supported", "b200_linear_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

@@ -207,6 +207,21 @@ __global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restric
         part[(size_t)blockIdx.x * C + tid] = v;
     }
 }
+// wide matrices (C > 256): one thread per column, blockIdx.y = row chunk; coalesced 1 KB row segments
+__global__ void __launch_bounds__(256) colsum_wide_part_kernel(const float* __restrict__ g, long long M, int C,
+                                                               long long rows_per_chunk, float* __restrict__ part) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long m0 = blockIdx.y * rows_per_chunk, m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
+    float s0 = 0.f, s1 = 0.f;
+    long long m = m0;
+    for (; m + 1 < m1; m += 2) {
+        s0 += __ldg(g + m * C + c);
+        s1 += __ldg(g + (m + 1) * C + c);
+    }
+    if (m < m1) s0 += __ldg(g + m * C + c);
+    part[(size_t)blockIdx.y * C + c] = s0 + s1;
+}
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ out, int accumulate) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         double s = 0;
@@ -272,15 +287,31 @@ B200_API int b200_nhwc_to_nchw(const float* src, float* dst, long long N, int C,
     return B200_OK;
 }
 
+static inline int colsum_wide_chunks(long long M, int C) {
+    const long long colblocks = (C + 255) / 256;
+    long long chunks = ((long long)b200_num_sms() * 4 + colblocks - 1) / colblocks;
+    if (chunks > (M + 15) / 16) chunks = (M + 15) / 16;
+    return (int)(chunks < 1 ? 1 : chunks);
+}
+
 B200_API long long b200_colsum_workspace_bytes(long long M, int C) {
-    (void)M;
+    if (C > 256) return (long long)colsum_wide_chunks(M, C) * C * sizeof(float);
     return (long long)b200_num_sms() * 4 * C * sizeof(float);
 }
 
 B200_API int b200_colsum(const float* g, long long M, int C, float* out, int accumulate, float* workspace,
                          long long workspace_bytes, cudaStream_t st) {
-    B200_REQUIRE(g && out && workspace && M > 0 && C > 0 && C <= 256, "colsum: bad arguments (C <= 256)");
+    B200_REQUIRE(g && out && workspace && M > 0 && C > 0, "colsum: bad arguments");
     B200_REQUIRE(workspace_bytes >= b200_colsum_workspace_bytes(M, C), "colsum: workspace too small");
+    if (C > 256) {
+        const int chunks = colsum_wide_chunks(M, C);
+        const long long rows_per_chunk = (M + chunks - 1) / chunks;
+        colsum_wide_part_kernel<<<dim3((C + 255) / 256, chunks), 256, 0, st>>>(g, M, C, rows_per_chunk, workspace);
+        B200_CHECK_LAUNCH("colsum_wide_part");
+        colsum_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(workspace, chunks, C, out, accumulate);
+        B200_CHECK_LAUNCH("colsum_final");
+        return B200_OK;
+    }
     const int SL = 256 / C;
     long long want = (M + SL - 1) / SL;
     int grid = (int)(want < (long long)b200_num_sms() * 4 ? want : (long long)b200_num_sms() * 4);

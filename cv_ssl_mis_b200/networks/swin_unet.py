@@ -259,16 +259,25 @@ class _Linear(_Op):
         O, I = weight.shape[0], weight[0].numel()
         c0, c1 = x0.C, (x1.C if x1 is not None else 0)
         assert c0 + c1 == I and x0.M % B == 0, (name, c0, c1, I)
-        self.O, self.I = O, I
+        self.O, self.I, self.M = O, I, x0.M
+        # tcgen05/TMA GEMM straight from the module's row-major weight (no packing); the implicit-GEMM convolution
+        # engine keeps the NCHW-writing head and the `exact` (3xTF32) validation mode
+        self.umma = (not rt.exact) and (not out_nchw) and ops.linear_supported(x0.M, O, c0, c1)
+        self.wp_fwd = self.wp_bwd = None
+        if self.umma:
+            if need_grad:
+                rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(x0.M, O, I), ops.colsum_workspace_bytes(x0.M, O)))
+            return
         self.desc = ops.conv_desc(B, 1, 1, x0.M // B, c0, c1, O, 1, 1, 0, 2)
         self.wp_fwd = torch.empty(ops.conv_packed_floats(PACK_CONV_FWD, O, I, 1), dtype=torch.float32, device=rt.device)
-        self.wp_bwd = None
         if need_grad:
             rt.need_scratch(ops.conv_wgrad_workspace_bytes(self.desc))
             if input_grad:
                 self.wp_bwd = torch.empty(ops.conv_packed_floats(PACK_CONV_DGRAD, O, I, 1), dtype=torch.float32, device=rt.device)
 
     def pack_jobs(self, need_dgrad):
+        if self.umma:
+            return []
         jobs = [(self.w, self.wp_fwd, 0, PACK_CONV_FWD, self.O, self.I, 1)]
         if need_dgrad and self.wp_bwd is not None:
             jobs.append((self.w, self.wp_bwd, 0, PACK_CONV_DGRAD, self.O, self.I, 1))
@@ -276,6 +285,10 @@ class _Linear(_Op):
 
     def fwd(self, rt, train):
         _lib.tag = self.name
+        if self.umma:
+            ops.linear_fwd(self.x0.v, self.x1.v if self.x1 is not None else None, self.w.view(self.O, self.I), self.b, self.y.v,
+                           self.M, self.O)
+            return
         ops.conv_fwd(self.desc, self.x0.v, self.x1.v if self.x1 is not None else None, self.wp_fwd, self.b, self.y.v,
                      self.out_nchw, rt.exact)
 
@@ -292,6 +305,13 @@ class _Linear(_Op):
     def bwd(self, rt):
         _lib.tag = self.name
         x1 = self.x1.v if self.x1 is not None else None
+        if self.umma:
+            ops.linear_wgrad(self.x0.v, x1, self.gy, self.w.grad.view(self.O, self.I), rt.scratch, self.M, self.O)
+            if self.b is not None:
+                ops.colsum(self.gy, self.M, self.O, self.b.grad, rt.scratch)
+            if self.input_grad:
+                ops.linear_dgrad(self.gy, self.w.view(self.O, self.I), self.gx0, self.gx1, self.acc0, self.M, self.O)
+            return
         ops.conv_wgrad(self.desc, self.x0.v, x1, self.gy, rt.scratch, self.w.grad, self.b.grad if self.b is not None else None,
                        False, rt.exact)
         if self.input_grad:

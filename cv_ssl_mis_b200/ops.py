@@ -247,6 +247,31 @@ def add(a, b, c):
     _lib.call("b200_add", _pf(a), _pf(b), _pf(c), a.numel(), _st())
 
 
+# ------------------------------------------------------------------ nn.Linear on tcgen05 (gemm_umma.cu)
+def linear_supported(M, O, c0, c1) -> bool:
+    return bool(_lib.query("b200_linear_supported", M, O, c0, c1))
+
+
+def linear_fwd(x0, x1, w, bias, y, M, O):
+    c0, c1 = x0.shape[-1], (x1.shape[-1] if x1 is not None else 0)
+    _lib.call("b200_linear_fwd", _pf(x0), _pf(x1), c0, c1, _pf(w), _pf(bias), _pf(y), M, O, _st())
+
+
+def linear_dgrad(dy, w, dx0, dx1, accumulate, M, O):
+    c0, c1 = dx0.shape[-1], (dx1.shape[-1] if dx1 is not None else 0)
+    _lib.call("b200_linear_dgrad", _pf(dy), _pf(w), _pf(dx0), _pf(dx1), c0, c1, int(accumulate), M, O, _st())
+
+
+def linear_wgrad_workspace_bytes(M, O, I) -> int:
+    return int(_lib.query("b200_linear_wgrad_workspace_bytes", M, O, I))
+
+
+def linear_wgrad(x0, x1, dy, dw, ws, M, O, accumulate=False):
+    c0, c1 = x0.shape[-1], (x1.shape[-1] if x1 is not None else 0)
+    _lib.call("b200_linear_wgrad", _pf(x0), _pf(x1), c0, c1, _pf(dy), _pf(dw), int(accumulate), _p(ws),
+              ws.numel() * ws.element_size() if ws is not None else 0, M, O, _st())
+
+
 # ------------------------------------------------------------------ Swin-UNet token ops
 def layernorm_workspace_bytes(M, C_) -> int:
     return int(_lib.query("b200_layernorm_workspace_bytes", M, C_))

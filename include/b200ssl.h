@@ -178,6 +178,24 @@ int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits, const vo
 int b200_mc_softmax_accumulate(const float* logits, float* psum, int R, int U, int C, long long S, int layout_nhwc,
                                int init, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ nn.Linear on tcgen05 (TMA-fed, TF32, TMEM accumulators)
+ * Replaces torch.nn.functional.linear and its autograd for the token matrices of the Swin-UNet
+ * (swin_transformer_unet_skip_expand_decoder_sys.py: Mlp :19-25, qkv/proj :115-150, PatchMerging.reduction :346,
+ * PatchExpand.expand :378, concat_back_dim :771) and any 1x1 convolution on channels-last rows.
+ * x = [x0 | x1] is a virtual concat along the feature dim (c1 = 0: single source; else c0 % 32 == 0); w is the
+ * module's own row-major [O][c0+c1] weight (no packing); rows M, features multiples of 4, O >= 16.
+ *   fwd   : y[M][O]  = x w^T (+ bias)
+ *   dgrad : dx0[M][c0] | dx1[M][c1] (+)= dy w
+ *   wgrad : dw[O][c0+c1] (+)= dy^T x   (split over row ranges into `workspace`, reduced in fixed order) */
+int b200_linear_supported(long long M, int O, int c0, int c1);
+int b200_linear_fwd(const float* x0, const float* x1, int c0, int c1, const float* w, const float* bias, float* y,
+                    long long M, int O, cudaStream_t stream);
+int b200_linear_dgrad(const float* dy, const float* w, float* dx0, float* dx1, int c0, int c1, int accumulate,
+                      long long M, int O, cudaStream_t stream);
+long long b200_linear_wgrad_workspace_bytes(long long M, int O, int I);
+int b200_linear_wgrad(const float* x0, const float* x1, int c0, int c1, const float* dy, float* dw, int accumulate,
+                      float* workspace, long long workspace_bytes, long long M, int O, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ Swin-UNet token ops
  * code/networks/swin_transformer_unet_skip_expand_decoder_sys.py: nn.LayerNorm (:204,211,...), nn.GELU in Mlp (:19-25),
  * WindowAttention + roll/partition/reverse of SwinTransformerBlock (:115-150,244-288), DropPath residual (:284-286),

@@ -409,6 +409,35 @@ def add(a, b, c):
     c.copy_(a + b)
 
 
+# ------------------------------------------------------------------ nn.Linear (gemm_umma.cu)
+def linear_supported(M, O, c0, c1):
+    return (M > 0 and O >= 16 and O % 4 == 0 and c0 > 0 and c0 % 4 == 0 and c1 >= 0 and c1 % 4 == 0
+            and (c1 == 0 or c0 % 32 == 0))
+
+
+def linear_fwd(x0, x1, w, bias, y, M, O):
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    out = x @ w.t()
+    y.copy_(out + bias if bias is not None else out)
+
+
+def linear_dgrad(dy, w, dx0, dx1, accumulate, M, O):
+    dx = dy @ w
+    c0 = dx0.shape[-1]
+    _store(dx0, dx[:, :c0], accumulate)
+    if dx1 is not None:
+        _store(dx1, dx[:, c0:], accumulate)
+
+
+def linear_wgrad_workspace_bytes(M, O, I):
+    return 64
+
+
+def linear_wgrad(x0, x1, dy, dw, ws, M, O, accumulate=False):
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    _store(dw, dy.t() @ x, accumulate)
+
+
 # ------------------------------------------------------------------ Swin-UNet token ops
 def layernorm_workspace_bytes(M, C):
     return 64
