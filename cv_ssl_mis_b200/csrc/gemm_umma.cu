@@ -12,7 +12,8 @@
 //              (K-major) or 32x32 boxes (MN-major) into a ring of shared-memory stages, mbarrier expect_tx
 //   warp 1     MMA issuer (one lane): 4 x tcgen05.mma (K = 8) per k-block, tcgen05.commit frees the stage;
 //              owns the TMEM allocation (two accumulator buffers of BN columns)
-//   warps 2-5  epilogue: tcgen05.ld 32x32b.x16 -> bias / accumulate / split destination -> 16-byte stores
+//   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> + bias -> swizzled shared-memory tile -> TMA store (or fp32 reduce-add
+//              for accumulate) through a {column, row, split} tensor map of the destination
 #include "common.cuh"
 #include <cuda.h>
 #include <cstring>
@@ -23,7 +24,8 @@ namespace {
 constexpr int BK = 32;                   // reduction elements per stage (= one 128-byte swizzle row of fp32)
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * BK * 4;     // 16 KB
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;           // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int G_MAX_STAGES = 8;
 
 struct GemmP {
@@ -68,6 +70,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global tile store / reduce-add (fp32) through the tensor map {column, row, split}; clipped at the matrix edge
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int add) {
+    if (add)
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // shared-memory matrix descriptor (sm_100 version bit).  layout 2 = 128-byte swizzle of 16-byte chunks (K-major
 // operands); layout 1 = 128-byte swizzle of 32-byte chunks, the only swizzled layout tcgen05 accepts for MN-major
 // 32-bit (TF32) operands -- TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
@@ -111,7 +123,9 @@ __device__ __forceinline__ void tmem_ld16_unused(uint32_t taddr, uint32_t (&r)[1
 __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_constant__ CUtensorMap ta0,
                                                               const __grid_constant__ CUtensorMap ta1,
                                                               const __grid_constant__ CUtensorMap tb0,
-                                                              const __grid_constant__ CUtensorMap tb1, const GemmP p) {
+                                                              const __grid_constant__ CUtensorMap tb1,
+                                                              const __grid_constant__ CUtensorMap tc0,
+                                                              const __grid_constant__ CUtensorMap tc1, const GemmP p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[G_MAX_STAGES], empty_bar[G_MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&acc_full[a]), 1);
-            mbar_init(smem_u32(&acc_empty[a]), 4);
+            mbar_init(smem_u32(&acc_empty[a]), EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -215,54 +229,56 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue
-        // TMEM lane = output row: a thread holds 32 consecutive columns of its row.  The warp transposes each
-        // 32x32 block through a swizzled shared-memory tile so that global stores are whole 128-byte lines.
-        const int lslice = (warp & 3) * 32;
-        float4* stg = reinterpret_cast<float4*>(smem_raw + (smem0 - smem_u32(smem_raw)) + (size_t)S * stage_bytes) + (warp & 3) * 256;
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        // TMEM lane = output row: a thread holds 32 consecutive columns of its row.  Each warp adds the bias, writes its
+        // 32x32 block into a 128-byte-swizzled shared-memory tile and one lane hands it to the TMA unit (plain store,
+        // or fp32 reduce-add for accumulate) -- whole 128-byte lines, clipped at the matrix edge by the tensor map.
+        // Two warps share each 32-lane TMEM quarter and alternate over the 32-column blocks.
+        const int ew = warp - 2, lslice = (warp & 3) * 32, half = ew >> 2;
+        const uint32_t stg = smem0 + (uint32_t)S * stage_bytes + (uint32_t)ew * 4096;
         int tl = 0;
+        bool pending = false;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
             const int nt = item % p.n_tiles, mt = (item / p.n_tiles) % p.m_tiles, sp = item / (p.n_tiles * p.m_tiles);
             const int as = tl & 1;
             const int row0 = mt * BM + lslice;
             mbar_wait(smem_u32(&acc_full[as]), (tl >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float* base0 = p.dst0 + (size_t)sp * p.split_stride;
 #pragma unroll 1
-            for (int j = 0; j < BN / 32; ++j) {
+            for (int j = half; j < BN / 32; j += 2) {
+                const int c0 = nt * BN + j * 32;
+                if (row0 >= p.M || c0 >= p.N) continue;                 // warp-uniform: nothing of this block is stored
+                float4 bv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    bv[c] = (p.bias && c0 + 4 * c < p.N) ? ldg4(p.bias + c0 + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 uint32_t rg[32];
                 tmem_ld32(tmem_base + ((uint32_t)lslice << 16) + (uint32_t)(as * BN + j * 32), rg);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int c0 = nt * BN + j * 32;
-                if (row0 >= p.M || c0 >= p.N) continue;                 // warp-uniform
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    stg[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(rg[4 * c]), __uint_as_float(rg[4 * c + 1]),
-                                                                   __uint_as_float(rg[4 * c + 2]), __uint_as_float(rg[4 * c + 3]));
-                __syncwarp();
-                const int cc = lane & 7, col = c0 + cc * 4;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && col < p.N) bv = ldg4(p.bias + col);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = 4 * i + (lane >> 3), row = row0 + r;
-                    float4 val = stg[r * 8 + (cc ^ (r & 7))];
-                    if (row < p.M && col < p.N) {
-                        val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
-                        float* o = col < p.ncol0 ? base0 + (size_t)row * p.ld0 + col : p.dst1 + (size_t)row * p.ld1 + (col - p.ncol0);
-                        if (p.accumulate) {
-                            const float4 old = *reinterpret_cast<const float4*>(o);
-                            val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-                        }
-                        *reinterpret_cast<float4*>(o) = val;
-                    }
+                if (pending) {                                           // the previous store must have read the tile
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
                 }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t dst = stg + (uint32_t)lane * 128 + (uint32_t)((c ^ (lane & 7)) * 16);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(__uint_as_float(rg[4 * c]) + bv[c].x),
+                                 "f"(__uint_as_float(rg[4 * c + 1]) + bv[c].y), "f"(__uint_as_float(rg[4 * c + 2]) + bv[c].z),
+                                 "f"(__uint_as_float(rg[4 * c + 3]) + bv[c].w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+                if (lane == 0) {
+                    if (c0 < p.ncol0) tma_store_3d(&tc0, stg, c0, row0, sp, p.accumulate);
+                    else tma_store_3d(&tc1, stg, c0 - p.ncol0, row0, 0, p.accumulate);
+                }
+                pending = true;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -322,6 +338,22 @@ int make_map(CUtensorMap* m, const float* base, long long rows, long long cols, 
     return B200_OK;
 }
 
+// output [splits][rows][cols] fp32, row stride ld, split stride ss (elements); 32x32 boxes, 128-byte swizzle
+int make_out_map(CUtensorMap* m, float* base, long long rows, long long cols, long long ld, long long splits, long long ss,
+                 const char* who) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { b200_set_error("%s: cuTensorMapEncodeTiled is unavailable", who); return B200_ERR_CUDA; }
+    if (((uintptr_t)base & 15) || (ld & 3) || (ss & 3)) { b200_set_error("%s: output must be 16-byte aligned with strides multiple of 4", who); return B200_ERR_ARG; }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(splits > 1 ? ss : rows * ld) * 4};
+    const cuuint32_t box[3] = {32u, 32u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200_set_error("%s: cuTensorMapEncodeTiled (output) failed (%d)", who, (int)r); return B200_ERR_CUDA; }
+    return B200_OK;
+}
+
 // tile width (multiple of 32, <= 256): minimise waves x per-tile cost, where a tile's k-block moves 128 + BN rows
 int choose_bn(int N, long long m_tiles, int splits) {
     int best = 32;
@@ -352,10 +384,14 @@ int launch_gemm(GemmP& p, const CUtensorMap& a0, const CUtensorMap& a1, const CU
     p.n_tiles = (p.N + p.BN - 1) / p.BN;
     p.kb_total = (p.K + BK - 1) / BK;
     const int stage = A_BYTES + p.BN * BK * 4;
-    int S = (184 * 1024) / stage;
+    int S = (190 * 1024) / stage;
     if (S > G_MAX_STAGES) S = G_MAX_STAGES;
     p.nstages = S;
-    const int bytes = S * stage + 1024 + 4 * 4096;           // + alignment slack + one 32x32 staging tile per epilogue warp
+    const int bytes = S * stage + 1024 + EPI_WARPS * 4096;   // + alignment slack + one 32x32 staging tile per epilogue warp
+    CUtensorMap c0, c1;
+    if (int rc = make_out_map(&c0, p.dst0, p.M, p.ncol0, p.ld0, p.splits, p.split_stride, who)) return rc;
+    c1 = c0;
+    if (p.dst1) if (int rc = make_out_map(&c1, p.dst1, p.M, p.N - p.ncol0, p.ld1, 1, 0, who)) return rc;
     static int attr_bytes = 0;
     if (bytes > attr_bytes) {
         cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -363,7 +399,7 @@ int launch_gemm(GemmP& p, const CUtensorMap& a0, const CUtensorMap& a1, const CU
     }
     const long long items = (long long)p.m_tiles * p.n_tiles * p.splits;
     const int grid = (int)(items < b200_num_sms() ? items : b200_num_sms());
-    gemm_umma_kernel<<<grid, G_THREADS, bytes, st>>>(a0, a1, b0, b1, p);
+    gemm_umma_kernel<<<grid, G_THREADS, bytes, st>>>(a0, a1, b0, b1, c0, c1, p);
     B200_CHECK_LAUNCH(who);
     return B200_OK;
 }

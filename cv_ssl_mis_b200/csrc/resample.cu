@@ -207,20 +207,44 @@ __global__ void __launch_bounds__(256) colsum_part_kernel(const float* __restric
         part[(size_t)blockIdx.x * C + tid] = v;
     }
 }
-// wide matrices (C > 256): one thread per column, blockIdx.y = row chunk; coalesced 1 KB row segments
-__global__ void __launch_bounds__(256) colsum_wide_part_kernel(const float* __restrict__ g, long long M, int C,
-                                                               long long rows_per_chunk, float* __restrict__ part) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// C % 4 == 0: a thread owns one float4 column; CW column-threads x (256 / CW) row slices per block, blockIdx.y = row
+// chunk; four independent 16-byte loads in flight per thread, slices reduced through shared memory in fixed order
+__global__ void __launch_bounds__(256) colsum_v4_part_kernel(const float* __restrict__ g, long long M, int C4, int CW,
+                                                             long long rows_per_chunk, float* __restrict__ part) {
+    __shared__ float4 sred[256];
+    const int tid = threadIdx.x, cw = tid % CW, sl = tid / CW, SL = 256 / CW;
+    const int c4 = blockIdx.x * CW + cw;
     const long long m0 = blockIdx.y * rows_per_chunk, m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
-    float s0 = 0.f, s1 = 0.f;
-    long long m = m0;
-    for (; m + 1 < m1; m += 2) {
-        s0 += __ldg(g + m * C + c);
-        s1 += __ldg(g + (m + 1) * C + c);
+    float4 s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < C4) {
+        const float* col = g + (size_t)c4 * 4;
+        const size_t ld = (size_t)C4 * 4;
+        long long m = m0 + sl;
+        for (; m + 3 * SL < m1; m += 4 * SL) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = ldg4_stream(col + (size_t)(m + u * SL) * ld);
+                s[u].x += v.x; s[u].y += v.y; s[u].z += v.z; s[u].w += v.w;
+            }
+        }
+        for (; m < m1; m += SL) {
+            const float4 v = ldg4_stream(col + (size_t)m * ld);
+            s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        }
     }
-    if (m < m1) s0 += __ldg(g + m * C + c);
-    part[(size_t)blockIdx.y * C + c] = s0 + s1;
+    sred[tid] = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                            (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
+    __syncthreads();
+    if (tid < CW && c4 < C4) {
+        float4 v = sred[tid];
+        for (int k = 1; k < SL; ++k) {
+            const float4 w = sred[k * CW + tid];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        stg4(part + (size_t)blockIdx.y * C4 * 4 + (size_t)c4 * 4, v);
+    }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ out, int accumulate) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
@@ -287,27 +311,34 @@ B200_API int b200_nhwc_to_nchw(const float* src, float* dst, long long N, int C,
     return B200_OK;
 }
 
-static inline int colsum_wide_chunks(long long M, int C) {
-    const long long colblocks = (C + 255) / 256;
-    long long chunks = ((long long)b200_num_sms() * 4 + colblocks - 1) / colblocks;
-    if (chunks > (M + 15) / 16) chunks = (M + 15) / 16;
+static inline int colsum_cw(int C4) {
+    int cw = 1;
+    while (cw < C4 && cw < 64) cw <<= 1;
+    return cw;
+}
+static inline int colsum_v4_chunks(long long M, int C) {
+    const int C4 = C / 4, CW = colsum_cw(C4);
+    const long long colblocks = (C4 + CW - 1) / CW;
+    long long chunks = ((long long)b200_num_sms() * 6 + colblocks - 1) / colblocks;
+    const long long max_chunks = (M + 63) / 64;
+    if (chunks > max_chunks) chunks = max_chunks;
     return (int)(chunks < 1 ? 1 : chunks);
 }
 
 B200_API long long b200_colsum_workspace_bytes(long long M, int C) {
-    if (C > 256) return (long long)colsum_wide_chunks(M, C) * C * sizeof(float);
+    if ((C & 3) == 0) return (long long)colsum_v4_chunks(M, C) * C * sizeof(float);
     return (long long)b200_num_sms() * 4 * C * sizeof(float);
 }
 
 B200_API int b200_colsum(const float* g, long long M, int C, float* out, int accumulate, float* workspace,
                          long long workspace_bytes, cudaStream_t st) {
-    B200_REQUIRE(g && out && workspace && M > 0 && C > 0, "colsum: bad arguments");
+    B200_REQUIRE(g && out && workspace && M > 0 && C > 0 && ((C & 3) == 0 || C <= 256), "colsum: bad arguments (C % 4 == 0 or C <= 256)");
     B200_REQUIRE(workspace_bytes >= b200_colsum_workspace_bytes(M, C), "colsum: workspace too small");
-    if (C > 256) {
-        const int chunks = colsum_wide_chunks(M, C);
+    if ((C & 3) == 0) {
+        const int C4 = C / 4, CW = colsum_cw(C4), chunks = colsum_v4_chunks(M, C);
         const long long rows_per_chunk = (M + chunks - 1) / chunks;
-        colsum_wide_part_kernel<<<dim3((C + 255) / 256, chunks), 256, 0, st>>>(g, M, C, rows_per_chunk, workspace);
-        B200_CHECK_LAUNCH("colsum_wide_part");
+        colsum_v4_part_kernel<<<dim3((C4 + CW - 1) / CW, chunks), 256, 0, st>>>(g, M, C4, CW, rows_per_chunk, workspace);
+        B200_CHECK_LAUNCH("colsum_v4_part");
         colsum_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(workspace, chunks, C, out, accumulate);
         B200_CHECK_LAUNCH("colsum_final");
         return B200_OK;
