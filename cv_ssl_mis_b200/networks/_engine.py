@@ -7,6 +7,7 @@ networks together with the BatchNorm -> activation -> dropout that follows it, e
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -52,6 +53,11 @@ class Runtime:
         self.seed_off = torch.zeros(1, dtype=torch.int64, device=device)
         self.scratch = None
         self.scratch_bytes = 0
+        # weight gradients only feed the optimizer, so they run on a side stream next to the data-gradient chain
+        # (own scratch buffer; joined at the end of the plan's backward).  B200_OVERLAP=0 keeps one stream.
+        self.overlap = torch.device(device).type == "cuda" and os.environ.get("B200_OVERLAP", "1") != "0"
+        self.side = torch.cuda.Stream(device=device) if self.overlap else None
+        self.scratch_side = None
 
     def need_scratch(self, nbytes):
         self.scratch_bytes = max(self.scratch_bytes, int(nbytes))
@@ -59,6 +65,18 @@ class Runtime:
     def alloc_scratch(self):
         if self.scratch is None or self.scratch.numel() * 4 < self.scratch_bytes:
             self.scratch = torch.empty((self.scratch_bytes + 3) // 4 + 4, dtype=torch.float32, device=self.device)
+            self.scratch_side = torch.empty_like(self.scratch) if self.overlap else self.scratch
+
+    def side_stream(self):
+        """Context: run the enclosed launches on the side stream, after everything issued so far on the current one."""
+        if not self.overlap:
+            return contextlib.nullcontext()
+        self.side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.side)
+
+    def join_side(self):
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.side)
 
 
 class ConvLayer:
@@ -211,12 +229,14 @@ class ConvLayer:
         dy = self.g
         bias_grad = conv.bias.grad if conv.bias is not None else None
         if self.kind == "conv":
-            if self.c1:
-                ops.conv_c1_wgrad(self.desc, src0, dy, rt.scratch, conv.weight.grad, bias_grad, False)
-            elif self.tile_wgrad:
-                ops.conv_tile_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False)
-            else:
-                ops.conv_wgrad(self.desc, src0, src1, dy, rt.scratch, conv.weight.grad, bias_grad, False, rt.exact)
+            with rt.side_stream():
+                ws = rt.scratch_side
+                if self.c1:
+                    ops.conv_c1_wgrad(self.desc, src0, dy, ws, conv.weight.grad, bias_grad, False)
+                elif self.tile_wgrad:
+                    ops.conv_tile_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, False)
+                else:
+                    ops.conv_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, False, rt.exact)
             if dx0 is not None:
                 if self.umma_dgrad:
                     ops.conv_umma_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
@@ -227,9 +247,10 @@ class ConvLayer:
                 else:
                     ops.conv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
         else:
-            ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch, conv.weight.grad, False, rt.exact)
-            if bias_grad is not None:
-                ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch)
+            with rt.side_stream():
+                ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch_side, conv.weight.grad, False, rt.exact)
+                if bias_grad is not None:
+                    ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side)
             if dx0 is not None:
                 ops.deconv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
 

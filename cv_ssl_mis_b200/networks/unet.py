@@ -171,6 +171,7 @@ class UNetPlan:
                 h, w = h * 2, w * 2
             else:
                 la.backward(rt, self.x_in, None, None)
+        rt.join_side()
 
 
 class _UNetFn(torch.autograd.Function):

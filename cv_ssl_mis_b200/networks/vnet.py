@@ -140,6 +140,7 @@ class VNetPlan:
                 dw.backward(rt, prev.a, None, prev.g, accumulate_dx=True)     # adds to the skip gradient
             else:
                 st[0].backward(rt, self.x_in, None, None)
+        rt.join_side()
 
 
 class _VNetFn(torch.autograd.Function):

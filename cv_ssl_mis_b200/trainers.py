@@ -114,23 +114,18 @@ class MeanTeacherTrainer:
         self.s_off += 1
         self.model.train()
         xu = self.x[self.Lb:]
-        self.s_plan.forward(self.x, train=True)
         teacher_logits = psum = thr = None
+        # the teacher passes (no grad, own buffers and RNG epoch) run on a side stream next to the student forward
+        t_rt = self.ema_model._rt if self.U else None
         if self.U:
-            self.t_off += 1
-            ops.noise_add(xu, self.ema_in, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
-            self.t_plan.forward(self.ema_in, train=True)          # teacher stays in train mode (Appendix A.1)
+            with t_rt.side_stream():
+                self._teacher_passes(xu)
             teacher_logits = self.t_plan.logits
-        if self.T:
-            # volume_batch_r = unlabeled.repeat(2, ...); T//2 noisy passes of the 2U batch (:153-160)
-            self.x_rep[:self.U].copy_(xu)
-            self.x_rep[self.U:].copy_(xu)
-            for i in range(self.T // 2):
-                self.t_off += 1
-                ops.noise_add(self.x_rep, self.ema_in2, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
-                self.t_plan2.forward(self.ema_in2, train=True)
-                ops.mc_softmax_accumulate(self.t_plan2.logits, self.psum, 2, self.U, self.C, self.S, False, i == 0)
-            psum, thr = self.psum, self.hp[HP_THRESHOLD:HP_THRESHOLD + 1]
+            if self.T:
+                psum, thr = self.psum, self.hp[HP_THRESHOLD:HP_THRESHOLD + 1]
+        self.s_plan.forward(self.x, train=True)
+        if self.U:
+            t_rt.join_side()
         w = self.hp[HP_WCONS:HP_WCONS + 1]
         ops.ssl_loss_fwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
                          self.lossbuf, self.loss_ws, psum, float(self.T), thr)
@@ -141,6 +136,20 @@ class MeanTeacherTrainer:
             torch.distributed.all_reduce(self.flat.grad, group=self.pg)
         ops.sgd_ema_step(self.flat.data, self.flat.grad, self.momentum_buf,
                          self.ema_flat.data if self.ema_flat is not None else None, self.hp)
+
+    def _teacher_passes(self, xu):
+        self.t_off += 1
+        ops.noise_add(xu, self.ema_in, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
+        self.t_plan.forward(self.ema_in, train=True)          # teacher stays in train mode (Appendix A.1)
+        if self.T:
+            # volume_batch_r = unlabeled.repeat(2, ...); T//2 noisy passes of the 2U batch (:153-160)
+            self.x_rep[:self.U].copy_(xu)
+            self.x_rep[self.U:].copy_(xu)
+            for i in range(self.T // 2):
+                self.t_off += 1
+                ops.noise_add(self.x_rep, self.ema_in2, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
+                self.t_plan2.forward(self.ema_in2, train=True)
+                ops.mc_softmax_accumulate(self.t_plan2.logits, self.psum, 2, self.U, self.C, self.S, False, i == 0)
 
     def step(self, images, labels, read_loss=False):
         """images [B,1,*patch] float32, labels [B,*patch] uint8 (2D) / int64 (3D) -- host (ideally pinned) or device.
