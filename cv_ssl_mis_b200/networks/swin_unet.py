@@ -306,11 +306,15 @@ class _Linear(_Op):
         _lib.tag = self.name
         x1 = self.x1.v if self.x1 is not None else None
         if self.umma:
-            ops.linear_wgrad(self.x0.v, x1, self.gy, self.w.grad.view(self.O, self.I), rt.scratch, self.M, self.O)
-            if self.b is not None:
-                ops.colsum(self.gy, self.M, self.O, self.b.grad, rt.scratch)
+            # weight / bias gradient on the side stream next to the data gradient; joined before the next tape
+            # op because the gradient pool may hand this op's dy buffer to a later op
+            with rt.side_stream():
+                ops.linear_wgrad(self.x0.v, x1, self.gy, self.w.grad.view(self.O, self.I), rt.scratch_side, self.M, self.O)
+                if self.b is not None:
+                    ops.colsum(self.gy, self.M, self.O, self.b.grad, rt.scratch_side)
             if self.input_grad:
                 ops.linear_dgrad(self.gy, self.w.view(self.O, self.I), self.gx0, self.gx1, self.acc0, self.M, self.O)
+            rt.join_side()
             return
         ops.conv_wgrad(self.desc, self.x0.v, x1, self.gy, rt.scratch, self.w.grad, self.b.grad if self.b is not None else None,
                        False, rt.exact)

@@ -218,6 +218,7 @@ class CrossTeachingTrainer:
                  max_iterations=30000, consistency=0.1, consistency_rampup=200.0, momentum=0.9, weight_decay=1e-4,
                  start_iter=0, label_dtype=torch.uint8, process_group=None, use_cuda_graph=False):
         self.models = (model1, model2)
+        self.aux = None
         self.B, self.Lb, self.patch, self.C = batch_size, labeled_bs, tuple(patch_size), num_classes
         self.base_lr, self.max_iterations = base_lr, max_iterations
         self.consistency, self.consistency_rampup = consistency, consistency_rampup
@@ -264,18 +265,40 @@ class CrossTeachingTrainer:
             off += 1
             m.train()
         p1, p2 = self.plans
-        p1.forward(self.x, train=True)                                     # :224-228
+        # the two networks are independent except at the loss: model 1 runs on an auxiliary stream next to model 2
+        overlap = self.dev.type == "cuda" and self.world == 1
+        if overlap and self.aux is None:
+            self.aux = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream() if overlap else None
+
+        def on_aux(fn):
+            if not overlap:
+                return fn()
+            self.aux.wait_stream(main)
+            with torch.cuda.stream(self.aux):
+                fn()
+
+        on_aux(lambda: p1.forward(self.x, train=True))                     # :224-228
         p2.forward(self.x, train=True)
+        if overlap:
+            main.wait_stream(self.aux)
         w = self.hp[HP_WCONS:HP_WCONS + 1]
         for mine, other, lb in ((p1, p2, self.lossbufs[0]), (p2, p1, self.lossbufs[1])):
             ops.ct_loss_fwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, w, lb, self.loss_ws)
             ops.ct_loss_bwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, lb, 1.0,
                             mine.g_logits, True)
-        for plan, flat, mom in zip(self.plans, self.flats, self.momentum_bufs):
+
+        def update(i):
+            plan, flat, mom = self.plans[i], self.flats[i], self.momentum_bufs[i]
             plan.backward(None)                                            # :252-255 (loss = model1_loss + model2_loss)
             if self.world > 1:
                 torch.distributed.all_reduce(flat.grad, group=self.pg)
             ops.sgd_ema_step(flat.data, flat.grad, mom, None, self.hp)     # :257-258
+
+        on_aux(lambda: update(0))
+        update(1)
+        if overlap:
+            main.wait_stream(self.aux)
 
     def step(self, images, labels, read_loss=False):
         """images [B,1,H,W] float32, labels [B,H,W] uint8.  Returns the two device loss buffers, or with read_loss the
