@@ -55,6 +55,12 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def rows(self):
+        try:
+            return sum(1 for _ in open(self.f.name))
+        except OSError:
+            return 0
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -223,18 +229,27 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    # nvidia-smi needs ~100 ms before its first sample: start it before the warm-up and keep it running through both
+    # timed regions (the GPU is under the same load from here to sampler.stop())
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(max(args.warmup, 3)):
         tr.step(xd, yd)
-    sampler = ClockSampler(local) if rank == 0 else None
     n0 = _lib.launch_count
     ms = timed(lambda i: tr.step(xd, yd), args.steps)
     launches = tr.kernel_launches_per_step * args.steps if tr.kernel_launches_per_step else _lib.launch_count - n0
-    clocks = sampler.stop() if sampler else None
     loss_dev = tr.lossbuf[:4].tolist()
 
     for i in range(2):
         tr.step(*host[i % 4], read_loss=True)
     ms_e2e = timed(lambda i: tr.step(*host[i % 4], read_loss=True), args.steps)
+    clocks = None
+    if sampler:
+        # short runs end before nvidia-smi has printed enough rows: hold the same load (untimed) until it has
+        t_end = time.time() + 3.0
+        while world == 1 and sampler.rows() < 5 and time.time() < t_end:      # (collective inside the step: 1 rank only)
+            tr.step(xd, yd)
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
 
     out = None
     # every rank runs the eager profiling pass (its steps contain the gradient all-reduce); rank 0 reports

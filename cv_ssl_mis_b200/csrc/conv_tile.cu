@@ -107,7 +107,7 @@ struct FwdSmem {
 };
 
 template <int DIMS, int BN>
-__global__ void __launch_bounds__(256) conv_tile_fwd_kernel(const TileP p) {
+__global__ void __launch_bounds__(256, (DIMS == 2 && BN == 16) ? 4 : 1) conv_tile_fwd_kernel(const TileP p) {
     using S = TileShape<DIMS>;
     using SM = FwdSmem<DIMS, BN>;
     constexpr int NT = BN / 8;                           // n8 tiles
