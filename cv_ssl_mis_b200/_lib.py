@@ -97,6 +97,12 @@ SIGNATURES = {
     "b200_linear_dgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _L, _I, _S]),
     "b200_linear_wgrad_workspace_bytes": (_L, [_L, _I, _I]),
     "b200_linear_wgrad": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _L, _L, _I, _S]),
+    "b200_patch3d_gather": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
+    "b200_mha_probs_floats": (_L, [_I, _I, _I]),
+    "b200_mha_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _S]),
+    "b200_mha_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _S]),
+    "b200_add_lrelu_fwd": (_I, [_P, _P, _P, _L, _F, _S]),
+    "b200_lrelu_bwd": (_I, [_P, _P, _P, _L, _F, _S]),
     "b200_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "b200_layernorm_workspace_bytes": (_L, [_L, _I]),
     "b200_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _S]),

@@ -217,8 +217,9 @@ class ConvLayer:
         return self.a
 
     # ---- backward: self.g holds d/d(output); writes parameter grads and (optionally) input grads
-    def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False, g_in=None):
-        """g_in: read d/d(output) from another buffer (left untouched) instead of self.g (needs has_act)."""
+    def backward(self, rt: Runtime, src0, src1=None, dx0=None, dx1=None, accumulate_dx=False, g_in=None, accumulate_w=False):
+        """g_in: read d/d(output) from another buffer (left untouched) instead of self.g (needs has_act).
+        accumulate_w: add to the parameter gradients (the same weights applied to several inputs, e.g. per-sample plans)."""
         conv, bn = self.conv, self.bn
         _lib.tag = self.name
         assert g_in is None or self.has_act
@@ -232,11 +233,11 @@ class ConvLayer:
             with rt.side_stream():
                 ws = rt.scratch_side
                 if self.c1:
-                    ops.conv_c1_wgrad(self.desc, src0, dy, ws, conv.weight.grad, bias_grad, False)
+                    ops.conv_c1_wgrad(self.desc, src0, dy, ws, conv.weight.grad, bias_grad, accumulate_w)
                 elif self.tile_wgrad:
-                    ops.conv_tile_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, False)
+                    ops.conv_tile_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, accumulate_w)
                 else:
-                    ops.conv_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, False, rt.exact)
+                    ops.conv_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, accumulate_w, rt.exact)
             if dx0 is not None:
                 if self.umma_dgrad:
                     ops.conv_umma_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
@@ -248,9 +249,9 @@ class ConvLayer:
                     ops.conv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
         else:
             with rt.side_stream():
-                ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch_side, conv.weight.grad, False, rt.exact)
+                ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch_side, conv.weight.grad, accumulate_w, rt.exact)
                 if bias_grad is not None:
-                    ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side)
+                    ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side, accumulate_w)
             if dx0 is not None:
                 ops.deconv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
 

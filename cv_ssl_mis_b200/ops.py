@@ -272,6 +272,31 @@ def linear_wgrad(x0, x1, dy, dw, ws, M, O, accumulate=False):
               ws.numel() * ws.element_size() if ws is not None else 0, M, O, _st())
 
 
+# ------------------------------------------------------------------ UNETR ops (vit.cu)
+def patch3d_gather(x, y, B, C_, D, H, W, patch):
+    _lib.call("b200_patch3d_gather", _pf(x), _pf(y), B, C_, D, H, W, patch, _st())
+
+
+def mha_probs_floats(B, N, heads) -> int:
+    return int(_lib.query("b200_mha_probs_floats", B, N, heads))
+
+
+def mha_fwd(qkv, out, probs, B, N, heads, hd):
+    _lib.call("b200_mha_fwd", _pf(qkv), _pf(out), _pf(probs), B, N, heads, hd, _st())
+
+
+def mha_bwd(qkv, probs, dout, dqkv, ws, B, N, heads, hd):
+    _lib.call("b200_mha_bwd", _pf(qkv), _pf(probs), _pf(dout), _pf(dqkv), _p(ws), ws.numel() * ws.element_size(), B, N, heads, hd, _st())
+
+
+def add_lrelu_fwd(a, b, out, slope):
+    _lib.call("b200_add_lrelu_fwd", _pf(a), _pf(b), _pf(out), a.numel(), slope, _st())
+
+
+def lrelu_bwd(out, dout, dx, slope):
+    _lib.call("b200_lrelu_bwd", _pf(out), _pf(dout), _pf(dx), out.numel(), slope, _st())
+
+
 # ------------------------------------------------------------------ Swin-UNet token ops
 def layernorm_workspace_bytes(M, C_) -> int:
     return int(_lib.query("b200_layernorm_workspace_bytes", M, C_))

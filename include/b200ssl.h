@@ -196,6 +196,19 @@ long long b200_linear_wgrad_workspace_bytes(long long M, int O, int I);
 int b200_linear_wgrad(const float* x0, const float* x1, int c0, int c1, const float* dy, float* dw, int accumulate,
                       float* workspace, long long workspace_bytes, long long M, int O, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ UNETR (code/networks/unetr.py:215-230 over MONAI blocks)
+ * patch3d_gather: einops "b c (h p1) (w p2) (d p3) -> b (h w d) (p1 p2 p3 c)" of PatchEmbeddingBlock("perceptron").
+ * mha: SABlock -- qkv [B*N][3C] (q | k | v, head-major inside each, no bias), softmax(q k^T / sqrt(hd)) v; N <= 256,
+ *      hd <= 64; `probs` [B*heads][N][N] is written by fwd and read by bwd (workspace: as many floats again).
+ * add_lrelu / lrelu_bwd: `out += residual; out = lrelu(out)` of UnetResBlock and its gradient. */
+int b200_patch3d_gather(const float* x, float* y, int B, int C, int D, int H, int W, int patch, cudaStream_t stream);
+long long b200_mha_probs_floats(int B, int N, int heads);
+int b200_mha_fwd(const float* qkv, float* out, float* probs, int B, int N, int heads, int hd, cudaStream_t stream);
+int b200_mha_bwd(const float* qkv, const float* probs, const float* dout, float* dqkv, float* workspace,
+                 long long workspace_bytes, int B, int N, int heads, int hd, cudaStream_t stream);
+int b200_add_lrelu_fwd(const float* a, const float* b, float* out, long long n, float slope, cudaStream_t stream);
+int b200_lrelu_bwd(const float* out, const float* dout, float* dx, long long n, float slope, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ Swin-UNet token ops
  * code/networks/swin_transformer_unet_skip_expand_decoder_sys.py: nn.LayerNorm (:204,211,...), nn.GELU in Mlp (:19-25),
  * WindowAttention + roll/partition/reverse of SwinTransformerBlock (:115-150,244-288), DropPath residual (:284-286),

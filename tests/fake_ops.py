@@ -438,6 +438,47 @@ def linear_wgrad(x0, x1, dy, dw, ws, M, O, accumulate=False):
     _store(dw, dy.t() @ x, accumulate)
 
 
+# ------------------------------------------------------------------ UNETR ops (vit.cu)
+def patch3d_gather(x, y, B, C, D, H, W, patch):
+    P = patch
+    t = x.reshape(B, C, D // P, P, H // P, P, W // P, P).permute(0, 2, 4, 6, 3, 5, 7, 1)      # b h w d p1 p2 p3 c
+    y.copy_(t.reshape(y.shape))
+
+
+def mha_probs_floats(B, N, heads):
+    return B * heads * N * N
+
+
+def _mha(qkv, B, N, heads, hd):
+    C = heads * hd
+    q, k, v = qkv.reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = ((q @ k.transpose(-1, -2)) * hd ** -0.5).softmax(-1)
+    return (att @ v).permute(0, 2, 1, 3).reshape(B * N, C), att
+
+
+def mha_fwd(qkv, out, probs, B, N, heads, hd):
+    o, att = _mha(qkv, B, N, heads, hd)
+    out.copy_(o)
+    if probs is not None:
+        probs[:B * heads * N * N].copy_(att.reshape(-1))
+
+
+def mha_bwd(qkv, probs, dout, dqkv, ws, B, N, heads, hd):
+    leaf = qkv.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        o, _ = _mha(leaf, B, N, heads, hd)
+        g, = torch.autograd.grad(o, leaf, dout.reshape(o.shape))
+    dqkv.copy_(g)
+
+
+def add_lrelu_fwd(a, b, out, slope):
+    out.copy_(F.leaky_relu(a + b, slope))
+
+
+def lrelu_bwd(out, dout, dx, slope):
+    dx.copy_(torch.where(out > 0, dout, dout * slope))
+
+
 # ------------------------------------------------------------------ Swin-UNet token ops
 def layernorm_workspace_bytes(M, C):
     return 64

@@ -298,3 +298,62 @@ def test_cross_teaching_trainer_matches_oracle(fake):
                 torch.testing.assert_close(now2[k], sd2[k], rtol=2e-3, atol=1e-6, msg=lambda m, k=k: f"swin {k}: {m}")
     assert tr.iter_num == it0 + 2
     assert abs(tr.lr - O.poly_lr(0.01, it0 + 2, 30000)) < 1e-15
+
+
+# ------------------------------------------------------------------ UNETR (config 5)
+UNETR_SMALL = dict(img_size=(32, 32, 32), feature_size=8, hidden_size=64, mlp_dim=128, num_heads=2, conv_block=True,
+                   res_block=True)
+
+
+def test_unetr_plan_matches_oracle(fake):
+    """Forward logits and every parameter gradient of the UNETR launch schedule (ViT tape + per-sample conv decoder,
+    InstanceNorm as batch-of-one BatchNorm, weight gradients accumulated over samples) against the restated oracle."""
+    from oracle import unetr_oracle as UO
+    from cv_ssl_mis_b200.networks import unetr as U
+    torch.manual_seed(5)
+    net = U.UNETR(1, 2, **UNETR_SMALL)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 1, 32, 32, 32, generator=g)
+    y = torch.randint(0, 2, (2, 32, 32, 32), generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, logits = UO.fully_supervised_loss(leaf, x, y, 2, 2)
+    loss.backward()
+    out = net(x)
+    torch.testing.assert_close(out, logits, rtol=1e-4, atol=1e-4)
+    O.supervised_loss(out, y, 2)[0].backward()
+    for k, p in net.named_parameters():
+        if leaf[k].grad is None:          # cls_token: unused when classification=False
+            continue
+        scale = float(leaf[k].grad.abs().max()) + 1e-12
+        assert float((p.grad - leaf[k].grad).abs().max()) / scale < 1e-2, k       # fp32 reassociation through 12 blocks
+    # MONAI's state_dict schema
+    for key in ("vit.patch_embedding.patch_embeddings.1.weight", "vit.patch_embedding.position_embeddings",
+                "vit.patch_embedding.cls_token", "vit.blocks.11.attn.qkv.weight", "vit.blocks.0.mlp.linear1.bias",
+                "vit.norm.weight", "encoder1.layer.conv3.conv.weight", "encoder2.transp_conv_init.conv.weight",
+                "encoder2.blocks.1.1.conv2.conv.weight", "decoder5.conv_block.conv3.conv.weight",
+                "decoder2.transp_conv.conv.weight", "out.conv.conv.bias"):
+        assert key in sd, key
+    assert "encoder2.blocks.0.1.conv3.conv.weight" not in sd and "vit.blocks.0.attn.qkv.bias" not in sd
+
+
+def test_unetr_fully_supervised_trainer_step(fake):
+    """One fully-supervised step (train_fully_supervised_3D_ViT.py: SGD on 0.5 (CE + Dice)) through MeanTeacherTrainer."""
+    from oracle import unetr_oracle as UO
+    from cv_ssl_mis_b200.networks import unetr as U
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(6)
+    net = U.UNETR(1, 2, **UNETR_SMALL)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 1, 32, 32, 32, generator=g)
+    y = torch.randint(0, 2, (2, 32, 32, 32), generator=g)
+    tr = MeanTeacherTrainer(net, None, batch_size=2, labeled_bs=2, patch_size=(32, 32, 32), num_classes=2, base_lr=0.01)
+    ce, dice, cons, total = tr.step(x, y)[:4].tolist()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss, _ = UO.fully_supervised_loss(leaf, x, y, 2, 2)
+    loss.backward()
+    assert abs(total - float(loss)) < 1e-4 * abs(float(loss))
+    k = "decoder2.conv_block.conv1.conv.weight"
+    expect = sd[k] - 0.01 * (leaf[k].grad + 1e-4 * sd[k])                 # first SGD step: buf = g + wd * p
+    torch.testing.assert_close(dict(net.named_parameters())[k].detach(), expect, rtol=1e-3, atol=1e-6)
