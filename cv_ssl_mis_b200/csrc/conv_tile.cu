@@ -239,19 +239,22 @@ __global__ void __launch_bounds__(256, (DIMS == 2 && BN == 16) ? 4 : 1) conv_til
 
 // =====================================================================================
 // wgrad: part[split][tap*Cin + c][n] = sum_{pixels of the split} halo[pixel + tap][c] * dy[pixel][n]
-//   CTA = (16-channel chunk of x, BN columns of dy, a range of pixel tiles); warps = (BN/16) column groups x
-//   pixel groups, each holding all 9 (2D) taps of its 16x16 block in registers.
+//   CTA = (16-channel chunk of x, BN columns of dy, [3D: one kd plane of taps,] a range of pixel tiles); warps =
+//   (BN/16) column groups x pixel groups, each holding the 9 (kh, kw) taps of its 16x16 block in registers.  In 3D the
+//   27 taps do not fit in registers, so blockIdx.y also enumerates kd and the CTA stages only the 4 depth planes
+//   [d0 + kd - 1, d0 + kd + 3) of the halo.
 // =====================================================================================
 template <int DIMS, int BN>
 struct WgSmem {
     using S = TileShape<DIMS>;
     static constexpr int GSTR = BN + 8;                  // dy row stride: (BN + 8) % 32 in {8, 24} -> conflict-free B frags
     static constexpr int XSTR = 24;                      // x row stride: lanes (pixel t, channel g) -> bank 24 t + g, all distinct
-    static constexpr int HALO_F = S::HPIX * XSTR;
+    static constexpr int HPIX_W = S::TD * S::HH * S::HW; // halo pixels staged per tile: the TD depth planes one kd needs
+    static constexpr int HALO_F = HPIX_W * XSTR;
     static constexpr int G_F = S::PIX * GSTR;
     static constexpr int STAGE_F = HALO_F + G_F;
     static constexpr int CG = BN / 16, PG = 8 / CG;      // column groups, pixel groups
-    static constexpr int RED_F = PG * S::TAPS * 16 * BN; // cross-pixel-group reduction buffer
+    static constexpr int RED_F = PG * S::TAPS2 * 16 * BN; // cross-pixel-group reduction buffer
     static constexpr int PIPE_F = 2 * STAGE_F;
     static constexpr size_t BYTES = (size_t)(PIPE_F > RED_F ? PIPE_F : RED_F) * sizeof(float);
 };
@@ -262,27 +265,27 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
     using SM = WgSmem<DIMS, BN>;
     constexpr int CG = SM::CG, PG = SM::PG, GSTR = SM::GSTR;
     constexpr int KSTEPS = S::PIX / 8 / PG;              // k8 (pixel) steps per warp per tile
-    static_assert(DIMS == 2, "3D weight gradients use the generic kernel (27 taps do not fit in registers)");
     extern __shared__ __align__(16) float smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int cg = warp % CG, pg = warp / CG;
-    const int chunk = blockIdx.x, n0 = blockIdx.y * BN;
+    const int kd = DIMS == 3 ? blockIdx.y % 3 : 0;
+    const int chunk = blockIdx.x, n0 = (DIMS == 3 ? blockIdx.y / 3 : blockIdx.y) * BN;
     const int tiles_img = p.tiles_d * p.tiles_h * p.tiles_w;
     const int ntiles = p.N * tiles_img;
     const int tbeg = blockIdx.z * p.tiles_per_split;
     const int tend = min(ntiles, tbeg + p.tiles_per_split);
 
-    float acc[S::TAPS][2][4];
+    float acc[S::TAPS2][2][4];
 #pragma unroll
-    for (int a = 0; a < S::TAPS; ++a)
+    for (int a = 0; a < S::TAPS2; ++a)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[a][j][e] = 0.f;
     float colsum = 0.f;
-    const bool do_colsum = p.part_colsum != nullptr && chunk == 0;
+    const bool do_colsum = p.part_colsum != nullptr && chunk == 0 && kd == 0;
 
     auto issue = [&](int tile, int stage) {
         int q = tile;
@@ -292,7 +295,24 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
         const int n = q / p.tiles_d;
         const int d0 = td * S::TD, h0 = th * S::TH, w0 = tw * S::TW;
         float* st = smem + stage * SM::STAGE_F;
-        load_halo<DIMS, SM::XSTR>(p, st, n, d0, h0, w0, chunk * KC, tid);
+        if (DIMS == 2) {
+            load_halo<DIMS, SM::XSTR>(p, st, n, d0, h0, w0, chunk * KC, tid);
+        } else {
+            // depth planes d0 + kd - 1 + [0, TD) only: local plane index hd pairs with output depth d0 + hd
+            for (int s = tid; s < SM::HPIX_W * 4; s += 256) {
+                const int hp = s >> 2, piece = s & 3;
+                const int hw = hp % S::HW, hh = (hp / S::HW) % S::HH, hd = hp / (S::HW * S::HH);
+                const int id = d0 + hd + kd - 1, ih = h0 + hh - 1, iw = w0 + hw - 1;
+                const int ch = chunk * KC + piece * 4;
+                const bool ok = (unsigned)id < (unsigned)p.D && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W && ch < p.Cin;
+                const float* src = p.src0;
+                if (ok) {
+                    const size_t pix = (((size_t)n * p.D + id) * p.H + ih) * p.W + iw;
+                    src = ch < p.C0 ? p.src0 + pix * p.C0 + ch : p.src1 + pix * p.C1 + (ch - p.C0);
+                }
+                cp_async16(st + hp * SM::XSTR + piece * 4, src, ok);
+            }
+        }
         float* sg = st + SM::HALO_F;
         for (int s = tid; s < S::PIX * (BN / 4); s += 256) {
             const int pt = s / (BN / 4), piece = s % (BN / 4);
@@ -332,7 +352,7 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) { bu[j][0] = f2tf32(bf[j][0]); bu[j][1] = f2tf32(bf[j][1]); }
 #pragma unroll
-            for (int tap = 0; tap < S::TAPS; ++tap) {
+            for (int tap = 0; tap < S::TAPS2; ++tap) {
                 const int kh = tap / 3, kw = tap % 3;
                 const float* a = sh + (hoff + kh * S::HW + kw + t) * SM::XSTR + g;
                 uint32_t au[4];
@@ -352,26 +372,26 @@ __global__ void __launch_bounds__(256) conv_tile_wgrad_kernel(const TileP p) {
     }
 
     // ---------------- reduce the pixel groups, write this split's partial
-    float* red = smem;                                     // [PG][TAPS][16][BN]
+    float* red = smem;                                     // [PG][9][16][BN]
 #pragma unroll
-    for (int tap = 0; tap < S::TAPS; ++tap)
+    for (int tap = 0; tap < S::TAPS2; ++tap)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int r = g + 8 * (e >> 1), c = cg * 16 + j * 8 + 2 * t + (e & 1);
-                red[((pg * S::TAPS + tap) * 16 + r) * BN + c] = acc[tap][j][e];
+                red[((pg * S::TAPS2 + tap) * 16 + r) * BN + c] = acc[tap][j][e];
             }
     __syncthreads();
     const int K = S::TAPS * p.Cin;
     float* out = p.part + (size_t)blockIdx.z * K * p.NG;
-    for (int idx = tid; idx < S::TAPS * 16 * BN; idx += 256) {
+    for (int idx = tid; idx < S::TAPS2 * 16 * BN; idx += 256) {
         const int c = idx % BN, r = (idx / BN) % 16, tap = idx / (BN * 16);
         float v = 0.f;
 #pragma unroll
-        for (int q = 0; q < PG; ++q) v += red[((q * S::TAPS + tap) * 16 + r) * BN + c];
+        for (int q = 0; q < PG; ++q) v += red[((q * S::TAPS2 + tap) * 16 + r) * BN + c];
         const int ci = chunk * KC + r, col = n0 + c;
-        if (ci < p.Cin && col < p.NG) out[((size_t)tap * p.Cin + ci) * p.NG + col] = v;
+        if (ci < p.Cin && col < p.NG) out[((size_t)(kd * S::TAPS2 + tap) * p.Cin + ci) * p.NG + col] = v;
     }
     if (do_colsum) {
         __syncthreads();
@@ -443,7 +463,7 @@ B200_API int b200_conv_tile_supported(const b200_conv_desc* d, int for_wgrad) {
     if (!d || d->stride != 1 || d->kh != 3 || d->kw != 3 || d->ph != 1 || d->pw != 1) return 0;
     if (!((d->kd == 1 && d->pd == 0) || (d->kd == 3 && d->pd == 1))) return 0;
     if ((d->c0 & 3) || (d->c1 & 3)) return 0;                         // 16-byte pieces must not straddle sources
-    if (for_wgrad) return d->kd == 1 && (d->cout & 3) == 0;
+    if (for_wgrad) return (d->cout & 3) == 0;
     return 1;
 }
 
@@ -515,18 +535,21 @@ B200_API int b200_conv_tile_dgrad(const b200_conv_desc* d, const float* dy, cons
 struct TileWgPlan { int BN; int splits; int tiles_per_split; size_t ws_bytes; };
 
 static TileWgPlan plan_tile_wgrad(const b200_conv_desc* d) {
-    using S = TileShape<2>;
     TileWgPlan pl;
     const int Cin = d->c0 + d->c1;
-    pl.BN = d->cout <= 16 ? 16 : (d->cout <= 32 ? 32 : 64);
-    const int ntiles = d->n * ((d->ih + S::TH - 1) / S::TH) * ((d->iw + S::TW - 1) / S::TW);
-    const int ctas = ((Cin + KC - 1) / KC) * ((d->cout + pl.BN - 1) / pl.BN);
+    const bool is3 = d->kd == 3;
+    // 3D: two stages of (4 x 10 x 10 halo + 256 x BN dy) must fit in shared memory -> BN <= 32
+    pl.BN = d->cout <= 16 ? 16 : ((d->cout <= 32 || is3) ? 32 : 64);
+    const int ntiles = is3 ? d->n * ((d->id + 3) / 4) * ((d->ih + 7) / 8) * ((d->iw + 7) / 8)
+                           : d->n * ((d->ih + 15) / 16) * ((d->iw + 15) / 16);
+    const int taps = is3 ? 27 : 9;
+    const int ctas = ((Cin + KC - 1) / KC) * ((d->cout + pl.BN - 1) / pl.BN) * (is3 ? 3 : 1);
     int splits = (2 * b200_num_sms() + ctas - 1) / ctas;
     if (splits > ntiles) splits = ntiles;
     if (splits < 1) splits = 1;
     pl.tiles_per_split = (ntiles + splits - 1) / splits;
     pl.splits = (ntiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
-    pl.ws_bytes = ((size_t)pl.splits * 9 * Cin * d->cout + (size_t)pl.splits * d->cout) * sizeof(float);
+    pl.ws_bytes = ((size_t)pl.splits * taps * Cin * d->cout + (size_t)pl.splits * d->cout) * sizeof(float);
     return pl;
 }
 
@@ -539,16 +562,16 @@ B200_API long long b200_conv_tile_wgrad_workspace_bytes(const b200_conv_desc* d)
 int b200_wgrad_reduce_launch(const float* part, const float* part_colsum, int splits, int K, int NG, int A, int T,
                              float* dw, float* db, int accumulate, cudaStream_t st);
 
-template <int BN>
+template <int DIMS, int BN>
 static int launch_tile_wgrad(const TileP& p, int splits, cudaStream_t st) {
-    using SM = WgSmem<2, BN>;
-    auto kern = conv_tile_wgrad_kernel<2, BN>;
+    using SM = WgSmem<DIMS, BN>;
+    auto kern = conv_tile_wgrad_kernel<DIMS, BN>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
         attr_done = true;
     }
-    dim3 grid((p.Cin + KC - 1) / KC, (p.NG + BN - 1) / BN, splits);
+    dim3 grid((p.Cin + KC - 1) / KC, ((p.NG + BN - 1) / BN) * (DIMS == 3 ? 3 : 1), splits);
     kern<<<grid, 256, SM::BYTES, st>>>(p);
     B200_CHECK_LAUNCH("conv_tile_wgrad");
     return B200_OK;
@@ -558,7 +581,6 @@ B200_API int b200_conv_tile_wgrad(const b200_conv_desc* d, const float* src0, co
                                   float* workspace, long long workspace_bytes, float* dw, float* db, int accumulate,
                                   cudaStream_t st) {
     if (int rc = tile_supported(d, "conv_tile_wgrad")) return rc;
-    B200_REQUIRE(d->kd == 1, "conv_tile_wgrad: 2D only");
     B200_REQUIRE(src0 && dy && workspace && dw && (d->c1 == 0 || src1), "conv_tile_wgrad: null pointer");
     B200_REQUIRE((d->c0 & 3) == 0 && (d->c1 & 3) == 0 && (d->cout & 3) == 0, "conv_tile_wgrad: channels must be multiples of 4");
     TileWgPlan pl = plan_tile_wgrad(d);
@@ -569,14 +591,18 @@ B200_API int b200_conv_tile_wgrad(const b200_conv_desc* d, const float* src0, co
     TileP p;
     memset(&p, 0, sizeof(p));
     p.src0 = src0; p.src1 = src1; p.C0 = d->c0; p.C1 = d->c1; p.Cin = d->c0 + d->c1;
-    p.N = d->n; p.D = 1; p.H = d->ih; p.W = d->iw;
-    fill_tiles<2>(p);
+    const bool is3 = d->kd == 3;
+    const int taps = is3 ? 27 : 9;
+    p.N = d->n; p.D = is3 ? d->id : 1; p.H = d->ih; p.W = d->iw;
+    if (is3) fill_tiles<3>(p); else fill_tiles<2>(p);
     p.g = dy; p.NG = d->cout;
     p.part = workspace;
-    p.part_colsum = db ? workspace + (size_t)pl.splits * 9 * p.Cin * p.NG : nullptr;
+    p.part_colsum = db ? workspace + (size_t)pl.splits * taps * p.Cin * p.NG : nullptr;
     p.tiles_per_split = pl.tiles_per_split;
-    int rc = pl.BN == 16 ? launch_tile_wgrad<16>(p, pl.splits, st)
-                         : (pl.BN == 32 ? launch_tile_wgrad<32>(p, pl.splits, st) : launch_tile_wgrad<64>(p, pl.splits, st));
+    int rc;
+    if (is3) rc = pl.BN == 16 ? launch_tile_wgrad<3, 16>(p, pl.splits, st) : launch_tile_wgrad<3, 32>(p, pl.splits, st);
+    else rc = pl.BN == 16 ? launch_tile_wgrad<2, 16>(p, pl.splits, st)
+                          : (pl.BN == 32 ? launch_tile_wgrad<2, 32>(p, pl.splits, st) : launch_tile_wgrad<2, 64>(p, pl.splits, st));
     if (rc) return rc;
-    return b200_wgrad_reduce_launch(p.part, p.part_colsum, pl.splits, 9 * p.Cin, p.NG, p.Cin, 9, dw, db, accumulate, st);
+    return b200_wgrad_reduce_launch(p.part, p.part_colsum, pl.splits, taps * p.Cin, p.NG, p.Cin, taps, dw, db, accumulate, st);
 }

@@ -438,6 +438,10 @@ class UNETRPlan:
     def logits(self):            # [B, C, D*H*W] (NCDHW)
         return self.logits_all
 
+    @property
+    def g_logits(self):          # channels-last d(loss)/d(logits), [B*D*H*W, C]
+        return self.g_logits_all
+
     def forward(self, x, train=True):
         """x: [B, C, D, H, W] fp32 contiguous (C = 1: identical to channels-last)."""
         rt = self.rt

@@ -92,6 +92,10 @@ class VNetPlan:
     def logits(self):
         return self.head.y
 
+    @property
+    def g_logits(self):          # channels-last d(loss)/d(logits), [B*D*H*W, C]
+        return self.head.g
+
     def forward(self, x, train=True):
         rt = self.rt
         self.packer.run()

@@ -6,7 +6,8 @@ code/train_cross_teaching_between_cnn_transformer_2D.py:221-262 (two students, n
   * Mean Teacher 2D/3D            code/train_mean_teacher_2D.py:201-238, code/train_mean_teacher_3D.py:134-166
   * Uncertainty-Aware Mean Teacher code/train_uncertainty_aware_mean_teacher_3D.py:135-189 (2D twin: ..._2D.py:147-201)
     (`uncertainty_T=8`: T/2 extra stochastic teacher passes on the twice-repeated unlabeled batch, entropy mask)
-  * fully supervised               code/train_fully_supervised_2D.py:104-123                  (`ema_model=None`)
+  * fully supervised               code/train_fully_supervised_2D.py:104-123, ..._3D_ViT.py   (`ema_model=None`)
+  * Mean Teacher with Swin-UNets   code/train_mean_teacher_ViT.py:201-233 (the same loop over two ViT_seg models)
 noise -> student forward -> teacher forward(s) (train mode, no grad) -> CE + Dice + (masked) consistency -> student
 backward -> [grad all-reduce] -> SGD + EMA -> poly LR.  Everything between the host->device copy of the batch and
 the loss read-back is asynchronous on one stream, allocates nothing, reads its per-step scalars from a small device
@@ -73,12 +74,12 @@ class MeanTeacherTrainer:
         self.lossbuf = torch.zeros(32, dtype=torch.float32, device=dev)
         self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if pin else torch.zeros(4)
         self.loss_ws = torch.empty(ops.ssl_loss_workspace_bytes(self.B, S) // 4 + 4, dtype=torch.float32, device=dev)
-        self.s_plan = model._get_plan(self.B, *self.patch, True)
-        self.t_plan = ema_model._get_plan(self.U, *self.patch, False) if self.U else None
+        self.s_plan = _plan_for(model, self.B, self.patch, True)
+        self.t_plan = _plan_for(ema_model, self.U, self.patch, False) if self.U else None
         if self.T:
             self.x_rep = torch.empty((2 * self.U, 1, *self.patch), dtype=torch.float32, device=dev)
             self.ema_in2 = torch.empty_like(self.x_rep)
-            self.t_plan2 = ema_model._get_plan(2 * self.U, *self.patch, False)
+            self.t_plan2 = _plan_for(ema_model, 2 * self.U, self.patch, False)
             self.psum = torch.empty((self.U, self.C, S), dtype=torch.float32, device=dev)
         self.lr = base_lr                     # the reference installs the poly LR *after* each step (:234-236)
         self.use_graph = use_cuda_graph and dev.type == "cuda"
@@ -130,7 +131,7 @@ class MeanTeacherTrainer:
         ops.ssl_loss_fwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
                          self.lossbuf, self.loss_ws, psum, float(self.T), thr)
         ops.ssl_loss_bwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
-                         self.lossbuf, 1.0, self.s_plan.head.g, True, psum, float(self.T), thr)
+                         self.lossbuf, 1.0, self.s_plan.g_logits, True, psum, float(self.T), thr)
         self.s_plan.backward(None)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat.grad, group=self.pg)

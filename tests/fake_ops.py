@@ -176,7 +176,7 @@ def conv_tile_supported(d, for_wgrad=False):
     ok = (d.stride == 1 and d.kh == 3 and d.kw == 3 and d.ph == 1 and d.pw == 1 and
           ((d.kd == 1 and d.pd == 0) or (d.kd == 3 and d.pd == 1)) and d.c0 % 4 == 0 and d.c1 % 4 == 0)
     if for_wgrad:
-        ok = ok and d.kd == 1 and d.cout % 4 == 0
+        ok = ok and d.cout % 4 == 0
     return bool(ok)
 
 

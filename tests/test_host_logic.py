@@ -357,3 +357,41 @@ def test_unetr_fully_supervised_trainer_step(fake):
     k = "decoder2.conv_block.conv1.conv.weight"
     expect = sd[k] - 0.01 * (leaf[k].grad + 1e-4 * sd[k])                 # first SGD step: buf = g + wd * p
     torch.testing.assert_close(dict(net.named_parameters())[k].detach(), expect, rtol=1e-3, atol=1e-6)
+
+
+def test_mean_teacher_with_swin_unets_matches_oracle(fake):
+    """code/train_mean_teacher_ViT.py:201-233: the Mean-Teacher loop over two ViT_seg (Swin-UNet) models.  One step with
+    the consistency term live (iter >= 1000): loss terms, the student's SGD update and the teacher's EMA update."""
+    from oracle import swin_oracle as SO
+    from tests import swin_common as SC
+    from cv_ssl_mis_b200.networks import swin_unet as S
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(41)
+    cfgd = dict(SWIN_SMALL, drop_path_rate=0.0)
+    student, teacher = S.SwinUnet(dict(cfgd), num_classes=4, seed=5), S.SwinUnet(dict(cfgd), num_classes=4, seed=6)
+    s_sd, t_sd = SC.swin_sd(student), SC.swin_sd(teacher)
+    B, Lb, P, it = 4, 2, 64, 1500
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it,
+                            noise_seed=7)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(B, 1, P, P, generator=g)
+    y = SC.blocky_labels(g, B, P, P, 4)
+    ce, dice, cons, total = tr.step(x, y, read_loss=True)
+    cfg = SO.swin_config(s_sd, P, 4, 0.0)
+    noise = torch.from_numpy(philox.clamp_noise(7 + 1, 1000, (B - Lb) * P * P)).reshape(B - Lb, 1, P, P)
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in s_sd.items()}
+    s_logits = SO.swin_unet_forward(leaf, x, cfg, True)
+    with torch.no_grad():
+        t_logits = SO.swin_unet_forward(t_sd, x[Lb:] + noise, cfg, True)
+    w = O.consistency_weight(it)
+    loss, ce_r, dice_r, cons_r = O.mt_loss(s_logits, t_logits, y, Lb, 4, w)
+    loss.backward()
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([ce_r, dice_r, cons_r, loss]).detach(),
+                               rtol=1e-4, atol=1e-6)
+    alpha = O.ema_alpha(it)
+    now_s, now_t = SC.swin_sd(student), SC.swin_sd(teacher)
+    for k in ("layers.0.blocks.0.mlp.fc1.weight", "layers_up.3.blocks.1.attn.qkv.bias", "output.weight"):
+        new = s_sd[k] - 0.01 * (leaf[k].grad + 1e-4 * s_sd[k])
+        torch.testing.assert_close(now_s[k], new, rtol=2e-3, atol=1e-6, msg=lambda m, k=k: f"student {k}: {m}")
+        torch.testing.assert_close(now_t[k], alpha * t_sd[k] + (1 - alpha) * new, rtol=2e-3, atol=1e-6,
+                                   msg=lambda m, k=k: f"teacher {k}: {m}")

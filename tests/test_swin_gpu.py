@@ -288,3 +288,31 @@ def test_cross_teaching_trainer_graph_matches_oracle(monkeypatch):
         if sd2[k].dtype.is_floating_point:
             torch.testing.assert_close(now2[k].cpu(), sd2[k], rtol=5e-3, atol=2e-5, msg=lambda m, k=k: f"swin {k}: {m}")
     assert tr.kernel_launches_per_step and tr.kernel_launches_per_step > 100
+
+
+def test_mean_teacher_vit_graph_matches_oracle():
+    """code/train_mean_teacher_ViT.py:201-233 -- MeanTeacherTrainer over two Swin-UNets (CUDA-graph replay, TF32 GEMMs)
+    against the oracle's Mean-Teacher loss at iter >= 1000; second step checks the EMA'd teacher is used."""
+    from oracle import philox
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(41)
+    cfgd = dict(img_size=64, embed_dim=32, num_heads=(1, 2, 4, 8), window_size=4, drop_path_rate=0.0)
+    student, teacher = S.SwinUnet(dict(cfgd), num_classes=4, seed=5), S.SwinUnet(dict(cfgd), num_classes=4, seed=6)
+    s_sd, t_sd = SC.swin_sd(student), SC.swin_sd(teacher)
+    student, teacher = student.cuda(), teacher.cuda()
+    B, Lb, P, it = 4, 2, 64, 1500
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it,
+                            noise_seed=7, use_cuda_graph=True)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(B, 1, P, P, generator=g)
+    y = SC.blocky_labels(g, B, P, P, 4)
+    got = tr.step(x, y, read_loss=True)
+    cfg = SO.swin_config(s_sd, P, 4, 0.0)
+    noise = torch.from_numpy(philox.clamp_noise(7 + 1, 1000, (B - Lb) * P * P)).reshape(B - Lb, 1, P, P)
+    with torch.no_grad():
+        s_logits = SO.swin_unet_forward(s_sd, x, cfg, True)
+        t_logits = SO.swin_unet_forward(t_sd, x[Lb:] + noise, cfg, True)
+        loss, ce, dice, cons = O.mt_loss(s_logits, t_logits, y, Lb, 4, O.consistency_weight(it))
+    torch.testing.assert_close(torch.tensor(got), torch.stack([ce, dice, cons, loss]), rtol=1e-2, atol=1e-4)
+    got2 = tr.step(x, y, read_loss=True)
+    assert got2[3] == got2[3] and got2[3] != got[3]
