@@ -496,9 +496,13 @@ static int launch_tile_fwd(const TileP& p, cudaStream_t st) {
 template <int DIMS>
 static int dispatch_tile_fwd(TileP& p, cudaStream_t st) {
     fill_tiles<DIMS>(p);
-    // wider column tiles amortise the halo reads; narrow ones keep more CTAs resident for small channel counts
-    if (p.Cout <= 16) return launch_tile_fwd<DIMS, 16>(p, st);
-    if (p.Cout <= 32) return launch_tile_fwd<DIMS, 32>(p, st);
+    // wider column tiles amortise the halo reads; narrow ones keep more CTAs resident for small channel counts --
+    // and the deep, spatially tiny layers (e.g. 256 channels at 6^3) need the narrow tiles to fill the 148 SMs at all
+    int bn = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : 64);
+    const long long tiles = (long long)p.N * p.tiles_d * p.tiles_h * p.tiles_w;
+    while (bn > 16 && tiles * ((p.Cout + bn - 1) / bn) < b200_num_sms()) bn >>= 1;
+    if (bn == 16) return launch_tile_fwd<DIMS, 16>(p, st);
+    if (bn == 32) return launch_tile_fwd<DIMS, 32>(p, st);
     return launch_tile_fwd<DIMS, 64>(p, st);
 }
 
