@@ -285,6 +285,14 @@ def run_ours(args):
                          "peak_source": pk["src"] + " (MEASURED_PEAKS.json: HBM copy GB/s; dense bf16 sustained TF/s for tensor)",
                          "share_of_step": t_ms / total,
                          "per_layer_us_GBs_TFs": sorted(per_layer, key=lambda r: -r[1])[:6]})
+        # dram__bytes_read + dram__bytes_write per launch of that kernel, from the committed ncu --set full capture
+        tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        if roof is not None and os.path.exists(tfile):
+            with open(tfile) as f:
+                tr_ = json.load(f)
+            if tr_.get("kernel") == top_name:
+                roof["traffic"] = tr_["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr_["source"]
         shares = {k: round(v / total, 4) for k, v in sorted(by_name.items(), key=lambda kv: -kv[1])[:8]}
         value = B * world * args.steps / (ms * 1e-3)
         e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
