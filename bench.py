@@ -162,6 +162,11 @@ def conv_cost(layer, op):
 def profile_pass(tr, x, y, reps=3):
     from cv_ssl_mis_b200 import _lib
     graph, tr.use_graph = tr.use_graph, False
+    # kernels are timed alone: the side streams (weight gradients, teacher passes) are folded back into the main one
+    rts = [m._rt for m in (tr.model, tr.ema_model) if m is not None]
+    overlap = [rt.overlap for rt in rts]
+    for rt in rts:
+        rt.overlap = False
     tr.step(x, y)
     torch.cuda.synchronize()
     _lib.profile = []
@@ -171,6 +176,8 @@ def profile_pass(tr, x, y, reps=3):
     torch.cuda.synchronize()
     rec, _lib.profile = _lib.profile, None
     tr.use_graph = graph
+    for rt, ov in zip(rts, overlap):
+        rt.overlap = ov
     agg = {}
     for name, tag, e0, e1 in rec:
         k = (name, tag)
@@ -293,6 +300,33 @@ def run_ours(args):
             if tr_.get("kernel") == top_name:
                 roof["traffic"] = tr_["dram_bytes_per_launch"]
                 roof["traffic_source"] = tr_["source"]
+        # per entry point: algorithmic bytes / flops of all its launches in one step over their summed device time
+        # (eager pass, CUDA events on the launching stream; small kernels carry ~2 us of event granularity each)
+        Sx, U_ = H * W, B - B // 2
+        extra = {"b200_sgd_ema_step": 28.0 * tr.flat.padded,
+                 "b200_ssl_loss_fwd": 4.0 * NCLS * Sx * (B + U_) + (B // 2) * Sx,
+                 "b200_ssl_loss_bwd": 4.0 * NCLS * Sx * (B + U_) + (B // 2) * Sx + 4.0 * NCLS * Sx * B,
+                 "b200_noise_add": 8.0 * U_ * Sx}
+        table = {}
+        for (name, tag), ms_step, calls in rows:
+            if tag in layers and name.startswith(("b200_conv", "b200_bn")):
+                by, fl = conv_cost(layers[tag], name)
+            elif name in extra:
+                by, fl = extra[name] / calls, 0.0
+            else:
+                continue
+            e = table.setdefault(name, [0.0, 0.0, 0.0, 0.0])
+            e[0] += ms_step; e[1] += by * calls; e[2] += fl * calls; e[3] += calls
+        ridge = pk["tf_sustained"] * 1e12 / (pk["hbm"] * 1e9)
+        kernels = []
+        for name, (ms_k, by_k, fl_k, calls_k) in sorted(table.items(), key=lambda kv: -kv[1][0]):
+            gbs, tfs = by_k / (ms_k * 1e-3) / 1e9, fl_k / (ms_k * 1e-3) / 1e12
+            bound = "tensor" if (fl_k and fl_k / by_k > ridge) else "hbm"
+            kernels.append({"entry": name, "launches_per_step": round(calls_k, 1), "ms_per_step": round(ms_k, 4),
+                            "GB/s": round(gbs, 1), "TFLOP/s": round(tfs, 1), "bound": bound,
+                            "frac": round(tfs / pk["tf_sustained"] if bound == "tensor" else gbs / pk["hbm"], 3)})
+            if bound == "tensor":      # the path computes in TF32, whose tensor-pipe rate is half the dense bf16 peak used above
+                kernels[-1]["frac_of_tf32_rate"] = round(2 * tfs / pk["tf_sustained"], 3)
         shares = {k: round(v / total, 4) for k, v in sorted(by_name.items(), key=lambda kv: -kv[1])[:8]}
         value = B * world * args.steps / (ms * 1e-3)
         e2e_v = B * world * args.steps / (ms_e2e * 1e-3)
@@ -306,7 +340,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * H * W * 4 + B * H * W + 32, "d2h_bytes_per_step": 16},
-            "roofline": roof, "step_time_shares": shares, "profiled_eager_ms_per_step": total, "loss": loss_dev,
+            "roofline": roof, "kernels": kernels, "step_time_shares": shares, "profiled_eager_ms_per_step": total, "loss": loss_dev,
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
