@@ -309,7 +309,7 @@ def run_ours(args):
                  "b200_noise_add": 8.0 * U_ * Sx}
         table = {}
         for (name, tag), ms_step, calls in rows:
-            if tag in layers and name.startswith(("b200_conv", "b200_bn")):
+            if tag in layers and name.startswith(("b200_conv", "b200_bn", "b200_linear")):
                 by, fl = conv_cost(layers[tag], name)
             elif name in extra:
                 by, fl = extra[name] / calls, 0.0

@@ -122,6 +122,16 @@ class ConvLayer:
         # production path for 3x3 / 3x3x3 stride-1 convs: shared-memory tile kernels (TF32); the generic implicit
         # GEMM serves everything else and the `exact` (3xTF32) validation mode
         is_conv = self.kind == "conv"
+        # 1x1 (1x1x1) convolutions are plain GEMMs over the channels-last rows: tcgen05/TMA GEMM, no weight packing
+        self.gemm = (is_conv and self.k == 1 and self.stride == 1 and not rt.exact and not self.out_nchw
+                     and self.cout >= 32 and self.cin >= 32 and ops.linear_supported(self.M, self.cout, c0, c1))
+        if self.gemm:
+            self.umma_fwd = self.umma_dgrad = self.c1 = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = False
+            self.wp_fwd = self.wp_bwd = None
+            if need_grad:
+                rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(self.M, self.cout, self.cin),
+                                    ops.colsum_workspace_bytes(self.M, self.cout)))
+            return self
         # 2D 3x3: tcgen05/TMEM kernel (B200_CONV=tile falls back to the mma.sync tile kernel for A/B comparisons)
         want_umma = is_conv and not rt.exact and os.environ.get("B200_CONV", "umma") == "umma"
         # measured (tools/bench_conv.py): with fp32 operands the UMMA is bound by its shared-memory operand reads,
@@ -158,6 +168,8 @@ class ConvLayer:
         """(weight, packed buffer, kind, mode, O, I, T) tuples for the one-launch packer (ops.conv_pack_batch)."""
         O, I, T, w = self.cout, self.cin, self.T, self.conv.weight
         jobs = []
+        if self.gemm:
+            return jobs
         if not self.c1:
             if self.umma_fwd:
                 jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
@@ -176,6 +188,8 @@ class ConvLayer:
 
     def pack(self, need_dgrad):
         O, I = self.cout, self.cin
+        if self.gemm:
+            return
         if self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
@@ -193,7 +207,9 @@ class ConvLayer:
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
         _lib.tag = self.name
-        if self.c1:
+        if self.gemm:
+            ops.linear_fwd(src0, src1, self.conv.weight.view(self.cout, self.cin), self.conv.bias, self.y, self.M, self.cout)
+        elif self.c1:
             ops.conv_c1_fwd(self.desc, src0, self.conv.weight, self.conv.bias, self.y)
         elif self.umma_fwd:
             ops.conv_umma_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
@@ -229,7 +245,15 @@ class ConvLayer:
                            self.spatial)
         dy = self.g
         bias_grad = conv.bias.grad if conv.bias is not None else None
-        if self.kind == "conv":
+        if self.gemm:
+            with rt.side_stream():
+                ops.linear_wgrad(src0, src1, dy, conv.weight.grad.view(self.cout, self.cin), rt.scratch_side, self.M, self.cout,
+                                 accumulate_w)
+                if bias_grad is not None:
+                    ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side, accumulate_w)
+            if dx0 is not None:
+                ops.linear_dgrad(dy, conv.weight.view(self.cout, self.cin), dx0, dx1, accumulate_dx, self.M, self.cout)
+        elif self.kind == "conv":
             with rt.side_stream():
                 ws = rt.scratch_side
                 if self.c1:
