@@ -131,12 +131,18 @@ __global__ void __launch_bounds__(256) ssl_loss_fwd_kernel(const LossGeom g, dou
             float lse2;
             softmax_inplace<C>(q, lse2);
             const int t = argmax_first<C>(q);
+            if (g.pseudo == 2) {                  // cross pseudo supervision: CE against the other model's argmax
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                acc[(PSEUDO ? 3 + 4 * C : 0) + c] += p[c] * p[c];
-                if (c == t) {
-                    acc[(PSEUDO ? 3 + 3 * C : 0) + c] += p[c];
-                    acc[(PSEUDO ? 3 + 5 * C : 0) + c] += 1.f;
+                for (int c = 0; c < C; ++c)
+                    if (c == t) acc[1] += lse - raw[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    acc[(PSEUDO ? 3 + 4 * C : 0) + c] += p[c] * p[c];
+                    if (c == t) {
+                        acc[(PSEUDO ? 3 + 3 * C : 0) + c] += p[c];
+                        acc[(PSEUDO ? 3 + 5 * C : 0) + c] += 1.f;
+                    }
                 }
             }
         } else if (g.teacher) {
@@ -217,7 +223,15 @@ __global__ void __launch_bounds__(1024) ssl_loss_finalize_kernel(const double* _
         }
         const float w = w_cons ? w_cons[0] : 0.f;
         float dscale = 0.f;
-        if (pseudo) {
+        if (pseudo == 2) {
+            // CE over the U*S unlabeled pixels; [4+2C] carries w / (U S) for the backward kernel
+            for (int c = 0; c < 2 * C; ++c) out[5 + 2 * C + c] = 0.f;
+            if (U > 0) {
+                const double denom = (double)U * (double)S;
+                cons = (float)(tot[1] / denom);
+                dscale = (float)((double)w / denom);
+            }
+        } else if (pseudo) {
             if (U > 0)
                 cons = (float)dice_from_sums(tot + 3 + 3 * Cpad, tot + 3 + 4 * Cpad, tot + 3 + 5 * Cpad, C, (double)w,
                                              out + 5 + 2 * C, out + 5 + 3 * C);
@@ -276,14 +290,20 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
             float lse2;
             softmax_inplace<C>(q, lse2);
             const int t = argmax_first<C>(q);
-            float gd[C], dot = 0.f;
+            if (g.pseudo == 2) {
+                const float sc = gscale * lossbuf[4 + 2 * g.C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                gd[c] = A2[c] * p[c] - (c == t ? B2[c] : 0.f);
-                dot += gd[c] * p[c];
+                for (int c = 0; c < C; ++c) dz[c] = sc * (p[c] - (c == t ? 1.f : 0.f));
+            } else {
+                float gd[C], dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    gd[c] = A2[c] * p[c] - (c == t ? B2[c] : 0.f);
+                    dot += gd[c] * p[c];
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) dz[c] = gscale * p[c] * (gd[c] - dot);
             }
-#pragma unroll
-            for (int c = 0; c < C; ++c) dz[c] = gscale * p[c] * (gd[c] - dot);
         } else if (g.teacher && mse_scale != 0.f && (g.mc_psum == nullptr || mc_mask<C>(g, n - g.Lb, s))) {
             float q[C];
             load_logits<C>(g.teacher, g.nhwc, n - g.Lb, s, g.S, g.C, q);
@@ -396,36 +416,67 @@ B200_API int b200_ssl_loss_bwd(const float* logits, const float* teacher_logits,
 // Cross-teaching loss of ONE model (code/train_cross_teaching_between_cnn_transformer_2D.py:229-247):
 //   0.5 (CE + Dice)(logits[:Lb], y) + w * Dice(softmax(logits[Lb:]), argmax softmax(other[Lb:]))
 // lossbuf (>= 5 + 4C floats): [0] ce [1] dice [2] pseudo-label dice [3] total, then gradient coefficients
-B200_API int b200_ct_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
-                              const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* w_cons,
-                              float* lossbuf, void* workspace, long long workspace_bytes, cudaStream_t st) {
+static int pseudo_loss_fwd(int kind, const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                           const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* w_cons,
+                           float* lossbuf, void* workspace, long long workspace_bytes, cudaStream_t st) {
     LossGeom g;
     if (int rc = fill_geom(g, logits, other_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, nullptr, 0.f, nullptr,
                            "ct_loss_fwd")) return rc;
     B200_REQUIRE(other_logits && lossbuf && workspace && w_cons, "ct_loss_fwd: null pointer");
     B200_REQUIRE(workspace_bytes >= b200_ssl_loss_workspace_bytes(B, S), "ct_loss_fwd: workspace too small");
-    g.pseudo = 1; g.teacher_nhwc = other_nhwc;
+    g.pseudo = kind; g.teacher_nhwc = other_nhwc;
     const int grid = loss_grid((long long)B * S);
     const int Cp = cpad_of(C);
     launch_loss_fwd<1>(g, Cp, grid, reinterpret_cast<double*>(workspace), st);
     B200_CHECK_LAUNCH("ct_loss_fwd");
-    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<double*>(workspace), grid, Cp, C, Lb, B - Lb, S, 1, 0, 1, w_cons,
+    ssl_loss_finalize_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<double*>(workspace), grid, Cp, C, Lb, B - Lb, S, 1, 0, kind, w_cons,
                                                  lossbuf);
     B200_CHECK_LAUNCH("ct_loss_finalize");
+    return B200_OK;
+}
+
+B200_API int b200_ct_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                              const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* w_cons,
+                              float* lossbuf, void* workspace, long long workspace_bytes, cudaStream_t st) {
+    return pseudo_loss_fwd(1, logits, layout_nhwc, other_logits, other_nhwc, labels, label_dtype, B, Lb, C, S, w_cons, lossbuf,
+                           workspace, workspace_bytes, st);
+}
+
+// Cross-pseudo-supervision loss of ONE model (code/train_cross_pseudo_supervision_2D.py:187-196):
+//   0.5 (CE + Dice)(logits[:Lb], y) + w * CE(logits[Lb:], argmax softmax(other[Lb:]))
+// lossbuf: [0] ce [1] dice [2] pseudo-label CE [3] total, then gradient coefficients (same layout as ct_loss)
+B200_API int b200_cps_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                               const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* w_cons,
+                               float* lossbuf, void* workspace, long long workspace_bytes, cudaStream_t st) {
+    return pseudo_loss_fwd(2, logits, layout_nhwc, other_logits, other_nhwc, labels, label_dtype, B, Lb, C, S, w_cons, lossbuf,
+                           workspace, workspace_bytes, st);
+}
+
+static int pseudo_loss_bwd(int kind, const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                           const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf,
+                           float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
+    LossGeom g;
+    if (int rc = fill_geom(g, logits, other_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, nullptr, 0.f, nullptr,
+                           "ct_loss_bwd")) return rc;
+    B200_REQUIRE(other_logits && lossbuf && dlogits, "ct_loss_bwd: null pointer");
+    g.pseudo = kind; g.teacher_nhwc = other_nhwc;
+    launch_loss_bwd<1>(g, cpad_of(C), loss_grid((long long)B * S), lossbuf, nullptr, grad_scale, dlogits, dlogits_nhwc, st);
+    B200_CHECK_LAUNCH("ct_loss_bwd");
     return B200_OK;
 }
 
 B200_API int b200_ct_loss_bwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
                               const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf,
                               float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
-    LossGeom g;
-    if (int rc = fill_geom(g, logits, other_logits, labels, label_dtype, layout_nhwc, B, Lb, C, S, nullptr, 0.f, nullptr,
-                           "ct_loss_bwd")) return rc;
-    B200_REQUIRE(other_logits && lossbuf && dlogits, "ct_loss_bwd: null pointer");
-    g.pseudo = 1; g.teacher_nhwc = other_nhwc;
-    launch_loss_bwd<1>(g, cpad_of(C), loss_grid((long long)B * S), lossbuf, nullptr, grad_scale, dlogits, dlogits_nhwc, st);
-    B200_CHECK_LAUNCH("ct_loss_bwd");
-    return B200_OK;
+    return pseudo_loss_bwd(1, logits, layout_nhwc, other_logits, other_nhwc, labels, label_dtype, B, Lb, C, S, lossbuf, grad_scale,
+                           dlogits, dlogits_nhwc, st);
+}
+
+B200_API int b200_cps_loss_bwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc,
+                               const void* labels, int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf,
+                               float grad_scale, float* dlogits, int dlogits_nhwc, cudaStream_t st) {
+    return pseudo_loss_bwd(2, logits, layout_nhwc, other_logits, other_nhwc, labels, label_dtype, B, Lb, C, S, lossbuf, grad_scale,
+                           dlogits, dlogits_nhwc, st);
 }
 
 // psum[u] (+)= sum_r softmax(logits[r*U + u])  -- the T stochastic teacher passes of UAMT

@@ -385,6 +385,16 @@ def ct_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C_, S, lossbuf, 
               C_, S, _pf(lossbuf), grad_scale, _pf(dlogits), int(dlogits_nhwc), _st())
 
 
+def cps_loss_fwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C_, S, w_cons, lossbuf, ws):
+    _lib.call("b200_cps_loss_fwd", _pf(logits), int(nhwc), _pf(other), int(other_nhwc), _p(labels), _label_dtype(labels), B, Lb,
+              C_, S, _pf(w_cons), _pf(lossbuf), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def cps_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C_, S, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+    _lib.call("b200_cps_loss_bwd", _pf(logits), int(nhwc), _pf(other), int(other_nhwc), _p(labels), _label_dtype(labels), B, Lb,
+              C_, S, _pf(lossbuf), grad_scale, _pf(dlogits), int(dlogits_nhwc), _st())
+
+
 def mc_softmax_accumulate(logits, psum, R, U, C_, S, nhwc=False, init=True):
     _lib.call("b200_mc_softmax_accumulate", _pf(logits), _pf(psum), R, U, C_, S, int(nhwc), int(init), _st())
 

@@ -217,7 +217,11 @@ class CrossTeachingTrainer:
 
     def __init__(self, model1, model2, *, batch_size=16, labeled_bs=8, patch_size=(224, 224), num_classes=4, base_lr=0.01,
                  max_iterations=30000, consistency=0.1, consistency_rampup=200.0, momentum=0.9, weight_decay=1e-4,
-                 start_iter=0, label_dtype=torch.uint8, process_group=None, use_cuda_graph=False):
+                 start_iter=0, label_dtype=torch.uint8, process_group=None, use_cuda_graph=False, pseudo_loss="dice"):
+        assert pseudo_loss in ("dice", "ce")
+        # "dice": Cross Teaching (train_cross_teaching_between_cnn_transformer_2D.py:242-245);
+        # "ce":   Cross Pseudo Supervision (train_cross_pseudo_supervision_2D.py:193-196) -- same loop, two CNNs
+        self.loss_fwd, self.loss_bwd = (ops.ct_loss_fwd, ops.ct_loss_bwd) if pseudo_loss == "dice" else (ops.cps_loss_fwd, ops.cps_loss_bwd)
         self.models = (model1, model2)
         self.aux = None
         self.B, self.Lb, self.patch, self.C = batch_size, labeled_bs, tuple(patch_size), num_classes
@@ -285,9 +289,9 @@ class CrossTeachingTrainer:
             main.wait_stream(self.aux)
         w = self.hp[HP_WCONS:HP_WCONS + 1]
         for mine, other, lb in ((p1, p2, self.lossbufs[0]), (p2, p1, self.lossbufs[1])):
-            ops.ct_loss_fwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, w, lb, self.loss_ws)
-            ops.ct_loss_bwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, lb, 1.0,
-                            mine.g_logits, True)
+            self.loss_fwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, w, lb, self.loss_ws)
+            self.loss_bwd(mine.logits, False, other.logits, False, self.y, self.B, self.Lb, self.C, self.S, lb, 1.0,
+                          mine.g_logits, True)
 
         def update(i):
             plan, flat, mom = self.plans[i], self.flats[i], self.momentum_bufs[i]

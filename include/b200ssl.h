@@ -251,6 +251,15 @@ int b200_ct_loss_bwd(const float* logits, int layout_nhwc, const float* other_lo
                      int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf, float grad_scale,
                      float* dlogits, int dlogits_nhwc, cudaStream_t stream);
 
+/* Cross-pseudo-supervision loss of ONE model (code/train_cross_pseudo_supervision_2D.py:187-196): as above with
+ *   w * CrossEntropy(logits[Lb:], argmax softmax(other_logits[Lb:]))  as the pseudo-label term ([2] of lossbuf). */
+int b200_cps_loss_fwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc, const void* labels,
+                      int label_dtype, int B, int Lb, int C, long long S, const float* w_cons_dev, float* lossbuf,
+                      void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b200_cps_loss_bwd(const float* logits, int layout_nhwc, const float* other_logits, int other_nhwc, const void* labels,
+                      int label_dtype, int B, int Lb, int C, long long S, const float* lossbuf, float grad_scale,
+                      float* dlogits, int dlogits_nhwc, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ optimizer / EMA / noise
  * optim.SGD + update_ema_variables + input noise: code/train_mean_teacher_2D.py:124-128,189-190,208-210,230-233
  * hparams_dev (DEVICE, 6 floats): [0] lr [1] momentum [2] weight_decay [3] ema_alpha [4] 1-ema_alpha [5] grad_scale */

@@ -661,30 +661,41 @@ def ssl_loss_bwd(logits, teacher, labels, nhwc, B, Lb, C, S, w_cons, lossbuf, gr
     dlogits.copy_((g.permute(0, 2, 1) if dlogits_nhwc else g).reshape(dlogits.shape))
 
 
-def _ct_loss(lg, other, lab, Lb, C, w):
+def _ct_loss(lg, other, lab, Lb, C, w, kind="dice"):
     from oracle import ssl_oracle as O
     sup, ce, dice = O.supervised_loss(lg[:Lb], lab, C)
     pseudo = torch.argmax(torch.softmax(other[Lb:], 1), dim=1)
-    ps = O.dice_loss_multiclass(torch.softmax(lg[Lb:], 1), pseudo.unsqueeze(1), C)
+    if kind == "ce":
+        ps = F.cross_entropy(lg[Lb:], pseudo)
+    else:
+        ps = O.dice_loss_multiclass(torch.softmax(lg[Lb:], 1), pseudo.unsqueeze(1), C)
     return sup + w * ps, ce, dice, ps
 
 
-def ct_loss_fwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, w_cons, lossbuf, ws):
+def ct_loss_fwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, w_cons, lossbuf, ws, kind="dice"):
     w = float(w_cons[0])
     lg, ot = _to_ncs(logits.detach(), nhwc, B, C, S), _to_ncs(other.detach(), other_nhwc, B, C, S)
-    tot, ce, dice, ps = _ct_loss(lg, ot, labels.reshape(-1, S)[:Lb], Lb, C, w)
+    tot, ce, dice, ps = _ct_loss(lg, ot, labels.reshape(-1, S)[:Lb], Lb, C, w, kind)
     lossbuf[0], lossbuf[1], lossbuf[2], lossbuf[3], lossbuf[4] = ce, dice, ps, tot, w
 
 
-def ct_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, lossbuf, grad_scale, dlogits, dlogits_nhwc):
+def ct_loss_bwd(logits, nhwc, other, other_nhwc, labels, B, Lb, C, S, lossbuf, grad_scale, dlogits, dlogits_nhwc, kind="dice"):
     w = float(lossbuf[4])
     with torch.enable_grad():
         raw = logits.detach().clone().requires_grad_(True)
         tot, *_ = _ct_loss(_to_ncs(raw, nhwc, B, C, S), _to_ncs(other.detach(), other_nhwc, B, C, S),
-                           labels.reshape(-1, S)[:Lb], Lb, C, w)
+                           labels.reshape(-1, S)[:Lb], Lb, C, w, kind)
         (g,) = torch.autograd.grad(tot * grad_scale, raw)
     g = _to_ncs(g, nhwc, B, C, S)
     dlogits.copy_((g.permute(0, 2, 1) if dlogits_nhwc else g).reshape(dlogits.shape))
+
+
+def cps_loss_fwd(*a):
+    ct_loss_fwd(*a, kind="ce")
+
+
+def cps_loss_bwd(*a):
+    ct_loss_bwd(*a, kind="ce")
 
 
 def mc_softmax_accumulate(logits, psum, R, U, C, S, nhwc=False, init=True):

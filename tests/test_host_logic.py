@@ -395,3 +395,39 @@ def test_mean_teacher_with_swin_unets_matches_oracle(fake):
         torch.testing.assert_close(now_s[k], new, rtol=2e-3, atol=1e-6, msg=lambda m, k=k: f"student {k}: {m}")
         torch.testing.assert_close(now_t[k], alpha * t_sd[k] + (1 - alpha) * new, rtol=2e-3, atol=1e-6,
                                    msg=lambda m, k=k: f"teacher {k}: {m}")
+
+
+def test_cross_pseudo_supervision_trainer_matches_oracle(fake):
+    """code/train_cross_pseudo_supervision_2D.py:176-212 -- two UNets, each supervised by the other's argmax pseudo labels
+    through a CE term: CrossTeachingTrainer(pseudo_loss="ce").  One iteration: both losses and both SGD updates."""
+    import torch.nn.functional as F
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+    torch.manual_seed(51)
+    m1, m2 = unet_mod.UNet(1, 4, seed=11), unet_mod.UNet(1, 4, seed=22)
+    sd = [{k: v.clone() for k, v in m.state_dict().items()} for m in (m1, m2)]
+    B, Lb, P, it = 4, 2, 32, 4000
+    tr = CrossTeachingTrainer(m1, m2, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it,
+                              pseudo_loss="ce")
+    g = torch.Generator().manual_seed(14)
+    x = torch.rand(B, 1, P, P, generator=g)
+    y = torch.randint(0, 4, (B, P, P), generator=g).to(torch.uint8)
+    got = tr.step(x, y, read_loss=True)
+    leaf = [{k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v.clone()) for k, v in s.items()} for s in sd]
+    outs = [O.unet_forward(leaf[i], x, True, unet_masks((11, 22)[i] + 1, B, P, P)) for i in range(2)]
+    w = O.consistency_weight(it)                                         # get_current_consistency_weight(iter_num // 150)
+    want, total = [], 0.0
+    for i in range(2):
+        sup, ce, dice = O.supervised_loss(outs[i][:Lb], y[:Lb], 4)                       # :182-185
+        pseudo = torch.argmax(torch.softmax(outs[1 - i][Lb:].detach(), 1), 1)            # :187-188
+        ps = F.cross_entropy(outs[i][Lb:], pseudo)                                       # :190-191
+        m = sup + w * ps                                                                 # :193-194
+        total = total + m
+        want += [ce, dice, ps, m]
+    total.backward()
+    torch.testing.assert_close(torch.tensor(got), torch.stack(want).detach(), rtol=1e-4, atol=1e-5)
+    lr = O.poly_lr(0.01, it, 30000)                                      # the rate in effect for iteration `it`
+    for i, m in enumerate((m1, m2)):
+        k = "decoder.up4.conv.conv_conv.0.weight"
+        new = sd[i][k] - lr * (leaf[i][k].grad + 1e-4 * sd[i][k])
+        torch.testing.assert_close(m.state_dict()[k], new, rtol=2e-3, atol=1e-6)
+    assert tr.iter_num == it + 1

@@ -136,9 +136,13 @@ def test_droppath_gathers_and_shuffle():
 
 @pytest.mark.parametrize("layouts", [(False, False), (True, False), (False, True)])
 @pytest.mark.parametrize("C", [2, 4])
-def test_cross_teaching_loss(layouts, C):
-    """0.5 (CE + Dice) + w * Dice vs the other model's argmax pseudo labels: values and d/d(logits)."""
+@pytest.mark.parametrize("kind", ["ct", "cps"])
+def test_cross_teaching_loss(layouts, C, kind):
+    """0.5 (CE + Dice) + w * {Dice (cross teaching) | CE (cross pseudo supervision)} vs the other model's argmax pseudo
+    labels: values and d/d(logits)."""
     nhwc, other_nhwc = layouts
+    fwd, bwd = (ops.ct_loss_fwd, ops.ct_loss_bwd) if kind == "ct" else (ops.cps_loss_fwd, ops.cps_loss_bwd)
+    rfwd, rbwd = (ref.ct_loss_fwd, ref.ct_loss_bwd) if kind == "ct" else (ref.cps_loss_fwd, ref.cps_loss_bwd)
     g = torch.Generator().manual_seed(12 + C)
     B, Lb, S = 6, 2, 40 * 24
     logits = torch.randn(B, C, S, generator=g) * 2
@@ -149,13 +153,13 @@ def test_cross_teaching_loss(layouts, C):
     lg, ot = lay(logits, nhwc), lay(other, other_nhwc)
     lb, lbr = torch.zeros(40, device=DEV), torch.zeros(40)
     ws = scratch(ops.ssl_loss_workspace_bytes(B, S))
-    ops.ct_loss_fwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, cu(w), lb, ws)
-    ref.ct_loss_fwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, w, lbr, None)
+    fwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, cu(w), lb, ws)
+    rfwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, w, lbr, None)
     torch.testing.assert_close(lb[:4].cpu(), lbr[:4], rtol=1e-5, atol=1e-6)
     for out_nhwc in (False, True):
         d, dr = torch.empty(B * C * S, device=DEV), torch.empty(B * C * S)
-        ops.ct_loss_bwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, lb, 0.5, d, out_nhwc)
-        ref.ct_loss_bwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, lbr, 0.5, dr, out_nhwc)
+        bwd(cu(lg), nhwc, cu(ot), other_nhwc, cu(y), B, Lb, C, S, lb, 0.5, d, out_nhwc)
+        rbwd(lg, nhwc, ot, other_nhwc, y, B, Lb, C, S, lbr, 0.5, dr, out_nhwc)
         torch.testing.assert_close(d.cpu(), dr, rtol=1e-4, atol=1e-9)
 
 
