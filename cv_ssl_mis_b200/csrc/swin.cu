@@ -249,11 +249,91 @@ __device__ __forceinline__ int wa_bias_index(int ws, int i, int j) {
     return dh * (2 * ws - 1) + dw;
 }
 
+// Register-tiled products on the shared-memory operands (one CTA = one window x head, N <= 49 tokens, head dim 32).
+// The old one-output-per-thread loops issued two shared-memory loads per FMA and were bound by the LSU; a 4x7 / 4x4
+// accumulator tile per thread brings that to ~0.4 loads per FMA.  Rows / columns past N are clamped on load and
+// skipped on store.
+#define WA_LDQ (WA_HD + 1)          // row stride of q / k / v / dO tiles
+#define WA_LDP (WA_MAXN + 1)        // row stride of the N x N score tile
+
+// acc[r][c] = sum_d A[i0 + r][d] * B[j0 + c][d]      (S = q k^T, dP = dO v^T)
+__device__ __forceinline__ void wa_mm_nt_4x7(const float* __restrict__ A, const float* __restrict__ B, int N, int i0, int j0,
+                                             float (&acc)[4][7]) {
+    int ra[4], rb[7];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ra[r] = min(i0 + r, N - 1) * WA_LDQ;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) rb[c] = min(j0 + c, N - 1) * WA_LDQ;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < WA_HD; ++d) {
+        float a[4], b[7];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = A[ra[r] + d];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) b[c] = B[rb[c] + d];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+}
+// acc[r][c] = sum_j P[i0 + r][j] * X[j][d0 + c]      (out = P v, dq = dS k)
+__device__ __forceinline__ void wa_mm_nn_4x4(const float* __restrict__ P, const float* __restrict__ X, int N, int i0, int d0,
+                                             float (&acc)[4][4]) {
+    int rp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rp[r] = min(i0 + r, N - 1) * WA_LDP;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < N; ++j) {
+        float a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = P[rp[r] + j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = X[j * WA_LDQ + d0 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+}
+// acc[r][c] = sum_i P[i][j0 + r] * X[i][d0 + c]      (dv = P^T dO, dk = dS^T q)
+__device__ __forceinline__ void wa_mm_tn_4x4(const float* __restrict__ P, const float* __restrict__ X, int N, int j0, int d0,
+                                             float (&acc)[4][4]) {
+    int cp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cp[r] = min(j0 + r, N - 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < N; ++i) {
+        float a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = P[i * WA_LDP + cp[r]];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = X[i * WA_LDQ + d0 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(128) window_attn_kernel(const WinP p) {
-    __shared__ float sq[WA_MAXN][WA_HD + 1], sk[WA_MAXN][WA_HD + 1], sv[WA_MAXN][WA_HD + 1];
-    __shared__ float sp[WA_MAXN][WA_MAXN + 1];
-    __shared__ float sdo[BWD ? WA_MAXN : 1][WA_HD + 1];
+    __shared__ float sq[WA_MAXN * WA_LDQ], sk[WA_MAXN * WA_LDQ], sv[WA_MAXN * WA_LDQ];
+    __shared__ float sp[WA_MAXN * WA_LDP];
+    __shared__ float sdo[BWD ? WA_MAXN * WA_LDQ : 1];
+    __shared__ float sdot[BWD ? WA_MAXN * 8 : 1];
     __shared__ int stok[WA_MAXN], sreg[WA_MAXN];
     const int N = p.ws * p.ws;
     const int nWw = p.W / p.ws, nW = (p.H / p.ws) * nWw;
@@ -271,89 +351,133 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinP p) {
     for (int idx = tid; idx < N * WA_HD; idx += 128) {
         const int r = idx / WA_HD, d = idx % WA_HD;
         const float* row = p.qkv + (size_t)stok[r] * C3 + head * WA_HD + d;
-        sq[r][d] = __ldg(row) * p.scale;
-        sk[r][d] = __ldg(row + p.C);
-        sv[r][d] = __ldg(row + 2 * p.C);
-        if (BWD) sdo[r][d] = __ldg(p.dout + (size_t)stok[r] * p.C + head * WA_HD + d);
+        sq[r * WA_LDQ + d] = __ldg(row) * p.scale;
+        sk[r * WA_LDQ + d] = __ldg(row + p.C);
+        sv[r * WA_LDQ + d] = __ldg(row + 2 * p.C);
+        if (BWD) sdo[r * WA_LDQ + d] = __ldg(p.dout + (size_t)stok[r] * p.C + head * WA_HD + d);
     }
     __syncthreads();
+    // tile coordinates: 4 x 7 tiles over the N x N matrices, 4 x 4 tiles over the N x 32 ones
+    const int nti = (N + 3) >> 2, ntj = (N + 6) / 7;
+    const int s_ti = tid / 7, s_tj = tid % 7;                 // score tile of this thread (if s_ti < nti && s_tj < ntj)
+    const bool s_on = s_ti < nti && s_tj < ntj;
+    const int o_ti = tid >> 3, o_td = tid & 7;                // N x 32 tile (if o_ti < nti)
+    const bool o_on = o_ti < nti;
     // scores + bias + mask
-    for (int idx = tid; idx < N * N; idx += 128) {
-        const int i = idx / N, j = idx % N;
-        float s = 0.f;
+    if (s_on) {
+        float acc[4][7];
+        wa_mm_nt_4x7(sq, sk, N, s_ti * 4, s_tj * 7, acc);
 #pragma unroll
-        for (int d = 0; d < WA_HD; ++d) s = fmaf(sq[i][d], sk[j][d], s);
-        s += __ldg(p.table + wa_bias_index(p.ws, i, j) * p.heads + head);
-        if (p.shift > 0 && sreg[i] != sreg[j]) s += -100.0f;
-        sp[i][j] = s;
+        for (int r = 0; r < 4; ++r) {
+            const int i = s_ti * 4 + r;
+            if (i >= N) break;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const int j = s_tj * 7 + c;
+                if (j >= N) break;
+                float s = acc[r][c] + __ldg(p.table + wa_bias_index(p.ws, i, j) * p.heads + head);
+                if (p.shift > 0 && sreg[i] != sreg[j]) s += -100.0f;
+                sp[i * WA_LDP + j] = s;
+            }
+        }
     }
     __syncthreads();
     // softmax over j (one warp per row, rows strided over the 4 warps)
     {
         const int lane = tid & 31, warp = tid >> 5;
         for (int i = warp; i < N; i += 4) {
-            const float a0 = lane < N ? sp[i][lane] : -INFINITY, a1 = lane + 32 < N ? sp[i][lane + 32] : -INFINITY;
+            float* row = sp + i * WA_LDP;
+            const float a0 = lane < N ? row[lane] : -INFINITY, a1 = lane + 32 < N ? row[lane + 32] : -INFINITY;
             float mx = fmaxf(a0, a1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             const float e0 = lane < N ? expf(a0 - mx) : 0.f, e1 = lane + 32 < N ? expf(a1 - mx) : 0.f;
             const float inv = 1.f / warp_sum(e0 + e1);
-            if (lane < N) sp[i][lane] = e0 * inv;
-            if (lane + 32 < N) sp[i][lane + 32] = e1 * inv;
+            if (lane < N) row[lane] = e0 * inv;
+            if (lane + 32 < N) row[lane + 32] = e1 * inv;
         }
     }
     __syncthreads();
     if (!BWD) {
-        for (int idx = tid; idx < N * WA_HD; idx += 128) {
-            const int i = idx / WA_HD, d = idx % WA_HD;
-            float o = 0.f;
-            for (int j = 0; j < N; ++j) o = fmaf(sp[i][j], sv[j][d], o);
-            p.out[(size_t)stok[i] * p.C + head * WA_HD + d] = o;
+        if (o_on) {
+            float acc[4][4];
+            wa_mm_nn_4x4(sp, sv, N, o_ti * 4, o_td * 4, acc);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = o_ti * 4 + r;
+                if (i >= N) break;
+                stg4(p.out + (size_t)stok[i] * p.C + head * WA_HD + o_td * 4, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+            }
         }
         return;
     }
     // ---------------- backward: dV = P^T dO ; dP = dO V^T ; dS = P o (dP - rowsum(dP o P)) ; dq = dS k scale ; dk = dS^T q
     float* dqkv = p.dqkv;
-    for (int idx = tid; idx < N * WA_HD; idx += 128) {
-        const int j = idx / WA_HD, d = idx % WA_HD;
-        float o = 0.f;
-        for (int i = 0; i < N; ++i) o = fmaf(sp[i][j], sdo[i][d], o);
-        dqkv[(size_t)stok[j] * C3 + 2 * p.C + head * WA_HD + d] = o;
+    if (o_on) {
+        float acc[4][4];
+        wa_mm_tn_4x4(sp, sdo, N, o_ti * 4, o_td * 4, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = o_ti * 4 + r;
+            if (j >= N) break;
+            stg4(dqkv + (size_t)stok[j] * C3 + 2 * p.C + head * WA_HD + o_td * 4, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+        }
     }
-    __syncthreads();
-    // dS in place of P: needs dP row sums first; one warp per row
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int i = warp; i < N; i += 4) {
-            float dp0 = 0.f, dp1 = 0.f;
-            if (lane < N) {
+    // dP tile in registers; per-row partial sums of dP o P go through shared memory (7 column tiles per row)
+    float dp[4][7];
+    if (s_on) {
+        wa_mm_nt_4x7(sdo, sv, N, s_ti * 4, s_tj * 7, dp);
 #pragma unroll
-                for (int d = 0; d < WA_HD; ++d) dp0 = fmaf(sdo[i][d], sv[lane][d], dp0);
-            }
-            if (lane + 32 < N) {
+        for (int r = 0; r < 4; ++r) {
+            const int i = s_ti * 4 + r;
+            if (i >= N) break;
+            float part = 0.f;
 #pragma unroll
-                for (int d = 0; d < WA_HD; ++d) dp1 = fmaf(sdo[i][d], sv[lane + 32][d], dp1);
+            for (int c = 0; c < 7; ++c) {
+                const int j = s_tj * 7 + c;
+                if (j < N) part = fmaf(dp[r][c], sp[i * WA_LDP + j], part);
             }
-            const float p0 = lane < N ? sp[i][lane] : 0.f, p1 = lane + 32 < N ? sp[i][lane + 32] : 0.f;
-            const float dot = warp_sum(dp0 * p0 + dp1 * p1);
-            if (lane < N) sp[i][lane] = p0 * (dp0 - dot);
-            if (lane + 32 < N) sp[i][lane + 32] = p1 * (dp1 - dot);
+            sdot[i * 8 + s_tj] = part;
+        }
+    }
+    __syncthreads();                                            // all reads of P (dV, partial dots) are done
+    if (s_on) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = s_ti * 4 + r;
+            if (i >= N) break;
+            float dot = 0.f;
+            for (int t = 0; t < ntj; ++t) dot += sdot[i * 8 + t];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const int j = s_tj * 7 + c;
+                if (j >= N) break;
+                sp[i * WA_LDP + j] *= dp[r][c] - dot;              // dS in place of P
+            }
         }
     }
     __syncthreads();
     if (p.dbias_part) {
         float* bp = p.dbias_part + ((size_t)(b * nW + win) * p.heads + head) * (WA_MAXN * WA_MAXN);
-        for (int idx = tid; idx < N * N; idx += 128) bp[idx] = sp[idx / N][idx % N];
+        for (int idx = tid; idx < N * N; idx += 128) bp[idx] = sp[(idx / N) * WA_LDP + idx % N];
     }
-    for (int idx = tid; idx < N * WA_HD; idx += 128) {
-        const int i = idx / WA_HD, d = idx % WA_HD;
-        float dq = 0.f, dk = 0.f;
-        for (int j = 0; j < N; ++j) {
-            dq = fmaf(sp[i][j], sk[j][d], dq);
-            dk = fmaf(sp[j][i], sq[j][d], dk);          // sq already carries the scale
+    if (o_on) {
+        float acc[4][4];
+        wa_mm_nn_4x4(sp, sk, N, o_ti * 4, o_td * 4, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = o_ti * 4 + r;
+            if (i >= N) break;
+            stg4(dqkv + (size_t)stok[i] * C3 + head * WA_HD + o_td * 4,
+                 make_float4(acc[r][0] * p.scale, acc[r][1] * p.scale, acc[r][2] * p.scale, acc[r][3] * p.scale));
         }
-        dqkv[(size_t)stok[i] * C3 + head * WA_HD + d] = dq * p.scale;
-        dqkv[(size_t)stok[i] * C3 + p.C + head * WA_HD + d] = dk;
+        wa_mm_tn_4x4(sp, sq, N, o_ti * 4, o_td * 4, acc);          // sq already carries the scale
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = o_ti * 4 + r;
+            if (j >= N) break;
+            stg4(dqkv + (size_t)stok[j] * C3 + p.C + head * WA_HD + o_td * 4, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+        }
     }
 }
 
