@@ -83,6 +83,7 @@ struct C1P {
     float* part_colsum;
     int N, D, H, W, Cout, KD;
     long long M;
+    FastDiv fd_w, fd_h, fd_d;  // pixel index -> (n, d, h, w) without 64-bit divisions (M < 2^31)
 };
 
 template <int COUT, int KD>
@@ -141,11 +142,12 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const C1P p) {
     for (int t = 0; t < T; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
 #pragma unroll 2
     for (long long m = (long long)blockIdx.x * PL + pl; m < p.M; m += (long long)gridDim.x * PL) {
-        long long r = m;
-        const int w = (int)(r % p.W); r /= p.W;
-        const int h = (int)(r % p.H); r /= p.H;
-        const int d = (int)(r % p.D);
-        const long long n = r / p.D;
+        uint32_t q1, q2, uw, uh, ud, un;
+        p.fd_w.divmod((uint32_t)m, q1, uw);
+        p.fd_h.divmod(q1, q2, uh);
+        p.fd_d.divmod(q2, un, ud);
+        const int w = (int)uw, h = (int)uh, d = (int)ud;
+        const int n = (int)un;
         const float4 g = ldg4_stream(p.dy + m * COUT + cq * 4);
         cs[0] += g.x; cs[1] += g.y; cs[2] += g.z; cs[3] += g.w;
 #pragma unroll
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const C1P p) {
                 for (int kw = 0; kw < 3; ++kw) {
                     const int id = d + kd - (KD == 3 ? 1 : 0), ih = h + kh - 1, iw = w + kw - 1;
                     const bool ok = (unsigned)id < (unsigned)p.D && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                    const float xv = ok ? __ldg(p.x + ((n * p.D + id) * p.H + ih) * p.W + iw) : 0.f;
+                    const float xv = ok ? __ldg(p.x + ((n * p.D + id) * p.H + ih) * p.W + iw) : 0.f;      // < 2^31 elements
                     const int t = (kd * 3 + kh) * 3 + kw;
                     acc[t][0] = fmaf(g.x, xv, acc[t][0]); acc[t][1] = fmaf(g.y, xv, acc[t][1]);
                     acc[t][2] = fmaf(g.z, xv, acc[t][2]); acc[t][3] = fmaf(g.w, xv, acc[t][3]);
@@ -198,6 +200,7 @@ static void fill_c1(C1P& p, const b200_conv_desc* d) {
     memset(&p, 0, sizeof(p));
     p.N = d->n; p.D = d->id; p.H = d->ih; p.W = d->iw; p.Cout = d->cout; p.KD = d->kd;
     p.M = (long long)d->n * d->id * d->ih * d->iw;
+    p.fd_w.init(d->iw); p.fd_h.init(d->ih); p.fd_d.init(d->id);
 }
 
 B200_API int b200_conv_c1_fwd(const b200_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
@@ -225,6 +228,7 @@ B200_API int b200_conv_c1_wgrad(const b200_conv_desc* d, const float* x, const f
                                 long long workspace_bytes, float* dw, float* db, int accumulate, cudaStream_t st) {
     B200_REQUIRE(b200_conv_c1_supported(d), "conv_c1_wgrad: unsupported convolution");
     B200_REQUIRE(x && dy && workspace && dw, "conv_c1_wgrad: null pointer");
+    B200_REQUIRE((long long)d->n * d->id * d->ih * d->iw < (1ll << 31), "conv_c1_wgrad: more than 2^31 pixels");
     B200_REQUIRE(workspace_bytes >= b200_conv_c1_wgrad_workspace_bytes(d), "conv_c1_wgrad: workspace too small");
     C1P p;
     fill_c1(p, d);

@@ -32,6 +32,7 @@ struct GemmP {
     int M, N, K;                 // output rows, output columns, reduction length
     int BN;                      // tile columns (multiple of 32, <= 256)
     int a_mn, b_mn;              // operand is MN-major in memory
+    int a_3d, b_3d;              // MN-major operand fetched with ONE 3-D box {32 columns, BK rows, column groups} per stage
     int a_k0;                    // reduction elements served by tensor map a0 (the rest by a1)   [A K-major only]
     int b_n0;                    // output columns served by tensor map b0 (the rest by b1)       [B MN-major only]
     int m_tiles, n_tiles, splits, kb_total;
@@ -69,6 +70,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // shared -> global tile store / reduce-add (fp32) through the tensor map {column, row, split}; clipped at the matrix edge
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int add) {
@@ -170,7 +176,9 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
                 // boxes entirely outside the matrix are skipped (their rows / columns are never stored)
                 const int a_boxes = p.a_mn ? min(4, (p.M - m0 + 31) / 32) : 1;
                 const int b_boxes = p.b_mn ? min(BN / 32, (p.N - n0 + 31) / 32) : 1;
-                const uint32_t tx = (p.a_mn ? a_boxes * 4096u : (uint32_t)A_BYTES) + (p.b_mn ? b_boxes * 4096u : (uint32_t)(BN * BK * 4));
+                // a 3-D box always delivers its full size (out-of-range column groups are zero-filled)
+                const uint32_t tx = ((p.a_mn && !p.a_3d) ? a_boxes * 4096u : (uint32_t)A_BYTES) +
+                                    ((p.b_mn && !p.b_3d) ? b_boxes * 4096u : (uint32_t)(BN * BK * 4));
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % S;
                     if (it >= S) mbar_wait(smem_u32(&empty_bar[s]), ((it / S) - 1) & 1);
@@ -181,11 +189,15 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
                     if (!p.a_mn) {
                         if (k < p.a_k0) tma_load_2d(a_dst, &ta0, k, m0, fb);
                         else tma_load_2d(a_dst, &ta1, k - p.a_k0, m0, fb);
+                    } else if (p.a_3d) {
+                        tma_load_3d(a_dst, &ta0, 0, k, m0 >> 5, fb);
                     } else {
                         for (int j = 0; j < a_boxes; ++j) tma_load_2d(a_dst + j * 4096, &ta0, m0 + 32 * j, k, fb);
                     }
                     if (!p.b_mn) {
                         tma_load_2d(b_dst, &tb0, k, n0, fb);
+                    } else if (p.b_3d) {
+                        tma_load_3d(b_dst, &tb0, 0, k, n0 >> 5, fb);
                     } else {
                         for (int j = 0; j < b_boxes; ++j) {
                             const int col = n0 + 32 * j;
@@ -338,6 +350,25 @@ int make_map(CUtensorMap* m, const float* base, long long rows, long long cols, 
     return B200_OK;
 }
 
+// MN-major operand as ONE box per stage: the row-major matrix [rows = reduction][cols] viewed as
+// {32 columns, rows, cols / 32 column groups}; box {32, BK, groups} lands as [group][BK rows][128 B], the layout the
+// per-box path builds with `groups` separate copies (a single elected thread issues every TMA, and the issue rate of
+// 4 KB boxes -- not bandwidth -- was what bounded dgrad / wgrad).  Needs cols % 32 == 0.
+int make_map_mn3d(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int groups, const char* who) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { b200_set_error("%s: cuTensorMapEncodeTiled is unavailable", who); return B200_ERR_CUDA; }
+    if (((uintptr_t)base & 15) || (ld & 3) || (cols & 31)) { b200_set_error("%s: bad MN-major operand", who); return B200_ERR_ARG; }
+    const cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128u};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)BK, (cuuint32_t)groups};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200_set_error("%s: cuTensorMapEncodeTiled (3-D MN-major) failed (%d)", who, (int)r); return B200_ERR_CUDA; }
+    return B200_OK;
+}
+
 // output [splits][rows][cols] fp32, row stride ld, split stride ss (elements); 32x32 boxes, 128-byte swizzle
 int make_out_map(CUtensorMap* m, float* base, long long rows, long long cols, long long ld, long long splits, long long ss,
                  const char* who) {
@@ -444,7 +475,10 @@ B200_API int b200_linear_dgrad(const float* dy, const float* w, float* dx0, floa
     p.dst0 = dx0; p.ld0 = c0; p.ncol0 = c0; p.dst1 = dx1; p.ld1 = c1; p.accumulate = accumulate;
     CUtensorMap a0, b0;
     if (int rc = make_map(&a0, dy, M, O, O, BM, false, "linear_dgrad")) return rc;
-    if (int rc = make_map(&b0, w, O, I, I, BK, true, "linear_dgrad")) return rc;      // rows = reduction index o, 32x32 boxes
+    if ((I & 31) == 0) {                                                              // rows = reduction index o
+        p.b_3d = 1;
+        if (int rc = make_map_mn3d(&b0, w, O, I, I, p.BN / 32, "linear_dgrad")) return rc;
+    } else if (int rc = make_map(&b0, w, O, I, I, BK, true, "linear_dgrad")) return rc;   // 32x32 boxes
     return launch_gemm(p, a0, a0, b0, b0, st, "linear_dgrad");
 }
 
@@ -470,8 +504,14 @@ B200_API int b200_linear_wgrad(const float* x0, const float* x1, int c0, int c1,
     p.dst0 = splits > 1 ? workspace : dw; p.ld0 = I; p.ncol0 = I; p.split_stride = (long long)O * I;
     p.accumulate = splits > 1 ? 0 : accumulate;
     CUtensorMap a0, b0, b1;
-    if (int rc = make_map(&a0, dy, M, O, O, BK, true, "linear_wgrad")) return rc;
-    if (int rc = make_map(&b0, x0, M, c0, c0, BK, true, "linear_wgrad")) return rc;
+    if ((O & 31) == 0) {
+        p.a_3d = 1;
+        if (int rc = make_map_mn3d(&a0, dy, M, O, O, BM / 32, "linear_wgrad")) return rc;
+    } else if (int rc = make_map(&a0, dy, M, O, O, BK, true, "linear_wgrad")) return rc;
+    if (c1 == 0 && (c0 & 31) == 0) {
+        p.b_3d = 1;
+        if (int rc = make_map_mn3d(&b0, x0, M, c0, c0, p.BN / 32, "linear_wgrad")) return rc;
+    } else if (int rc = make_map(&b0, x0, M, c0, c0, BK, true, "linear_wgrad")) return rc;
     b1 = b0;
     if (c1) if (int rc = make_map(&b1, x1, M, c1, c1, BK, true, "linear_wgrad")) return rc;
     if (int rc = launch_gemm(p, a0, a0, b0, b1, st, "linear_wgrad")) return rc;

@@ -110,12 +110,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
 }
 
+// one warp per (dgamma | dbeta) column: lanes stride over the per-block partials, fixed-order shuffle tree
 __global__ void __launch_bounds__(256) colpart_finalize_kernel(const float* __restrict__ part, int nblk, int C2,
                                                               float* __restrict__ out0, float* __restrict__ out1, int C,
                                                               int accumulate) {
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < C2; idx += gridDim.x * blockDim.x) {
-        double s = 0;
-        for (int b = 0; b < nblk; ++b) s += part[(size_t)b * C2 + idx];
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= C2) return;
+    double s = 0;
+    for (int b = lane; b < nblk; b += 32) s += (double)part[(size_t)b * C2 + idx];
+    s = warp_sum_d(s);
+    if (lane == 0) {
         float* o = idx < C ? out0 + idx : out1 + (idx - C);
         *o = accumulate ? *o + (float)s : (float)s;
     }
@@ -166,7 +171,7 @@ B200_API int b200_layernorm_bwd(const float* x, const float* stats, const float*
     else if (C <= 768) layernorm_bwd_kernel<24><<<grid, 256, smem, st>>>(x, stats, gamma, dy, dx, workspace, M, C, accumulate_dx);
     else layernorm_bwd_kernel<48><<<grid, 256, smem, st>>>(x, stats, gamma, dy, dx, workspace, M, C, accumulate_dx);
     B200_CHECK_LAUNCH("layernorm_bwd");
-    colpart_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, grid, 2 * C, dgamma, dbeta, C, 0);
+    colpart_finalize_kernel<<<(2 * C + 7) / 8, 256, 0, st>>>(workspace, grid, 2 * C, dgamma, dbeta, C, 0);
     B200_CHECK_LAUNCH("layernorm_bwd_finalize");
     return B200_OK;
 }
