@@ -143,8 +143,17 @@ class UNetPlan:
         self.head.forward(rt, cur, None, train)
         return self.head.y
 
-    def backward(self, dlogits_nhwc=None):
-        """d(loss)/d(logits), channels-last [B*H*W, C]; if None it is already in self.head.g."""
+    def decoder_grad_offset(self):
+        """First element of the decoder's parameters in the flat parameter / gradient buffer (encoder first, then
+        decoder: registration order of code/networks/unet.py:309-316)."""
+        flat = self.net._flat
+        first = next(p for p in self.net.decoder.parameters())
+        return flat.offsets[[id(q) for q in flat.params].index(id(first))]
+
+    def backward(self, dlogits_nhwc=None, after_decoder=None):
+        """d(loss)/d(logits), channels-last [B*H*W, C]; if None it is already in self.head.g.
+        after_decoder(): called once every launch that writes a decoder parameter gradient has been issued (main and
+        side stream) -- the data-parallel trainer starts the all-reduce of that bucket there."""
         rt, B = self.rt, self.B
         if dlogits_nhwc is not None and dlogits_nhwc.data_ptr() != self.head.g.data_ptr():
             self.head.g.copy_(dlogits_nhwc.view_as(self.head.g))
@@ -161,6 +170,8 @@ class UNetPlan:
             ops.upsample2x_bwd(up_g, l1.g, B, h, w, l1.cout)
             src_l = self.dec[j - 1][4] if j > 0 else self.enc[4][1]
             l1.backward(rt, src_l.a, None, src_l.g)
+        if after_decoder is not None:
+            after_decoder()
         for i in range(4, -1, -1):
             la, lb = self.enc[i]
             lb.backward(rt, la.a, None, la.g)
