@@ -27,7 +27,8 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, buckets):
+    os.environ["B200_DP_BUCKETS"] = buckets          # "1": decoder / encoder gradient buckets (trainers.py), "0": one all-reduce
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(2)
@@ -76,7 +77,8 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_gradient_allreduce_gloo(tmp_path):
+@pytest.mark.parametrize("buckets", ["0", "1"])
+def test_two_rank_gradient_allreduce_gloo(tmp_path, buckets):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), buckets), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
