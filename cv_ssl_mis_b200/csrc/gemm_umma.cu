@@ -8,8 +8,9 @@
 // 115-150, 336-346, 378, 405): no weight packing, no transposed copies -- the MN-major cases use the transposing
 // operand fetch of the UMMA descriptor (instruction-descriptor bits 15/16).
 //
-//   warp 0     TMA producer (one lane): per 32-deep k-block one 128x32 box of A and one BNx32 box of B
-//              (K-major) or 32x32 boxes (MN-major) into a ring of shared-memory stages, mbarrier expect_tx
+//   warp 0     TMA producer (one lane): per 32-deep k-block ONE box of A and ONE box of B -- 2-D {32, rows} for K-major
+//              operands, 3-D {32 columns, 32 k-rows, column groups} for MN-major ones (per-32-column boxes only as the
+//              fallback for ragged / concatenated operands) -- into a ring of shared-memory stages, mbarrier expect_tx
 //   warp 1     MMA issuer (one lane): 4 x tcgen05.mma (K = 8) per k-block, tcgen05.commit frees the stage;
 //              owns the TMEM allocation (two accumulator buffers of BN columns)
 //   warps 2-9  epilogue: tcgen05.ld 32x32b.x32 -> + bias -> swizzled shared-memory tile -> TMA store (or fp32 reduce-add
@@ -118,14 +119,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_unused(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
 __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_constant__ CUtensorMap ta0,
                                                               const __grid_constant__ CUtensorMap ta1,
                                                               const __grid_constant__ CUtensorMap tb0,
