@@ -431,3 +431,40 @@ def test_cross_pseudo_supervision_trainer_matches_oracle(fake):
         new = sd[i][k] - lr * (leaf[i][k].grad + 1e-4 * sd[i][k])
         torch.testing.assert_close(m.state_dict()[k], new, rtol=2e-3, atol=1e-6)
     assert tr.iter_num == it + 1
+
+
+def test_uamt_2d_unet_trainer_matches_oracle(fake):
+    """code/train_uncertainty_aware_mean_teacher_2D.py:147-201 -- the 2D twin of UAMT: UNet student/teacher, T = 8 stochastic
+    teacher passes (4 forwards of the twice-repeated unlabeled batch, fresh noise and dropout each), entropy mask.
+    One step of MeanTeacherTrainer(uncertainty_T=8) against the oracle's loss with OUR Philox noise / dropout streams."""
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    torch.manual_seed(61)
+    student, teacher = unet_mod.UNet(1, 4, seed=11), unet_mod.UNet(1, 4, seed=22)
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    t_sd = {k: v.clone() for k, v in teacher.state_dict().items()}
+    B, Lb, P, it, T = 4, 2, 32, 2000, 8
+    U = B - Lb
+    tr = MeanTeacherTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it,
+                            noise_seed=7, uncertainty_T=T, consistency_gate_iters=0)
+    g = torch.Generator().manual_seed(16)
+    x = torch.rand(B, 1, P, P, generator=g)
+    y = torch.randint(0, 4, (B, P, P), generator=g).to(torch.uint8)
+    ce, dice, cons, total = tr.step(x, y, read_loss=True)
+
+    noise = lambda off, n: torch.from_numpy(philox.clamp_noise(7 + off, 1000, n * P * P)).reshape(n, 1, P, P)
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v.clone()) for k, v in s_sd.items()}
+    s_logits = O.unet_forward(leaf, x, True, unet_masks(11 + 1, B, P, P))
+    with torch.no_grad():
+        # the teacher's RNG epoch is bumped before every teacher forward: pass 0 -> +1, MC pass i -> +2 + i
+        t_logits = O.unet_forward(t_sd, x[Lb:] + noise(1, U), True, unet_masks(22 + 1, U, P, P))
+        x_rep = x[Lb:].repeat(2, 1, 1, 1)
+        mc = [O.unet_forward(t_sd, x_rep + noise(2 + i, 2 * U), True, unet_masks(22 + 2 + i, 2 * U, P, P)) for i in range(T // 2)]
+    w = O.consistency_weight(it)
+    thr = (0.75 + 0.25 * O.sigmoid_rampup(it, 30000)) * np.log(2)
+    loss, ce_r, dice_r, cons_r, mask = O.uamt_loss(s_logits, t_logits, mc, y, Lb, 4, w, thr, T)
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([ce_r, dice_r, cons_r, loss]).detach(),
+                               rtol=1e-4, atol=1e-6)
+    loss.backward()
+    k = "encoder.down2.maxpool_conv.1.conv_conv.0.weight"
+    new = s_sd[k] - 0.01 * (leaf[k].grad + 1e-4 * s_sd[k])
+    torch.testing.assert_close(student.state_dict()[k], new, rtol=2e-3, atol=1e-6)
