@@ -1,0 +1,44 @@
+"""Command line of code/train_cross_teaching_between_cnn_transformer_2D.py; --pseudo_loss ce with --model2 unet gives
+code/train_cross_pseudo_supervision_2D.py."""
+import sys
+
+from ._common import (add_swin_flags, base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir,
+                      synthetic_batches)
+
+
+def main(argv=None, loader=None):
+    p = base_parser("ACDC/Cross_Teaching_Between_CNN_Transformer", "unet", 16, (224, 224), 8, 7, "../data/ACDC", num_classes=4)
+    add_swin_flags(p)
+    p.add_argument('--model2', type=str, default="ViT_Seg", help='second network (reference: the Swin-UNet ViT_seg)')
+    p.add_argument('--pseudo_loss', type=str, default="dice", choices=["dice", "ce"],
+                   help='dice: cross teaching (:242-245); ce: cross pseudo supervision')
+    args = p.parse_args(argv)
+    seed_everything(args)
+    from ..networks.net_factory import net_factory
+    from ..trainers import CrossTeachingTrainer
+    pg, rank = process_group()
+    model1 = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)              # :134-141
+    model2 = net_factory(net_type=args.model2, in_chns=1, class_num=args.num_classes)             # :142-144 (ViT_seg)
+    if model1 is None or model2 is None:
+        raise SystemExit("--model / --model2: not built (available: unet, ViT_Seg)")
+    if pg is not None:
+        import torch.distributed as dist
+        for m in (model1, model2):
+            dist.broadcast(m.materialize().data, 0)
+    trainer = CrossTeachingTrainer(model1, model2, batch_size=args.batch_size, labeled_bs=args.labeled_bs,
+                                   patch_size=tuple(args.patch_size), num_classes=args.num_classes, base_lr=args.base_lr,
+                                   max_iterations=args.max_iterations, consistency=args.consistency,
+                                   consistency_rampup=args.consistency_rampup, process_group=pg,
+                                   use_cuda_graph=not args.no_graph, pseudo_loss=args.pseudo_loss)
+    if loader is None:
+        if not args.synthetic:
+            raise SystemExit("no h5 dataset reader in this package: pass batches to main() or use --synthetic 1")
+        loader = synthetic_batches(args.batch_size, args.patch_size, args.num_classes, args.seed + rank)
+    path = snapshot_dir(args)
+    setup_logging(path)
+    fmt = lambda it, l: 'iteration %d : model1 loss : %f model2 loss : %f' % (it, l[3], l[7])      # :271-272
+    return run_loop(args, trainer, loader, path, {"model1_": model1, "model2_": model2}, fmt, rank)
+
+
+if __name__ == "__main__":
+    print(main(sys.argv[1:]))

@@ -1,0 +1,55 @@
+"""Command line of code/train_mean_teacher_2D.py (also code/train_uncertainty_aware_mean_teacher_2D.py with
+--uncertainty_T 8, and code/train_fully_supervised_2D.py with --labeled_bs equal to --batch_size)."""
+import sys
+
+from ._common import base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
+
+
+def main(argv=None, loader=None):
+    p = base_parser("ACDC/Mean_Teacher", "unet", 24, (224, 224), 12, 7, "../data/ACDC", num_classes=4)
+    p.add_argument('--uncertainty_T', type=int, default=0, help='8: the uncertainty-aware variant (MC-dropout mask)')
+    args = p.parse_args(argv)
+    seed_everything(args)
+    from ..networks.net_factory import net_factory
+    from ..trainers import MeanTeacherTrainer
+    pg, rank = process_group()
+
+    def create_model(ema=False):                                  # code/train_mean_teacher_2D.py:136-144
+        model = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)
+        if model is None:
+            raise SystemExit(f"--model {args.model}: not built (available: unet, ViT_Seg)")
+        if ema:
+            for param in model.parameters():
+                param.detach_()
+        return model
+
+    model = create_model()
+    supervised = args.labeled_bs >= args.batch_size
+    ema_model = None if supervised else create_model(ema=True)
+    if pg is not None:                                            # identical replicas
+        import torch.distributed as dist
+        for m in (model, ema_model):
+            if m is not None:
+                dist.broadcast(m.materialize().data, 0)
+    trainer = MeanTeacherTrainer(model, ema_model, batch_size=args.batch_size, labeled_bs=args.labeled_bs,
+                                 patch_size=tuple(args.patch_size), num_classes=args.num_classes, base_lr=args.base_lr,
+                                 max_iterations=args.max_iterations, ema_decay=args.ema_decay, consistency=args.consistency,
+                                 consistency_rampup=args.consistency_rampup, uncertainty_T=args.uncertainty_T,
+                                 consistency_gate_iters=0 if args.uncertainty_T else 1000,      # only MT2D gates (:224-225)
+                                 process_group=pg, use_cuda_graph=not args.no_graph)
+    if loader is None:
+        if not args.synthetic:
+            raise SystemExit("no h5 dataset reader in this package: pass an iterable of {'image','label'} batches to main(), "
+                             "or use --synthetic 1")
+        loader = synthetic_batches(args.batch_size, args.patch_size, args.num_classes, args.seed + rank)
+    path = snapshot_dir(args)
+    setup_logging(path)
+    fmt = lambda it, l: 'iteration %d : loss : %f, loss_ce: %f, loss_dice: %f' % (it, l[3], l[0], l[1])      # :252-254
+    models = {"": model}
+    if ema_model is not None:
+        models["ema_"] = ema_model
+    return run_loop(args, trainer, loader, path, models, fmt, rank)
+
+
+if __name__ == "__main__":
+    print(main(sys.argv[1:]))

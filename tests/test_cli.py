@@ -1,0 +1,66 @@
+"""The train_*.py command lines keep the reference's flag sets (code/train_*.py argparse blocks) and drive the fused
+trainers; exercised on CPU with the stand-in ops at toy sizes (two iterations each, synthetic batches)."""
+import os
+
+import pytest
+import torch
+
+from tests import fake_ops
+
+
+@pytest.fixture()
+def cpu_env(monkeypatch, tmp_path):
+    fake_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)     # net_factory(...).cuda() like the reference
+    code = tmp_path / "code"
+    code.mkdir()
+    monkeypatch.chdir(code)                                                       # snapshots go to ../model/<exp>_<n>_labeled/<model>
+    return tmp_path
+
+
+COMMON = ["--max_iterations", "2", "--log_every", "1", "--save_every", "0", "--no_graph", "--seed", "7"]
+
+
+def test_mean_teacher_2d_cli(cpu_env):
+    from cv_ssl_mis_b200.cli import train_mean_teacher_2D as cli
+    out = cli.main(["--root_path", "../data/ACDC", "--exp", "ACDC/Mean_Teacher", "--model", "unet", "--batch_size", "4",
+                    "--labeled_bs", "2", "--patch_size", "32", "32", "--num_classes", "4", "--labeled_num", "7",
+                    "--ema_decay", "0.99", "--consistency_type", "mse", "--consistency", "0.1", "--consistency_rampup", "200.0",
+                    "--base_lr", "0.01", "--deterministic", "1"] + COMMON)
+    assert out == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Mean_Teacher_7_labeled" / "unet"
+    sd = torch.load(snap / "iter_2.pth")
+    assert "encoder.in_conv.conv_conv.0.weight" in sd and "decoder.out_conv.bias" in sd       # reference checkpoint schema
+    assert (snap / "ema_iter_2.pth").exists()
+    log = (snap / "log.txt").read_text()
+    assert "iteration 2 : loss :" in log and "loss_ce:" in log and "loss_dice:" in log
+
+
+def test_mean_teacher_2d_cli_uamt_and_supervised(cpu_env):
+    from cv_ssl_mis_b200.cli import train_mean_teacher_2D as cli
+    assert cli.main(["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32", "--uncertainty_T", "8"] + COMMON) \
+        == "Training Finished!"
+    assert cli.main(["--batch_size", "2", "--labeled_bs", "2", "--patch_size", "32", "32", "--exp", "ACDC/Fully_Supervised"]
+                    + COMMON) == "Training Finished!"
+    with pytest.raises(SystemExit):
+        cli.main(["--model", "enet"] + COMMON)
+
+
+def test_cross_teaching_cli_flags_and_cps(cpu_env):
+    from cv_ssl_mis_b200.cli import train_cross_teaching_between_cnn_transformer_2D as cli
+    out = cli.main(["--model", "unet", "--model2", "unet", "--pseudo_loss", "ce", "--batch_size", "4", "--labeled_bs", "2",
+                    "--patch_size", "32", "32", "--cfg", "../code/configs/swin_tiny_patch4_window7_224_lite.yaml",
+                    "--opts", "MODEL.DROP_PATH_RATE", "0.2", "--cache-mode", "part", "--amp-opt-level", "O1"] + COMMON)
+    assert out == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Cross_Teaching_Between_CNN_Transformer_7_labeled" / "unet"
+    assert (snap / "model1_iter_2.pth").exists() and (snap / "model2_iter_2.pth").exists()
+    assert "model1 loss" in (snap / "log.txt").read_text()
+
+
+def test_3d_clis(cpu_env):
+    from cv_ssl_mis_b200.cli import train_uncertainty_aware_mean_teacher_3D as uamt, train_fully_supervised_3D_ViT as fs
+    assert uamt.main(["--model", "vnet", "--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16",
+                      "--uncertainty_T", "2"] + COMMON) == "Training Finished!"
+    assert fs.main(["--model", "vnet", "--batch_size", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
+    with pytest.raises(SystemExit):
+        fs.main(["--model", "unet_3D"] + COMMON)
