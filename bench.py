@@ -333,9 +333,10 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (fp32 storage, TF32 tensor-core math, fp32 accumulate)", "data": "synthetic",
+            "dtype": "tf32", "data": "synthetic",
             "config": {"workload": "configs[1]: 2D UNet Mean-Teacher, ACDC-shape 256x256, 4 classes, bs24 per GPU (12 lab/12 unlab)",
                        "iter_num": "1000+ (consistency term live)", "cuda_graph": tr.use_graph,
+                       "numerics": "fp32 storage, TF32 tensor-core products, fp32 accumulation (the class cuDNN runs for the reference)",
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush needed"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
