@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 B, LB, H, W, NCLS = 24, 12, 256, 256, 4
+WORKLOAD = "configs[1]: 2D UNet Mean-Teacher, ACDC-shape 256x256, 4 classes, bs24 per GPU (12 lab/12 unlab)"
 METRIC = "train-step slices/sec (ACDC 256x256 bs24 MT-UNet)"
 UNIT = "slices/s"
 
@@ -136,7 +137,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": "configs[1]: 2D UNet Mean-Teacher 256x256 bs24 (12 lab/12 unlab)"},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -334,7 +335,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 2D UNet Mean-Teacher, ACDC-shape 256x256, 4 classes, bs24 per GPU (12 lab/12 unlab)",
+            "config": {"workload": WORKLOAD,
                        "iter_num": "1000+ (consistency term live)", "cuda_graph": tr.use_graph,
                        "numerics": "fp32 storage, TF32 tensor-core products, fp32 accumulation (the class cuDNN runs for the reference)",
                        "l2": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush needed"},
