@@ -82,3 +82,42 @@ def test_two_rank_gradient_allreduce_gloo(tmp_path, buckets):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), buckets), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _ct_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests import fake_ops
+    fake_ops.install(_Patch())
+    from cv_ssl_mis_b200.networks import unet as unet_mod
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+
+    B, Lb, P, it0 = 4, 2, 32, 3000
+
+    def run(r, pg):
+        torch.manual_seed(321)
+        m1, m2 = unet_mod.UNet(1, 4, seed=11), unet_mod.UNet(1, 4, seed=22)
+        tr = CrossTeachingTrainer(m1, m2, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it0,
+                                  pseudo_loss="ce", process_group=pg)
+        g = torch.Generator().manual_seed(2000 + r)
+        tr.step(torch.rand(B, 1, P, P, generator=g), torch.randint(0, 4, (B, P, P), generator=g).to(torch.uint8))
+        return tr
+
+    solo = [run(r, None) for r in range(world)]
+    tr = run(rank, dist.group.WORLD)
+    for i in range(2):                                 # one all-reduce per model: both stay replicated, update = mean of solos
+        flat = tr.flats[i].data
+        torch.testing.assert_close(flat, sum(s.flats[i].data for s in solo) / world, rtol=1e-5, atol=1e-7)
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat.clone())
+        assert torch.equal(both[0], both[1])
+    open(os.path.join(out_dir, f"ct_ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_cross_pseudo_supervision_gloo(tmp_path):
+    world = 2
+    mp.spawn(_ct_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ct_ok{r}").exists() for r in range(world))
