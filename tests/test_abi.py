@@ -56,3 +56,13 @@ def test_reference_arm_prints_the_bench_contract():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "MT-UNet" in line["metric"] and "workload" in line["config"]
+
+
+def test_every_op_has_a_cpu_stand_in():
+    """tests/fake_ops.py mirrors the whole ops surface, so every launch schedule can be exercised without a GPU."""
+    from cv_ssl_mis_b200 import ops
+    from tests import fake_ops
+    skip = {"ConvDesc", "B200Error", "conv_desc", "desc_out_dims"}
+    missing = [n for n in dir(ops) if not n.startswith("_") and callable(getattr(ops, n)) and n not in skip
+               and not hasattr(fake_ops, n)]
+    assert not missing, missing
