@@ -229,6 +229,90 @@ class MeanTeacherTrainer:
         return [b for m in mods for b in m.buffers() if b.dtype.is_floating_point]
 
 
+class ICTTrainer(MeanTeacherTrainer):
+    """Interpolation Consistency Training (code/train_interpolation_consistency_training_2D.py:150-193).
+
+    Per iteration: mix factors f ~ Beta(alpha, alpha) for `labeled_bs // 2` pairs of unlabeled samples; the student sees
+    [labeled | u0 (1 - f) + u1 f]; the teacher (train mode, no grad) sees u0 and u1 separately and its softmax outputs
+    are mixed with the same f; consistency = mean((softmax(student_mixed) - mixed teacher probabilities)^2), no
+    `iter < 1000` gate.  The mixed probabilities enter the fused loss kernel as pseudo-logits log(p) (softmax(log p) == p
+    because p sums to one), so no new kernel is needed; the mixing itself is a handful of elementwise torch ops on
+    [h, C, H, W] tensors inside the same CUDA graph.  Validated on CPU against the oracle (tests/test_host_logic.py)."""
+
+    def __init__(self, model, ema_model, *, batch_size=24, labeled_bs=12, ict_alpha=0.2, mix_seed=None, **kw):
+        self.h = labeled_bs // 2
+        assert batch_size - labeled_bs == 2 * self.h and self.h > 0, "ICT pairs the unlabeled half: U == 2 * (labeled_bs // 2)"
+        assert not kw.get("uncertainty_T"), "ICT has no MC-dropout branch"
+        kw.setdefault("consistency_gate_iters", 0)
+        self.B_in, self.ict_alpha = batch_size, ict_alpha
+        # the schedule below runs the student on Lb + h samples and the teacher on h samples (twice)
+        super().__init__(model, ema_model, batch_size=labeled_bs + self.h, labeled_bs=labeled_bs, **kw)
+        import numpy as np
+        self.mix_rng = np.random.RandomState(mix_seed) if mix_seed is not None else np.random
+        dev, h = self.dev, self.h
+        self.x_in = torch.empty((self.B_in, 1, *self.patch), dtype=torch.float32, device=dev)
+        self.y_in = torch.empty((self.B_in, *self.patch), dtype=self.y.dtype, device=dev)
+        self.mix_host = torch.zeros(h, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(h)
+        self.mix = torch.zeros((h, 1, 1, 1), dtype=torch.float32, device=dev)
+        self.p0 = torch.empty((h, self.C, self.S), dtype=torch.float32, device=dev)
+        self.p1 = torch.empty_like(self.p0)
+        self.pseudo_logits = torch.empty_like(self.p0)
+
+    def _device_step(self):
+        Lb, h = self.Lb, self.h
+        self.s_off += 1
+        self.model.train()
+        f = self.mix
+        u0, u1 = self.x_in[Lb:Lb + h], self.x_in[Lb + h:]
+        self.x[:Lb].copy_(self.x_in[:Lb])
+        torch.add(u0 * (1.0 - f), u1 * f, out=self.x[Lb:])                         # :163-165
+        self.y[:Lb].copy_(self.y_in[:Lb])
+        t_rt = self.ema_model._rt
+        with t_rt.side_stream():                                                    # :170-176
+            for src, dst in ((u0, self.p0), (u1, self.p1)):
+                self.t_off += 1
+                self.ema_in.copy_(src)
+                self.t_plan.forward(self.ema_in, train=True)
+                torch.softmax(self.t_plan.logits.view(h, self.C, self.S), dim=1, out=dst)
+            f3 = f.view(h, 1, 1)
+            torch.log(self.p0 * (1.0 - f3) + self.p1 * f3, out=self.pseudo_logits)
+        self.s_plan.forward(self.x, train=True)
+        t_rt.join_side()
+        w = self.hp[HP_WCONS:HP_WCONS + 1]
+        ops.ssl_loss_fwd(self.s_plan.logits, self.pseudo_logits, self.y, False, self.B, Lb, self.C, self.S, w, self.lossbuf,
+                         self.loss_ws, None, 0.0, None)
+        ops.ssl_loss_bwd(self.s_plan.logits, self.pseudo_logits, self.y, False, self.B, Lb, self.C, self.S, w, self.lossbuf,
+                         1.0, self.s_plan.g_logits, True, None, 0.0, None)
+        self.s_plan.backward(None)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat.grad, group=self.pg)
+        ops.sgd_ema_step(self.flat.data, self.flat.grad, self.momentum_buf, self.ema_flat.data, self.hp)
+
+    def step(self, images, labels, read_loss=False, mix_factors=None):
+        """images [batch_size, 1, H, W], labels [batch_size, H, W]; mix_factors: optional [labeled_bs // 2] values
+        (default: numpy Beta(ict_alpha, ict_alpha) draws, :155-158)."""
+        if mix_factors is None:
+            mix_factors = self.mix_rng.beta(self.ict_alpha, self.ict_alpha, size=(self.h,))
+        self.mix_host.copy_(torch.as_tensor(mix_factors, dtype=torch.float32).reshape(self.h))
+        self.mix.view(self.h).copy_(self.mix_host, non_blocking=True)
+        self.x_in.copy_(images, non_blocking=True)
+        self.y_in.copy_(labels, non_blocking=True)
+        self._set_hparams()
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._device_step()
+        self.lr = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9
+        self.iter_num += 1
+        if read_loss:
+            self.loss_host.copy_(self.lossbuf[:4], non_blocking=True)
+            torch.cuda.current_stream().synchronize() if self.dev.type == "cuda" else None
+            return self.loss_host.tolist()
+        return self.lossbuf
+
+
 def _plan_for(model, B, patch, need_grad):
     """UNet-style plans are keyed by (B, H, W), the Swin-UNet's by B alone (its token grid is fixed by its config)."""
     if getattr(model, "plan_key_is_batch", False):

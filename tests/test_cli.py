@@ -64,3 +64,9 @@ def test_3d_clis(cpu_env):
     assert fs.main(["--model", "vnet", "--batch_size", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
     with pytest.raises(SystemExit):
         fs.main(["--model", "unet_3D"] + COMMON)
+
+
+def test_ict_cli(cpu_env):
+    from cv_ssl_mis_b200.cli import train_interpolation_consistency_training_2D as cli
+    assert cli.main(["--batch_size", "8", "--labeled_bs", "4", "--patch_size", "32", "32", "--ict_alpha", "1"] + COMMON) \
+        == "Training Finished!"

@@ -468,3 +468,49 @@ def test_uamt_2d_unet_trainer_matches_oracle(fake):
     k = "encoder.down2.maxpool_conv.1.conv_conv.0.weight"
     new = s_sd[k] - 0.01 * (leaf[k].grad + 1e-4 * s_sd[k])
     torch.testing.assert_close(student.state_dict()[k], new, rtol=2e-3, atol=1e-6)
+
+
+def test_ict_trainer_matches_oracle(fake):
+    """code/train_interpolation_consistency_training_2D.py:150-193 -- input mix-up of unlabeled pairs, teacher probabilities
+    mixed with the same factors, MSE consistency.  One ICTTrainer step against the oracle pieces, then the SGD / EMA update."""
+    from cv_ssl_mis_b200.trainers import ICTTrainer
+    torch.manual_seed(71)
+    student, teacher = unet_mod.UNet(1, 4, seed=11), unet_mod.UNet(1, 4, seed=22)
+    s_sd = {k: v.clone() for k, v in student.state_dict().items()}
+    t_sd = {k: v.clone() for k, v in teacher.state_dict().items()}
+    B, Lb, P, it = 8, 4, 32, 700                      # below the MT2D gate: ICT applies the consistency term from the start
+    h = Lb // 2
+    tr = ICTTrainer(student, teacher, batch_size=B, labeled_bs=Lb, patch_size=(P, P), num_classes=4, start_iter=it)
+    g = torch.Generator().manual_seed(18)
+    x = torch.rand(B, 1, P, P, generator=g)
+    y = torch.randint(0, 4, (B, P, P), generator=g).to(torch.uint8)
+    f = torch.tensor([0.3, 0.85])
+    ce, dice, cons, total = tr.step(x, y, read_loss=True, mix_factors=f)
+
+    fm = f.view(h, 1, 1, 1)
+    u0, u1 = x[Lb:Lb + h], x[Lb + h:]
+    leaf = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v.clone()) for k, v in s_sd.items()}
+    s_in = torch.cat([x[:Lb], u0 * (1 - fm) + u1 * fm], 0)                                           # :163-167
+    outputs = O.unet_forward(leaf, s_in, True, unet_masks(11 + 1, Lb + h, P, P))
+    with torch.no_grad():                                                                            # :170-176
+        p0 = torch.softmax(O.unet_forward(t_sd, u0, True, unet_masks(22 + 1, h, P, P)), 1)
+        p1 = torch.softmax(O.unet_forward(t_sd, u1, True, unet_masks(22 + 2, h, P, P)), 1)
+        mixed = p0 * (1 - fm) + p1 * fm
+    sup, ce_r, dice_r = O.supervised_loss(outputs[:Lb], y[:Lb], 4)
+    cons_r = torch.mean((torch.softmax(outputs, 1)[Lb:] - mixed) ** 2)                               # :184-185
+    w = O.consistency_weight(it)
+    assert w > 0
+    loss = sup + w * cons_r
+    loss.backward()
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([ce_r, dice_r, cons_r, loss]).detach(),
+                               rtol=1e-4, atol=1e-6)
+    k = "decoder.up1.conv1x1.weight"
+    new = s_sd[k] - 0.01 * (leaf[k].grad + 1e-4 * s_sd[k])
+    torch.testing.assert_close(student.state_dict()[k], new, rtol=2e-3, atol=1e-6)
+    alpha = O.ema_alpha(it)
+    torch.testing.assert_close(teacher.state_dict()[k], alpha * t_sd[k] + (1 - alpha) * new, rtol=2e-3, atol=1e-6)
+    # default mix factors come from numpy's Beta(alpha, alpha)
+    tr2 = ICTTrainer(unet_mod.UNet(1, 4, seed=1), unet_mod.UNet(1, 4, seed=2), batch_size=B, labeled_bs=Lb, patch_size=(P, P),
+                     num_classes=4, mix_seed=5)
+    out = tr2.step(x, y, read_loss=True)
+    assert all(v == v for v in out) and 0.0 <= float(tr2.mix.min()) and float(tr2.mix.max()) <= 1.0
