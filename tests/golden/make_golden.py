@@ -419,8 +419,105 @@ def swin_fixture():
           "ps", float(pseudo_supervision1), float(pseudo_supervision2))
 
 
+def cps_ict_fixture():
+    """One iteration each of Cross Pseudo Supervision (code/train_cross_pseudo_supervision_2D.py:170-213) and of
+    Interpolation Consistency Training (code/train_interpolation_consistency_training_2D.py:150-197), driven through the
+    reference's UNet / DiceLoss / ramps / torch.optim.SGD, lines quoted below.  Dropout off (its masks cannot be shared
+    with torch's RNG); BatchNorm in train mode."""
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(4)
+    base_lr, max_iterations, consistency, consistency_rampup = 0.01, 30000, 0.1, 200.0
+    out = {}
+    # ---------------------------------------------------------------- CPS
+    seed = 8765
+    torch.manual_seed(seed)
+    model1, model2 = RefUNet(in_chns=1, class_num=4), RefUNet(in_chns=1, class_num=4)          # :118-126 (two create_model())
+    no_dropout(model1), no_dropout(model2)
+    model1.train(), model2.train()
+    init_ck = (checksum(model1.state_dict()), checksum(model2.state_dict()))
+    iter_num, labeled_bs = 4000, 2
+    lr_ = base_lr * (1.0 - iter_num / max_iterations) ** 0.9                                    # rate installed by iteration 3999 (:203-207)
+    optimizer1 = torch.optim.SGD(model1.parameters(), lr=lr_, momentum=0.9, weight_decay=0.0001)
+    optimizer2 = torch.optim.SGD(model2.parameters(), lr=lr_, momentum=0.9, weight_decay=0.0001)
+    g = torch.Generator().manual_seed(6)
+    volume_batch = torch.rand(4, 1, 32, 32, generator=g)
+    label_batch = blocky_labels(g, 4, 32, 32, 4)
+    outputs1 = model1(volume_batch)                                                             # :176
+    outputs_soft1 = torch.softmax(outputs1, dim=1)
+    outputs2 = model2(volume_batch)                                                             # :179
+    outputs_soft2 = torch.softmax(outputs2, dim=1)
+    consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :180
+    loss1 = 0.5 * (ce_loss(outputs1[:labeled_bs], label_batch[:][:labeled_bs].long()) + dice_loss(
+        outputs_soft1[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1)))                    # :182-183
+    loss2 = 0.5 * (ce_loss(outputs2[:labeled_bs], label_batch[:][:labeled_bs].long()) + dice_loss(
+        outputs_soft2[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1)))                    # :184-185
+    pseudo_outputs1 = torch.argmax(outputs_soft1[labeled_bs:].detach(), dim=1, keepdim=False)  # :187
+    pseudo_outputs2 = torch.argmax(outputs_soft2[labeled_bs:].detach(), dim=1, keepdim=False)  # :188
+    pseudo_supervision1 = ce_loss(outputs1[labeled_bs:], pseudo_outputs2)                       # :190
+    pseudo_supervision2 = ce_loss(outputs2[labeled_bs:], pseudo_outputs1)                       # :191
+    model1_loss = loss1 + consistency_weight * pseudo_supervision1                              # :193
+    model2_loss = loss2 + consistency_weight * pseudo_supervision2                              # :194
+    loss = model1_loss + model2_loss                                                            # :196
+    optimizer1.zero_grad()
+    optimizer2.zero_grad()
+    loss.backward()
+    optimizer1.step()
+    optimizer2.step()
+    key = "decoder.up4.conv.conv_conv.0.weight"
+    out["cps"] = dict(seed=seed, init_ck=init_ck, iter_num=iter_num, labeled_bs=labeled_bs, lr=lr_, w=consistency_weight,
+                      x=volume_batch, y=label_batch, model1_loss=model1_loss.detach(), model2_loss=model2_loss.detach(),
+                      ps1=pseudo_supervision1.detach(), ps2=pseudo_supervision2.detach(), loss1=loss1.detach(),
+                      loss2=loss2.detach(), key=key, w1=model1.state_dict()[key].clone(), w2=model2.state_dict()[key].clone())
+    # ---------------------------------------------------------------- ICT
+    seed = 9876
+    torch.manual_seed(seed)
+    model, ema_model = RefUNet(in_chns=1, class_num=4), RefUNet(in_chns=1, class_num=4)        # :112-121
+    for p in ema_model.parameters():
+        p.detach_()
+    no_dropout(model), no_dropout(ema_model)
+    model.train()
+    init_ck = (checksum(model.state_dict()), checksum(ema_model.state_dict()))
+    iter_num, labeled_bs, ema_decay = 700, 4, 0.99
+    lr_ = base_lr * (1.0 - (iter_num - 1) / max_iterations) ** 0.9                              # installed after iteration 699 (:191-193)
+    optimizer = torch.optim.SGD(model.parameters(), lr=lr_, momentum=0.9, weight_decay=0.0001)
+    g = torch.Generator().manual_seed(8)
+    volume_batch = torch.rand(8, 1, 32, 32, generator=g)
+    label_batch = blocky_labels(g, 8, 32, 32, 4)
+    unlabeled_volume_batch = volume_batch[labeled_bs:]                                          # :152
+    labeled_volume_batch = volume_batch[:labeled_bs]
+    ict_mix_factors = torch.tensor([0.3, 0.85], dtype=torch.float).view(labeled_bs // 2, 1, 1, 1)   # :156-159 (Beta draws, fixed here)
+    unlabeled_volume_batch_0 = unlabeled_volume_batch[0:labeled_bs // 2, ...]                   # :160
+    unlabeled_volume_batch_1 = unlabeled_volume_batch[labeled_bs // 2:, ...]                    # :161
+    batch_ux_mixed = unlabeled_volume_batch_0 * (1.0 - ict_mix_factors) + unlabeled_volume_batch_1 * ict_mix_factors   # :164-166
+    input_volume_batch = torch.cat([labeled_volume_batch, batch_ux_mixed], dim=0)               # :167-168
+    outputs = model(input_volume_batch)                                                         # :169
+    outputs_soft = torch.softmax(outputs, dim=1)
+    with torch.no_grad():
+        ema_output_ux0 = torch.softmax(ema_model(unlabeled_volume_batch_0), dim=1)             # :172-173
+        ema_output_ux1 = torch.softmax(ema_model(unlabeled_volume_batch_1), dim=1)             # :174-175
+        batch_pred_mixed = ema_output_ux0 * (1.0 - ict_mix_factors) + ema_output_ux1 * ict_mix_factors   # :176-177
+    loss_ce = ce_loss(outputs[:labeled_bs], label_batch[:labeled_bs][:].long())                 # :179-180
+    loss_dice = dice_loss(outputs_soft[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1))     # :181-182
+    supervised_loss = 0.5 * (loss_dice + loss_ce)
+    consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :184
+    consistency_loss = torch.mean((outputs_soft[labeled_bs:] - batch_pred_mixed) ** 2)          # :185-186
+    loss = supervised_loss + consistency_weight * consistency_loss                              # :187
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    update_ema_variables(model, ema_model, ema_decay, iter_num)                                 # :192
+    key = "decoder.up1.conv1x1.weight"
+    out["ict"] = dict(seed=seed, init_ck=init_ck, iter_num=iter_num, labeled_bs=labeled_bs, lr=lr_, w=consistency_weight,
+                      x=volume_batch, y=label_batch, mix=ict_mix_factors.view(-1).clone(), loss=loss.detach(),
+                      ce=loss_ce.detach(), dice=loss_dice.detach(), cons=consistency_loss.detach(), key=key,
+                      w_student=model.state_dict()[key].clone(), w_teacher=ema_model.state_dict()[key].clone())
+    torch.save(out, os.path.join(HERE, "cps_ict.pt"))
+    print("cps: m1", float(model1_loss), "m2", float(model2_loss), "ps", float(pseudo_supervision1), float(pseudo_supervision2),
+          "| ict: loss", float(loss), "cons", float(consistency_loss), "w", consistency_weight)
+
+
 if __name__ == "__main__":
     fixtures = dict(unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
-                    vnet=vnet_fixture, swin=swin_fixture)
+                    vnet=vnet_fixture, swin=swin_fixture, cps_ict=cps_ict_fixture)
     for name in (sys.argv[1:] or list(fixtures)):
         fixtures[name]()

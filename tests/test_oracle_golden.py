@@ -163,3 +163,56 @@ def test_swin_cross_teaching_step(golden):
     torch.testing.assert_close(sd2["layers.1.blocks.1.attn.qkv.weight"][:8], g["qkv_w2"], rtol=1e-5, atol=1e-7)
     assert abs(checksum(sd1) - g["ck1"]) <= 1e-6 * g["ck1"]
     assert abs(checksum({"swin_unet." + k: v for k, v in sd2.items()}) - g["ck2"]) <= 1e-6 * g["ck2"]
+
+
+# ------------------------------------------------------------------ CPS / ICT: OUR trainers against the reference-driven fixture
+@pytest.fixture()
+def fake_no_dropout(monkeypatch):
+    from tests import fake_ops
+    from cv_ssl_mis_b200.networks import unet as unet_mod
+    fake_ops.install(monkeypatch)
+    monkeypatch.setattr(unet_mod, "DROPOUT", [0.0] * 5)       # the fixture ran the reference with dropout off
+
+
+def _seeded_models(seed, n=2):
+    torch.manual_seed(seed)
+    return [UNet(1, 4) for _ in range(n)]
+
+
+def test_cps_trainer_matches_reference_fixture(golden, fake_no_dropout):
+    """CrossTeachingTrainer(pseudo_loss='ce') (launch schedule + fused loss stand-in) against one iteration of
+    code/train_cross_pseudo_supervision_2D.py run on the reference's own UNet / DiceLoss / SGD."""
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+    g = golden("cps_ict.pt")["cps"]
+    m1, m2 = _seeded_models(g["seed"])
+    ck = (checksum(m1.state_dict()), checksum(m2.state_dict()))
+    if abs(ck[0] - g["init_ck"][0]) > 1e-6 * ck[0] or abs(ck[1] - g["init_ck"][1]) > 1e-6 * ck[1]:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    tr = CrossTeachingTrainer(m1, m2, batch_size=4, labeled_bs=g["labeled_bs"], patch_size=(32, 32), num_classes=4,
+                              start_iter=g["iter_num"], pseudo_loss="ce")
+    assert abs(tr.lr - g["lr"]) < 1e-12
+    got = tr.step(g["x"], g["y"], read_loss=True)
+    want = [g["ps1"], g["model1_loss"], g["ps2"], g["model2_loss"]]
+    torch.testing.assert_close(torch.tensor([got[2], got[3], got[6], got[7]]), torch.stack(want), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.tensor(0.5 * (got[0] + got[1])), g["loss1"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(m1.state_dict()[g["key"]], g["w1"], rtol=1e-3, atol=2e-6)
+    torch.testing.assert_close(m2.state_dict()[g["key"]], g["w2"], rtol=1e-3, atol=2e-6)
+
+
+def test_ict_trainer_matches_reference_fixture(golden, fake_no_dropout):
+    """ICTTrainer against one iteration of code/train_interpolation_consistency_training_2D.py run on the reference's
+    own modules (same mix factors)."""
+    from cv_ssl_mis_b200.trainers import ICTTrainer
+    g = golden("cps_ict.pt")["ict"]
+    student, teacher = _seeded_models(g["seed"])
+    ck = (checksum(student.state_dict()), checksum(teacher.state_dict()))
+    if abs(ck[0] - g["init_ck"][0]) > 1e-6 * ck[0] or abs(ck[1] - g["init_ck"][1]) > 1e-6 * ck[1]:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    tr = ICTTrainer(student, teacher, batch_size=8, labeled_bs=g["labeled_bs"], patch_size=(32, 32), num_classes=4,
+                    start_iter=g["iter_num"])
+    tr.lr = g["lr"]                                   # the rate the reference installed after the previous iteration
+    ce, dice, cons, total = tr.step(g["x"], g["y"], read_loss=True, mix_factors=g["mix"])
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([g["ce"], g["dice"], g["cons"], g["loss"]]),
+                               rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(student.state_dict()[g["key"]], g["w_student"], rtol=1e-3, atol=2e-6)
+    torch.testing.assert_close(teacher.state_dict()[g["key"]], g["w_teacher"], rtol=1e-3, atol=2e-6)
