@@ -516,8 +516,75 @@ def cps_ict_fixture():
           "| ict: loss", float(loss), "cons", float(consistency_loss), "w", consistency_weight)
 
 
+def mt_vit_fixture():
+    """One Mean-Teacher iteration over two Swin-UNets (code/train_mean_teacher_ViT.py:147-158, 201-233) through the
+    reference's own SwinUnet / DiceLoss / ramps / SGD; DropPath rate 0, the input noise is OUR Philox stream (seed 7,
+    epoch 1, stream 1000) so the trainer under test draws the same values."""
+    from types import SimpleNamespace as NS
+    from oracle import philox
+    from cv_ssl_mis_b200.networks.swin_unet import SwinUnet as OurSwin
+    _install_timm_shim(lambda *a: None)
+    from networks.vision_transformer import SwinUnet as RefSwin
+    c = dict(SWIN_SMALL, drop_path_rate=0.0)
+    config = NS(DATA=NS(IMG_SIZE=c["img_size"]),
+                MODEL=NS(DROP_RATE=0.0, DROP_PATH_RATE=0.0, PRETRAIN_CKPT=None,
+                         SWIN=NS(PATCH_SIZE=c["patch_size"], IN_CHANS=c["in_chans"], EMBED_DIM=c["embed_dim"],
+                                 DEPTHS=list(c["depths"]), NUM_HEADS=list(c["num_heads"]), WINDOW_SIZE=c["window_size"],
+                                 MLP_RATIO=c["mlp_ratio"], QKV_BIAS=True, QK_SCALE=False, APE=False, PATCH_NORM=True)),
+                TRAIN=NS(USE_CHECKPOINT=False))
+    seed = 2468
+    torch.manual_seed(seed)
+    model = RefSwin(config, img_size=c["img_size"], num_classes=4)                              # :147-148
+    ema_model = RefSwin(config, img_size=c["img_size"], num_classes=4)                          # :151-152
+    for param in ema_model.parameters():                                                        # :155-156
+        param.detach_()
+    torch.manual_seed(seed)
+    ours = [OurSwin(config, img_size=c["img_size"], num_classes=4) for _ in range(2)]
+    for ref, our in zip((model, ema_model), ours):
+        for k, v in ref.state_dict().items():
+            assert torch.equal(v, our.state_dict()[k]), k
+    init_ck = (checksum(model.state_dict()), checksum(ema_model.state_dict()))
+    model.train()
+    base_lr, max_iterations, labeled_bs, ema_decay, consistency, consistency_rampup = 0.01, 30000, 2, 0.99, 0.1, 200.0
+    iter_num = 1500
+    lr_ = base_lr * (1.0 - (iter_num - 1) / max_iterations) ** 0.9
+    optimizer = torch.optim.SGD(model.parameters(), lr=lr_, momentum=0.9, weight_decay=0.0001)   # :186-187
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(4)
+    g = torch.Generator().manual_seed(12)
+    P = c["img_size"]
+    volume_batch = torch.rand(4, 1, P, P, generator=g)
+    label_batch = blocky_labels(g, 4, P, P, 4)
+    unlabeled_volume_batch = volume_batch[labeled_bs:]                                          # :205
+    noise = torch.from_numpy(philox.clamp_noise(7 + 1, 1000, 2 * P * P)).reshape(2, 1, P, P)    # stands for :207-208
+    ema_inputs = unlabeled_volume_batch + noise                                                 # :209
+    outputs = model(volume_batch)                                                               # :211
+    outputs_soft = torch.softmax(outputs, dim=1)
+    with torch.no_grad():
+        ema_output = ema_model(ema_inputs)                                                      # :214
+        ema_output_soft = torch.softmax(ema_output, dim=1)
+    loss_ce = ce_loss(outputs[:labeled_bs], label_batch[:][:labeled_bs].long())                 # :217-218
+    loss_dice = dice_loss(outputs_soft[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1))     # :219-220
+    supervised_loss = 0.5 * (loss_dice + loss_ce)
+    consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :222
+    consistency_loss = torch.mean((outputs_soft[labeled_bs:] - ema_output_soft) ** 2)           # :226-227 (iter >= 1000)
+    loss = supervised_loss + consistency_weight * consistency_loss
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    update_ema_variables(model, ema_model, ema_decay, iter_num)                                 # :232
+    keys = ["swin_unet.layers.0.blocks.0.mlp.fc1.weight", "swin_unet.layers_up.3.blocks.1.attn.qkv.bias", "swin_unet.output.weight"]
+    torch.save(dict(seed=seed, init_ck=init_ck, cfg=c, iter_num=iter_num, labeled_bs=labeled_bs, lr=lr_, w=consistency_weight,
+                    x=volume_batch, y=label_batch, loss=loss.detach(), ce=loss_ce.detach(), dice=loss_dice.detach(),
+                    cons=consistency_loss.detach(), keys=keys,
+                    student={k: model.state_dict()[k].clone() for k in keys},
+                    teacher={k: ema_model.state_dict()[k].clone() for k in keys}),
+               os.path.join(HERE, "mt_vit.pt"))
+    print("mt_vit: loss", float(loss), "cons", float(consistency_loss), "w", consistency_weight)
+
+
 if __name__ == "__main__":
-    fixtures = dict(unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
+    fixtures = dict(mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
                     vnet=vnet_fixture, swin=swin_fixture, cps_ict=cps_ict_fixture)
     for name in (sys.argv[1:] or list(fixtures)):
         fixtures[name]()

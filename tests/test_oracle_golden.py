@@ -227,3 +227,31 @@ def test_ict_trainer_matches_reference_fixture(golden, fake_no_dropout):
                                rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(student.state_dict()[g["key"]], g["w_student"], rtol=1e-3, atol=2e-6)
     torch.testing.assert_close(teacher.state_dict()[g["key"]], g["w_teacher"], rtol=1e-3, atol=2e-6)
+
+
+def test_mean_teacher_vit_trainer_matches_reference_fixture(golden, monkeypatch):
+    """MeanTeacherTrainer over two of OUR Swin-UNet containers (launch tape + stand-in ops) against one iteration of
+    code/train_mean_teacher_ViT.py run on the reference's own SwinUnet modules (tests/golden/make_golden.py:mt_vit_fixture)."""
+    from tests import fake_ops
+    from cv_ssl_mis_b200.networks.swin_unet import SwinUnet
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    fake_ops.install(monkeypatch)
+    g = golden("mt_vit.pt")
+    c = g["cfg"]
+    cfg = dict(img_size=c["img_size"], embed_dim=c["embed_dim"], num_heads=tuple(c["num_heads"]), window_size=c["window_size"],
+               drop_path_rate=0.0)
+    torch.manual_seed(g["seed"])
+    student, teacher = SwinUnet(dict(cfg), num_classes=4, seed=5), SwinUnet(dict(cfg), num_classes=4, seed=6)
+    ck = (checksum(student.state_dict()), checksum(teacher.state_dict()))
+    if abs(ck[0] - g["init_ck"][0]) > 1e-6 * ck[0] or abs(ck[1] - g["init_ck"][1]) > 1e-6 * ck[1]:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    P = c["img_size"]
+    tr = MeanTeacherTrainer(student, teacher, batch_size=4, labeled_bs=g["labeled_bs"], patch_size=(P, P), num_classes=4,
+                            start_iter=g["iter_num"], noise_seed=7)
+    tr.lr = g["lr"]
+    ce, dice, cons, total = tr.step(g["x"], g["y"], read_loss=True)
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([g["ce"], g["dice"], g["cons"], g["loss"]]),
+                               rtol=1e-4, atol=1e-6)
+    for k in g["keys"]:
+        torch.testing.assert_close(student.state_dict()[k], g["student"][k], rtol=1e-3, atol=2e-6, msg=lambda m, k=k: f"student {k}: {m}")
+        torch.testing.assert_close(teacher.state_dict()[k], g["teacher"][k], rtol=1e-3, atol=2e-6, msg=lambda m, k=k: f"teacher {k}: {m}")
