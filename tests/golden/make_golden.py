@@ -583,8 +583,79 @@ def mt_vit_fixture():
     print("mt_vit: loss", float(loss), "cons", float(consistency_loss), "w", consistency_weight)
 
 
+def uamt2d_fixture():
+    """One iteration of code/train_uncertainty_aware_mean_teacher_2D.py:150-196 through the reference's own UNet /
+    DiceLoss / softmax_mse_loss / ramps / SGD.  Dropout off; the five noise tensors are OUR Philox stream (seed 7, epochs
+    1..5, stream 1000) so the trainer under test draws the same values."""
+    import torch.nn.functional as F
+    from oracle import philox
+    seed = 1470
+    torch.manual_seed(seed)
+    model, ema_model = RefUNet(in_chns=1, class_num=4), RefUNet(in_chns=1, class_num=4)
+    for p in ema_model.parameters():
+        p.detach_()
+    no_dropout(model), no_dropout(ema_model)
+    model.train()
+    init_ck = (checksum(model.state_dict()), checksum(ema_model.state_dict()))
+    # freshly initialised networks predict near-uniform classes (entropy ~ ln 4 > threshold: an empty mask); sharpen the
+    # logits so that the uncertainty mask is partial.  The test applies the same scaling.
+    with torch.no_grad():
+        for m in (model, ema_model):
+            m.decoder.out_conv.weight.mul_(40.0)
+    base_lr, max_iterations, labeled_bs, ema_decay, consistency, consistency_rampup = 0.01, 30000, 2, 0.99, 0.1, 200.0
+    num_classes, iter_num = 4, 2000
+    lr_ = base_lr * (1.0 - (iter_num - 1) / max_iterations) ** 0.9
+    optimizer = torch.optim.SGD(model.parameters(), lr=lr_, momentum=0.9, weight_decay=0.0001)
+    ce_loss = torch.nn.CrossEntropyLoss()
+    dice_loss = ref_losses.DiceLoss(num_classes)
+    g = torch.Generator().manual_seed(16)
+    P = 32
+    volume_batch = torch.rand(4, 1, P, P, generator=g)
+    label_batch = blocky_labels(g, 4, P, P, 4)
+    noise_of = lambda epoch, n: torch.from_numpy(philox.clamp_noise(7 + epoch, 1000, n * P * P)).reshape(n, 1, P, P)
+    unlabeled_volume_batch = volume_batch[labeled_bs:]                                          # :151
+    ema_inputs = unlabeled_volume_batch + noise_of(1, 2)                                        # :153-155
+    outputs = model(volume_batch)                                                               # :157
+    outputs_soft = torch.softmax(outputs, dim=1)
+    with torch.no_grad():
+        ema_output = ema_model(ema_inputs)                                                      # :160
+    T = 8
+    _, _, w, h = unlabeled_volume_batch.shape
+    volume_batch_r = unlabeled_volume_batch.repeat(2, 1, 1, 1)                                  # :163
+    stride = volume_batch_r.shape[0] // 2
+    preds = torch.zeros([stride * T, num_classes, w, h])
+    for i in range(T // 2):                                                                     # :166-172
+        ema_inputs = volume_batch_r + noise_of(2 + i, 4)
+        with torch.no_grad():
+            preds[2 * stride * i:2 * stride * (i + 1)] = ema_model(ema_inputs)
+    preds = F.softmax(preds, dim=1)
+    preds = preds.reshape(T, stride, num_classes, w, h)
+    preds = torch.mean(preds, dim=0)
+    uncertainty = -1.0 * torch.sum(preds * torch.log(preds + 1e-6), dim=1, keepdim=True)       # :176-177
+    loss_ce = ce_loss(outputs[:labeled_bs], label_batch[:labeled_bs][:].long())                 # :179-180
+    loss_dice = dice_loss(outputs_soft[:labeled_bs], label_batch[:labeled_bs].unsqueeze(1))     # :181-182
+    supervised_loss = 0.5 * (loss_dice + loss_ce)
+    consistency_weight = consistency * ref_ramps.sigmoid_rampup(iter_num // 150, consistency_rampup)   # :184
+    consistency_dist = ref_losses.softmax_mse_loss(outputs[labeled_bs:], ema_output)            # :185-186
+    threshold = (0.75 + 0.25 * ref_ramps.sigmoid_rampup(iter_num, max_iterations)) * np.log(2)  # :187-188
+    mask = (uncertainty < threshold).float()
+    consistency_loss = torch.sum(mask * consistency_dist) / (2 * torch.sum(mask) + 1e-16)       # :190-191
+    loss = supervised_loss + consistency_weight * consistency_loss
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    update_ema_variables(model, ema_model, ema_decay, iter_num)
+    key = "encoder.down2.maxpool_conv.1.conv_conv.0.weight"
+    torch.save(dict(seed=seed, init_ck=init_ck, iter_num=iter_num, labeled_bs=labeled_bs, lr=lr_, w=consistency_weight,
+                    threshold=float(threshold), mask_frac=float(mask.mean()), x=volume_batch, y=label_batch,
+                    loss=loss.detach(), ce=loss_ce.detach(), dice=loss_dice.detach(), cons=consistency_loss.detach(), key=key,
+                    w_student=model.state_dict()[key].clone(), w_teacher=ema_model.state_dict()[key].clone()),
+               os.path.join(HERE, "uamt2d.pt"))
+    print("uamt2d: loss", float(loss), "cons", float(consistency_loss), "mask fraction", float(mask.mean()))
+
+
 if __name__ == "__main__":
-    fixtures = dict(mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
+    fixtures = dict(uamt2d=uamt2d_fixture, mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
                     vnet=vnet_fixture, swin=swin_fixture, cps_ict=cps_ict_fixture)
     for name in (sys.argv[1:] or list(fixtures)):
         fixtures[name]()

@@ -255,3 +255,27 @@ def test_mean_teacher_vit_trainer_matches_reference_fixture(golden, monkeypatch)
     for k in g["keys"]:
         torch.testing.assert_close(student.state_dict()[k], g["student"][k], rtol=1e-3, atol=2e-6, msg=lambda m, k=k: f"student {k}: {m}")
         torch.testing.assert_close(teacher.state_dict()[k], g["teacher"][k], rtol=1e-3, atol=2e-6, msg=lambda m, k=k: f"teacher {k}: {m}")
+
+
+def test_uamt_2d_trainer_matches_reference_fixture(golden, fake_no_dropout):
+    """MeanTeacherTrainer(uncertainty_T=8) over UNets against one iteration of
+    code/train_uncertainty_aware_mean_teacher_2D.py run on the reference's own modules (tests/golden/uamt2d.pt)."""
+    from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+    g = golden("uamt2d.pt")
+    student, teacher = _seeded_models(g["seed"])
+    ck = (checksum(student.state_dict()), checksum(teacher.state_dict()))
+    if abs(ck[0] - g["init_ck"][0]) > 1e-6 * ck[0] or abs(ck[1] - g["init_ck"][1]) > 1e-6 * ck[1]:
+        pytest.skip("torch RNG stream differs from the one the fixture was generated with")
+    with torch.no_grad():                             # the fixture sharpens the logits so that the mask is partial
+        for m in (student, teacher):
+            m.decoder.out_conv.weight.mul_(40.0)
+    tr = MeanTeacherTrainer(student, teacher, batch_size=4, labeled_bs=g["labeled_bs"], patch_size=(32, 32), num_classes=4,
+                            start_iter=g["iter_num"], noise_seed=7, uncertainty_T=8, consistency_gate_iters=0)
+    tr.lr = g["lr"]
+    assert abs(tr.uncertainty_threshold(g["iter_num"]) - g["threshold"]) < 1e-12
+    ce, dice, cons, total = tr.step(g["x"], g["y"], read_loss=True)
+    assert 0.05 < g["mask_frac"] < 0.95
+    torch.testing.assert_close(torch.tensor([ce, dice, cons, total]), torch.stack([g["ce"], g["dice"], g["cons"], g["loss"]]),
+                               rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(student.state_dict()[g["key"]], g["w_student"], rtol=1e-3, atol=2e-6)
+    torch.testing.assert_close(teacher.state_dict()[g["key"]], g["w_teacher"], rtol=1e-3, atol=2e-6)
