@@ -66,6 +66,9 @@ SIGNATURES = {
     "b200_conv_umma_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_row_wgrad_supported": (_I, [_D]),
+    "b200_conv_row_wgrad_workspace_bytes": (_L, [_D]),
+    "b200_conv_row_wgrad": (_I, [_D, _P, _P, _P, _P, _L, _P, _P, _I, _S]),
     "b200_conv_pack_batch": (_I, [_P, _I, _I, _S]),
     "b200_conv_c1_supported": (_I, [_D]),
     "b200_conv_c1_fwd": (_I, [_D, _P, _P, _P, _P, _S]),
@@ -124,7 +127,7 @@ SIGNATURES = {
 
 # entry points whose int return value is NOT a status code
 _NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported",
-               "b200_conv_c1_supported", "b200_linear_supported"}
+               "b200_conv_c1_supported", "b200_linear_supported", "b200_conv_row_wgrad_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

@@ -126,7 +126,7 @@ class ConvLayer:
         self.gemm = (is_conv and self.k == 1 and self.stride == 1 and not rt.exact and not self.out_nchw
                      and self.cout >= 32 and self.cin >= 32 and ops.linear_supported(self.M, self.cout, c0, c1))
         if self.gemm:
-            self.umma_fwd = self.umma_dgrad = self.c1 = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = False
+            self.umma_fwd = self.umma_dgrad = self.c1 = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = self.row_wgrad = False
             self.wp_fwd = self.wp_bwd = None
             if need_grad:
                 rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(self.M, self.cout, self.cin),
@@ -144,6 +144,9 @@ class ConvLayer:
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
         self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)
+        # 2D 3x3 weight gradient on tcgen05 (row-ring kernel); B200_WGRAD=tile keeps the mma.sync kernel for A/B runs
+        self.row_wgrad = (is_conv and not rt.exact and need_grad and os.environ.get("B200_WGRAD", "row") == "row"
+                          and ops.conv_row_wgrad_supported(self.desc))
         fwd_mode = PACK_CONV_FWD if is_conv else PACK_DECONV_FWD
         nfwd = (ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
                 ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
@@ -153,6 +156,8 @@ class ConvLayer:
             if is_conv:
                 self.bwd_mode = PACK_CONV_DGRAD if self.stride == 1 else PACK_CONV_DGRAD_D2S
                 rt.need_scratch(ops.conv_c1_wgrad_workspace_bytes(self.desc) if self.c1 else
+                                max(ops.conv_row_wgrad_workspace_bytes(self.desc), ops.colsum_workspace_bytes(self.M, self.cout))
+                                if self.row_wgrad else
                                 ops.conv_tile_wgrad_workspace_bytes(self.desc) if self.tile_wgrad
                                 else ops.conv_wgrad_workspace_bytes(self.desc))
             else:
@@ -207,6 +212,7 @@ class ConvLayer:
     # ---- forward
     def forward(self, rt: Runtime, src0, src1=None, train=True):
         _lib.tag = self.name
+        self.bn_train = train
         if self.gemm:
             ops.linear_fwd(src0, src1, self.conv.weight.view(self.cout, self.cin), self.conv.bias, self.y, self.M, self.cout)
         elif self.c1:
@@ -258,6 +264,14 @@ class ConvLayer:
                 ws = rt.scratch_side
                 if self.c1:
                     ops.conv_c1_wgrad(self.desc, src0, dy, ws, conv.weight.grad, bias_grad, accumulate_w)
+                elif self.row_wgrad:
+                    # a bias in front of a train-mode BatchNorm has an identically zero gradient (the BatchNorm backward
+                    # removes the per-channel mean of dy); otherwise it is the column sum of dy
+                    zero_db = self.has_act and getattr(self, "bn_train", True)
+                    ops.conv_row_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, accumulate_w,
+                                       bias_grad if zero_db else None)
+                    if bias_grad is not None and not zero_db:
+                        ops.colsum(dy, self.M, self.cout, bias_grad, ws, accumulate_w)
                 elif self.tile_wgrad:
                     ops.conv_tile_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, accumulate_w)
                 else:

@@ -127,6 +127,21 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
               _pf(dw), _pf(db), int(accumulate), _st())
 
 
+# row-ring tcgen05 weight gradient (2D 3x3 stride-1 pad-1)
+def conv_row_wgrad_supported(d) -> bool:
+    return bool(_lib.query("b200_conv_row_wgrad_supported", C.byref(d)))
+
+
+def conv_row_wgrad_workspace_bytes(d) -> int:
+    return int(_lib.query("b200_conv_row_wgrad_workspace_bytes", C.byref(d)))
+
+
+def conv_row_wgrad(d, src0, src1, dy, ws, dw, accumulate=False, db_zero=None):
+    """db_zero: bias gradient of a convolution feeding a train-mode BatchNorm (identically zero; written as such)."""
+    _lib.call("b200_conv_row_wgrad", C.byref(d), _pf(src0), _pf(src1), _pf(dy), _p(ws), ws.numel() * ws.element_size(),
+              _pf(dw), _pf(db_zero), int(accumulate), _st())
+
+
 # tcgen05 kernels (2D 3x3 stride-1 pad-1 forward / data gradient)
 def conv_umma_supported(d, for_dgrad=False) -> bool:
     return bool(_lib.query("b200_conv_umma_supported", C.byref(d), int(for_dgrad)))

@@ -109,6 +109,18 @@ int b200_conv_umma2_fwd(const b200_conv_desc* d, const float* src0, const float*
 int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
                           int accumulate, cudaStream_t stream);
 
+/* Row-ring tcgen05 weight gradient of the 2D 3x3 stride-1 pad-1 convolutions (backward of code/networks/unet.py:37,41;
+ * csrc/conv_row_wgrad.cu): image rows staged by TMA, the nine taps expressed as descriptor shifts, TF32 products with fp32
+ * accumulation in TMEM, row-range partials reduced in fixed order.  Channel counts: c0, c1, cout multiples of 32
+ * (cout <= 128 or a multiple of 128), or the 16-channel family (c0 = 16, c1 in {0, 16}, cout = 16, even width).
+ * dw in the framework layout [cout][c0+c1][3][3].  The bias gradient is not summed here (b200_colsum); db_zero, if not
+ * NULL, is the bias gradient of a convolution that feeds a TRAIN-mode BatchNorm: it is identically zero there (the
+ * BatchNorm backward removes the per-channel mean of its gradient) and is written as such (left alone when accumulating). */
+int b200_conv_row_wgrad_supported(const b200_conv_desc* d);
+long long b200_conv_row_wgrad_workspace_bytes(const b200_conv_desc* d);
+int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
+                        long long workspace_bytes, float* dw, float* db_zero, int accumulate, cudaStream_t stream);
+
 /* One-launch weight packing for a whole network.  jobs_dev: DEVICE array of njobs x 8 int64:
  * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma), mode (generic: B200_PACK_*; tile/umma: dgrad flag), O, I, T, total]. */
 int b200_conv_pack_batch(const long long* jobs_dev, int njobs, int blocks_per_job, cudaStream_t stream);

@@ -236,6 +236,26 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
     conv_wgrad(d, src0, src1, dy, ws, dw, db, accumulate)
 
 
+# ------------------------------------------------------------------ row-ring tcgen05 weight gradient
+def conv_row_wgrad_supported(d):
+    if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
+        return False
+    c0, c1, co = d.c0, d.c1, d.cout
+    if c0 > 0 and c0 % 32 == 0 and c1 % 32 == 0 and co % 32 == 0 and (co <= 128 or co % 128 == 0):
+        return d.iw + 2 <= 256
+    return c0 == 16 and c1 in (0, 16) and co == 16 and d.iw % 2 == 0 and d.iw // 2 + 2 <= 256
+
+
+def conv_row_wgrad_workspace_bytes(d):
+    return 64
+
+
+def conv_row_wgrad(d, src0, src1, dy, ws, dw, accumulate=False, db_zero=None):
+    conv_wgrad(d, src0, src1, dy, ws, dw, None, accumulate)
+    if db_zero is not None and not accumulate:
+        db_zero.zero_()
+
+
 # ------------------------------------------------------------------ tcgen05 kernels (own weight packing)
 def conv_umma_supported(d, for_dgrad=False):
     ok = (d.stride == 1 and d.kd == 1 and d.kh == 3 and d.kw == 3 and d.pd == 0 and d.ph == 1 and d.pw == 1 and
