@@ -84,32 +84,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0 && !(p.debug & 2)) {
-            tma_prefetch_desc(&tx0); tma_prefetch_desc(&tx1); tma_prefetch_desc(&tdy);
-            int xq = 0, dq = 0;
+        // whole warp in warp-uniform control flow, one elected lane issues (see the MMA issuer below)
+        if (!(p.debug & 2)) {
+            const bool leader = elect_one();
+            if (leader) { tma_prefetch_desc(&tx0); tma_prefetch_desc(&tx1); tma_prefetch_desc(&tdy); }
+            int xs = 0, xph = 0, xcnt = 0;            // x ring slot / parity of the fill being overwritten / fills so far
+            int ds = 0, dph = 0, dcnt = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int g = item % p.G, t = item / p.G, mb = t % p.MB, s = t / p.MB;
                 const int r0 = (int)((long long)s * R / p.S), r1 = (int)((long long)(s + 1) * R / p.S);
-                const CUtensorMap* tx = g < p.G0 ? &tx0 : &tx1;
-                const int gl = g < p.G0 ? g : g - p.G0;
+                const bool second = g >= p.G0;
+                const int gl = second ? g - p.G0 : g;
+                int n = r0 / p.H, X = r0 - n * p.H;
                 for (int r = r0; r < r1; ++r) {
-                    const int n = r / p.H, X = r - n * p.H;
                     const bool new_seg = (r == r0) || (X == 0);
                     const int first = new_seg ? X - 1 : X + 1, cnt = new_seg ? 3 : 1;
-                    for (int k = 0; k < cnt; ++k, ++dq) {
-                        const int slot = dq % p.RD;
-                        if (dq >= p.RD) mbar_wait(smem_u32(&empty_d[slot]), ((dq / p.RD) - 1) & 1);
-                        const uint32_t fb = smem_u32(&full_d[slot]);
-                        mbar_expect_tx(fb, (uint32_t)p.ds_bytes * (slot < 2 ? 2u : 1u));
-                        tma_load_5d(d_base + (uint32_t)slot * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
-                        if (slot < 2) tma_load_5d(d_base + (uint32_t)(p.RD + slot) * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
+                    for (int k = 0; k < cnt; ++k, ++dcnt) {
+                        if (dcnt >= p.RD) mbar_wait(smem_u32(&empty_d[ds]), dph ^ 1);
+                        const uint32_t fb = smem_u32(&full_d[ds]);
+                        if (leader) {
+                            mbar_expect_tx(fb, (uint32_t)p.ds_bytes * (ds < 2 ? 2u : 1u));
+                            tma_load_5d(d_base + (uint32_t)ds * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
+                            if (ds < 2) tma_load_5d(d_base + (uint32_t)(p.RD + ds) * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
+                        }
+                        __syncwarp();
+                        if (++ds == p.RD) { ds = 0; dph ^= 1; }
                     }
-                    const int slot = xq % p.RX;
-                    if (xq >= p.RX) mbar_wait(smem_u32(&empty_x[slot]), ((xq / p.RX) - 1) & 1);
-                    const uint32_t fb = smem_u32(&full_x[slot]);
-                    mbar_expect_tx(fb, (uint32_t)p.xs_bytes);
-                    tma_load_5d(x_base + (uint32_t)slot * p.xs_bytes, tx, 0, -1, gl, X, n, fb);
-                    ++xq;
+                    if (xcnt >= p.RX) mbar_wait(smem_u32(&empty_x[xs]), xph ^ 1);
+                    const uint32_t fb = smem_u32(&full_x[xs]);
+                    if (leader) {
+                        mbar_expect_tx(fb, (uint32_t)p.xs_bytes);
+                        if (second) tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx1, 0, -1, gl, X, n, fb);
+                        else tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx0, 0, -1, gl, X, n, fb);
+                    }
+                    __syncwarp();
+                    ++xcnt;
+                    if (++xs == p.RX) { xs = 0; xph ^= 1; }
+                    if (++X == p.H) { X = 0; ++n; }
                 }
             }
         }

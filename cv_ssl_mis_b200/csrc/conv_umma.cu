@@ -526,9 +526,20 @@ __global__ void __launch_bounds__(U2_THREADS) conv_umma2_kernel(const Umma2P p) 
         }
     } else if (warp == 4) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers; under
+        // `if (lane == 0)` every tcgen05.mma is wrapped in a uniformisation loop) and ONE elected lane issues.  The
+        // descriptors of a stage are built once; a tap / k-step / row block only adds to their 14-bit address field
+        // (units of 16 B = one halo pixel of a 4-channel plane).  tools/umma_peak.cu: an N = 64 TF32 MMA retires every
+        // 48 cycles, the previous 40-instruction loop body issued one every ~250.
+        {
+            uint32_t leader_u;
+            asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(leader_u));
+            const bool leader = leader_u != 0;
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t a_ks = (uint64_t)((2 * plane_a) >> 4);          // second k-step: two 4-channel planes further
+            const uint64_t row1 = (uint64_t)p.HW, row2 = (uint64_t)(2 * p.HW);
             int it = 0, tl = 0;
+            int s = 0, fph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
                 const int as = tl & 1;
                 // the epilogue must have drained this accumulator buffer (used two tiles ago)
@@ -536,28 +547,34 @@ __global__ void __launch_bounds__(U2_THREADS) conv_umma2_kernel(const Umma2P p) 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t dcol = tmem_base + as * acc_cols;
                 for (int chunk = 0; chunk < nchunks; ++chunk, ++it) {
-                    const int s = it % S;
-                    mbar_wait(smem_u32(&full_bar[s]), (it / S) & 1);
+                    mbar_wait(smem_u32(&full_bar[s]), fph);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) data -> tensor core
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sh = smem0 + s * stage_bytes, sw = sh + halo_bytes;
+                    const uint64_t ad0 = umma_desc(sh, plane_a, 128);
+                    const uint64_t bd0 = umma_desc(sw, BN * 16, 128);
+                    const uint32_t first = chunk == 0 ? 0u : 1u;
 #pragma unroll 1
                     for (int b = 0; b < p.MB; ++b) {
-#pragma unroll 1
+                        const uint64_t ab = ad0 + (uint64_t)(b * 128);
+                        const uint32_t d = dcol + b * BN;
+#pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const int kh = tap / 3, kw = tap % 3;
-                            const uint32_t a0 = sh + (uint32_t)(b * 128 + kh * p.HW + kw) * 16;
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t ad = umma_desc(a0 + 2 * ks * plane_a, plane_a, 128);
-                                const uint64_t bd = umma_desc(sw + (uint32_t)((tap * 4 + 2 * ks) * BN) * 16, BN * 16, 128);
-                                umma_tf32(dcol + b * BN, ad, bd, idesc, (chunk | tap | ks) != 0);
+                            const uint64_t at = ab + (kh == 0 ? 0 : (kh == 1 ? row1 : row2)) + (uint64_t)kw;
+                            const uint64_t bt = bd0 + (uint64_t)(tap * 4 * BN);
+                            if (leader) {
+                                umma_tf32(d, at, bt, idesc, tap == 0 ? first : 1u);
+                                umma_tf32(d, at + a_ks, bt + (uint64_t)(2 * BN), idesc, 1u);
                             }
                         }
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));     // frees the stage when these MMAs retire
+                    if (leader) umma_commit(smem_u32(&empty_bar[s]));     // frees the stage when these MMAs retire
+                    __syncwarp();
+                    if (++s == S) { s = 0; fph ^= 1; }
                 }
-                umma_commit(smem_u32(&acc_full[as]));          // accumulator of this tile complete
+                if (leader) umma_commit(smem_u32(&acc_full[as]));          // accumulator of this tile complete
+                __syncwarp();
             }
         }
     } else {

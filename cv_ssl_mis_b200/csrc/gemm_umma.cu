@@ -160,8 +160,12 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int it = 0;
+        // whole warp in warp-uniform control flow, one elected lane issues (see the MMA issuer below)
+        {
+            uint32_t leader_u;
+            asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(leader_u));
+            const bool leader = leader_u != 0;
+            int s = 0, eph = 0, it = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int nt = item % p.n_tiles, mt = (item / p.n_tiles) % p.m_tiles, sp = item / (p.n_tiles * p.m_tiles);
                 const int kb0 = (int)((long long)sp * p.kb_total / p.splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / p.splits);
@@ -173,40 +177,50 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
                 const uint32_t tx = ((p.a_mn && !p.a_3d) ? a_boxes * 4096u : (uint32_t)A_BYTES) +
                                     ((p.b_mn && !p.b_3d) ? b_boxes * 4096u : (uint32_t)(BN * BK * 4));
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % S;
-                    if (it >= S) mbar_wait(smem_u32(&empty_bar[s]), ((it / S) - 1) & 1);
+                    if (it >= S) mbar_wait(smem_u32(&empty_bar[s]), eph ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     const uint32_t a_dst = smem0 + s * stage_bytes, b_dst = a_dst + A_BYTES;
                     const int k = kb * BK;
-                    mbar_expect_tx(fb, tx);
-                    if (!p.a_mn) {
-                        if (k < p.a_k0) tma_load_2d(a_dst, &ta0, k, m0, fb);
-                        else tma_load_2d(a_dst, &ta1, k - p.a_k0, m0, fb);
-                    } else if (p.a_3d) {
-                        tma_load_3d(a_dst, &ta0, 0, k, m0 >> 5, fb);
-                    } else {
-                        for (int j = 0; j < a_boxes; ++j) tma_load_2d(a_dst + j * 4096, &ta0, m0 + 32 * j, k, fb);
-                    }
-                    if (!p.b_mn) {
-                        tma_load_2d(b_dst, &tb0, k, n0, fb);
-                    } else if (p.b_3d) {
-                        tma_load_3d(b_dst, &tb0, 0, k, n0 >> 5, fb);
-                    } else {
-                        for (int j = 0; j < b_boxes; ++j) {
-                            const int col = n0 + 32 * j;
-                            if (col < p.b_n0) tma_load_2d(b_dst + j * 4096, &tb0, col, k, fb);
-                            else tma_load_2d(b_dst + j * 4096, &tb1, col - p.b_n0, k, fb);
+                    if (leader) {
+                        mbar_expect_tx(fb, tx);
+                        if (!p.a_mn) {
+                            if (k < p.a_k0) tma_load_2d(a_dst, &ta0, k, m0, fb);
+                            else tma_load_2d(a_dst, &ta1, k - p.a_k0, m0, fb);
+                        } else if (p.a_3d) {
+                            tma_load_3d(a_dst, &ta0, 0, k, m0 >> 5, fb);
+                        } else {
+                            for (int j = 0; j < a_boxes; ++j) tma_load_2d(a_dst + j * 4096, &ta0, m0 + 32 * j, k, fb);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_2d(b_dst, &tb0, k, n0, fb);
+                        } else if (p.b_3d) {
+                            tma_load_3d(b_dst, &tb0, 0, k, n0 >> 5, fb);
+                        } else {
+                            for (int j = 0; j < b_boxes; ++j) {
+                                const int col = n0 + 32 * j;
+                                if (col < p.b_n0) tma_load_2d(b_dst + j * 4096, &tb0, col, k, fb);
+                                else tma_load_2d(b_dst + j * 4096, &tb1, col - p.b_n0, k, fb);
+                            }
                         }
                     }
+                    __syncwarp();
+                    if (++s == S) { s = 0; eph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers; under
+        // `if (lane == 0)` every tcgen05.mma is wrapped in a uniformisation loop) and ONE elected lane issues.  The two
+        // descriptors of a stage are built once, a k-step adds 32 B (K-major) or 1024 B (MN-major) to the address field.
+        {
+            uint32_t leader_u;
+            asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(leader_u));
+            const bool leader = leader_u != 0;
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-            int it = 0, tl = 0;
+            const uint64_t a_step = p.a_mn ? 64 : 2, b_step = p.b_mn ? 64 : 2;       // in units of 16 B
+            int tl = 0, s = 0, fph = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
                 const int sp = item / (p.n_tiles * p.m_tiles);
                 const int kb0 = (int)((long long)sp * p.kb_total / p.splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / p.splits);
@@ -214,23 +228,29 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
                 if (tl >= 2) mbar_wait(smem_u32(&acc_empty[as]), ((tl >> 1) - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t dcol = tmem_base + as * BN;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % S;
-                    mbar_wait(smem_u32(&full_bar[s]), (it / S) & 1);
+                uint32_t acc = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[s]), fph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_base = smem0 + s * stage_bytes, b_base = a_base + A_BYTES;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart (SBO); a k-step is 32 bytes along the row.
-                        // MN-major: a 32-column box is [32 k][128 B]; 4 k-rows = one 512-byte atom (SBO), the next
-                        // 32 columns are the next 4096-byte box (LBO); a k-step (8 k-rows) is 1024 bytes.
-                        const uint64_t ad = p.a_mn ? smem_desc(a_base + ks * 1024, 4096, 512, 1) : smem_desc(a_base + ks * 32, 16, 1024, 2);
-                        const uint64_t bd = p.b_mn ? smem_desc(b_base + ks * 1024, 4096, 512, 1) : smem_desc(b_base + ks * 32, 16, 1024, 2);
-                        umma_tf32(dcol, ad, bd, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+                    // K-major: 8 rows x 128 B swizzle atoms, 1024 B apart (SBO); a k-step is 32 bytes along the row.
+                    // MN-major: a 32-column box is [32 k][128 B]; 4 k-rows = one 512-byte atom (SBO), the next
+                    // 32 columns are the next 4096-byte box (LBO); a k-step (8 k-rows) is 1024 bytes.
+                    const uint64_t ad = p.a_mn ? smem_desc(a_base, 4096, 512, 1) : smem_desc(a_base, 16, 1024, 2);
+                    const uint64_t bd = p.b_mn ? smem_desc(b_base, 4096, 512, 1) : smem_desc(b_base, 16, 1024, 2);
+                    if (leader) {
+                        umma_tf32(dcol, ad, bd, idesc, acc);
+                        umma_tf32(dcol, ad + a_step, bd + b_step, idesc, 1u);
+                        umma_tf32(dcol, ad + 2 * a_step, bd + 2 * b_step, idesc, 1u);
+                        umma_tf32(dcol, ad + 3 * a_step, bd + 3 * b_step, idesc, 1u);
+                        umma_commit(smem_u32(&empty_bar[s]));
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));
+                    __syncwarp();
+                    acc = 1;
+                    if (++s == S) { s = 0; fph ^= 1; }
                 }
-                umma_commit(smem_u32(&acc_full[as]));
+                if (leader) umma_commit(smem_u32(&acc_full[as]));
+                __syncwarp();
             }
         }
     } else {
