@@ -69,6 +69,13 @@ SIGNATURES = {
     "b200_conv_row_wgrad_supported": (_I, [_D]),
     "b200_conv_row_wgrad_workspace_bytes": (_L, [_D]),
     "b200_conv_row_wgrad": (_I, [_D, _P, _P, _P, _P, _L, _P, _P, _I, _S]),
+    "b200_conv_row_supported": (_I, [_D, _I]),
+    "b200_conv_row_packed_floats": (_L, [_I, _I]),
+    "b200_conv_row_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_conv_row_stats_blocks": (_L, [_D]),
+    "b200_conv_row_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
+    "b200_conv_row_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_bn_finalize": (_I, [_P, _I, _L, _I, _P, _P, _F, _F, _P, _P, _P, _S]),
     "b200_conv_pack_batch": (_I, [_P, _I, _I, _S]),
     "b200_conv_c1_supported": (_I, [_D]),
     "b200_conv_c1_fwd": (_I, [_D, _P, _P, _P, _P, _S]),
@@ -127,7 +134,7 @@ SIGNATURES = {
 
 # entry points whose int return value is NOT a status code
 _NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported",
-               "b200_conv_c1_supported", "b200_linear_supported", "b200_conv_row_wgrad_supported"}
+               "b200_conv_c1_supported", "b200_linear_supported", "b200_conv_row_wgrad_supported", "b200_conv_row_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

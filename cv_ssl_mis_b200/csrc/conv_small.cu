@@ -7,7 +7,7 @@
 #include "../../include/b200ssl.h"
 
 // ---------------------------------------------------------------------------------------------------- batched packing
-// job layout (8 x int64): [0] src ptr [1] dst ptr [2] kind (0 generic, 1 tile, 2 umma) [3] mode (generic pack mode or
+// job layout (8 x int64): [0] src ptr [1] dst ptr [2] kind (0 generic, 1 tile, 2 umma, 3 row) [3] mode (generic pack mode or
 // dgrad flag) [4] O [5] I [6] T [7] total output floats
 __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind, int mode, int O, int I, int T, int idx) {
     if (kind == 0) {
@@ -31,8 +31,18 @@ __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind
             default: { int tap = r / O, o = r % O; return w[((size_t)c * O + o) * T + tap]; }
         }
     }
-    const int dgrad = mode;
+    const int dgrad = mode & 1;
     const int rows = dgrad ? O : I, cols = dgrad ? I : O;
+    if (kind == 3) {            // row-ring kernels: [tap][plane][col][k in cpp] (same layout as conv_row_pack_kernel); mode bit 1: cpp = 16
+        const int cpp = (mode & 2) ? 16 : 32, np = rows / cpp;
+        const int k = idx % cpp;
+        int r = idx / cpp;
+        const int col = r % cols; r /= cols;
+        const int pl = r % np, tap = r / np;
+        const int row = pl * cpp + k;
+        const float v = dgrad ? w[((size_t)row * I + col) * T + (T - 1 - tap)] : w[((size_t)col * I + row) * T + tap];
+        return __uint_as_float(f2tf32(v));
+    }
     const int colsP = (cols + 15) / 16 * 16;
     int row, col, tap;
     if (kind == 1) {            // [chunk][tap][colsP][16]

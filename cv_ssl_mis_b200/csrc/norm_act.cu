@@ -308,6 +308,15 @@ B200_API int b200_bn_stats_fwd(const float* y, long long M, int C, const float* 
     return B200_OK;
 }
 
+B200_API int b200_bn_finalize(const double* partials, int nblocks, long long M, int C, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, float* state, cudaStream_t st) {
+    if (int rc = check_bn(M, C, "bn_finalize")) return rc;
+    B200_REQUIRE(partials && state && nblocks > 0, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<C, 256, 0, st>>>(partials, nblocks, M, C, gamma, beta, eps, momentum, running_mean, running_var, state);
+    B200_CHECK_LAUNCH("bn_finalize");
+    return B200_OK;
+}
+
 B200_API int b200_bn_eval_state(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
                                 const float* running_var, float* state, cudaStream_t st) {
     B200_REQUIRE(C > 0 && running_mean && running_var && state, "bn_eval_state: bad arguments");

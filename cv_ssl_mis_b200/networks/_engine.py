@@ -127,6 +127,7 @@ class ConvLayer:
                      and self.cout >= 32 and self.cin >= 32 and ops.linear_supported(self.M, self.cout, c0, c1))
         if self.gemm:
             self.umma_fwd = self.umma_dgrad = self.c1 = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = self.row_wgrad = False
+            self.row_fwd = self.row_dgrad = False
             self.wp_fwd = self.wp_bwd = None
             if need_grad:
                 rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(self.M, self.cout, self.cin),
@@ -137,9 +138,14 @@ class ConvLayer:
         # measured (tools/bench_conv.py): with fp32 operands the UMMA is bound by its shared-memory operand reads,
         # 4(M+N)/(MN) bytes per MAC, so it only beats mma.sync when both channel counts are >= 32
         wide = self.cout >= 32 and self.cin >= 32
-        self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False)
+        # wide images (W % 128 == 0: the 16 / 32-channel levels): row-ring tcgen05 kernel, weights resident in shared
+        # memory, BatchNorm statistics taken in the epilogue.  B200_CONV_ROW=0 keeps the older kernels for A/B runs.
+        want_row = is_conv and not rt.exact and os.environ.get("B200_CONV_ROW", "1") != "0"
+        self.row_fwd = ops.conv_row_supported(self.desc, False) if (want_row and not self.out_nchw) else 0     # plane width or 0
+        self.row_dgrad = ops.conv_row_supported(self.desc, True) if (want_row and need_grad) else 0
+        self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False) and not self.row_fwd
                          and (self.out_nchw or self.cout % 4 == 0))
-        self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True)
+        self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True) and not self.row_dgrad
         self.c1 = is_conv and not rt.exact and ops.conv_c1_supported(self.desc)       # first layer: FFMA kernels
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
@@ -148,7 +154,11 @@ class ConvLayer:
         self.row_wgrad = (is_conv and not rt.exact and need_grad and os.environ.get("B200_WGRAD", "row") == "row"
                           and ops.conv_row_wgrad_supported(self.desc))
         fwd_mode = PACK_CONV_FWD if is_conv else PACK_DECONV_FWD
-        nfwd = (ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
+        if self.row_fwd and self.has_act:
+            self.stats_blocks = ops.conv_row_stats_blocks(self.desc)
+            rt.need_scratch(self.stats_blocks * 2 * self.cout * 8)
+        nfwd = (ops.conv_row_packed_floats(O, I) if self.row_fwd else
+                ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
                 ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
         self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
         self.wp_bwd = None
@@ -164,7 +174,8 @@ class ConvLayer:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            nbwd = (ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
+            nbwd = (ops.conv_row_packed_floats(O, I) if self.row_dgrad else
+                    ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
                     ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
         return self
@@ -176,14 +187,18 @@ class ConvLayer:
         if self.gemm:
             return jobs
         if not self.c1:
-            if self.umma_fwd:
+            if self.row_fwd:
+                jobs.append((w, self.wp_fwd, 3, 0 | (2 if self.row_fwd == 16 else 0), O, I, T))
+            elif self.umma_fwd:
                 jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
             elif self.tile_fwd:
                 jobs.append((w, self.wp_fwd, 1, 0, O, I, T))
             else:
                 jobs.append((w, self.wp_fwd, 0, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, T))
         if need_dgrad and self.wp_bwd is not None:
-            if self.umma_dgrad:
+            if self.row_dgrad:
+                jobs.append((w, self.wp_bwd, 3, 1 | (2 if self.row_dgrad == 16 else 0), O, I, T))
+            elif self.umma_dgrad:
                 jobs.append((w, self.wp_bwd, 2, 1, O, I, T))
             elif self.tile_dgrad:
                 jobs.append((w, self.wp_bwd, 1, 1, O, I, T))
@@ -195,14 +210,20 @@ class ConvLayer:
         O, I = self.cout, self.cin
         if self.gemm:
             return
-        if self.umma_fwd:
+        if self.c1:
+            pass
+        elif self.row_fwd:
+            ops.conv_row_pack_weights(self.conv.weight, self.wp_fwd, False, self.row_fwd, O, I)
+        elif self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
             ops.conv_tile_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         else:
             ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
         if need_dgrad and self.wp_bwd is not None:
-            if self.umma_dgrad:
+            if self.row_dgrad:
+                ops.conv_row_pack_weights(self.conv.weight, self.wp_bwd, True, self.row_dgrad, O, I)
+            elif self.umma_dgrad:
                 ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.tile_dgrad:
                 ops.conv_tile_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
@@ -217,6 +238,9 @@ class ConvLayer:
             ops.linear_fwd(src0, src1, self.conv.weight.view(self.cout, self.cin), self.conv.bias, self.y, self.M, self.cout)
         elif self.c1:
             ops.conv_c1_fwd(self.desc, src0, self.conv.weight, self.conv.bias, self.y)
+        elif self.row_fwd:
+            fused_stats = self.has_act and train
+            ops.conv_row_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, rt.scratch if fused_stats else None)
         elif self.umma_fwd:
             ops.conv_umma_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
         elif self.tile_fwd:
@@ -228,7 +252,13 @@ class ConvLayer:
         if not self.has_act:
             return self.y
         bn = self.bn
-        if train:
+        if train and self.row_fwd:
+            # the statistics pass happened in the convolution's epilogue: only the per-channel finalize is left
+            ops.bn_finalize(rt.scratch, self.stats_blocks, self.M, self.cout, bn.weight, bn.bias, bn.eps, bn.momentum,
+                            bn.running_mean, bn.running_var, self.state)
+            ops.bn_act_fwd(self.y, self.state, self.a, self.M, self.cout, self.slope, self.p_drop, self.drop_mode,
+                           rt.seed, rt.seed_off, self.rng_stream, self.spatial)
+        elif train:
             ops.bn_stats_fwd(self.y, self.M, self.cout, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean,
                              bn.running_var, self.state, rt.scratch)
             ops.bn_act_fwd(self.y, self.state, self.a, self.M, self.cout, self.slope, self.p_drop, self.drop_mode,
@@ -277,7 +307,9 @@ class ConvLayer:
                 else:
                     ops.conv_wgrad(self.desc, src0, src1, dy, ws, conv.weight.grad, bias_grad, accumulate_w, rt.exact)
             if dx0 is not None:
-                if self.umma_dgrad:
+                if self.row_dgrad:
+                    ops.conv_row_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
+                elif self.umma_dgrad:
                     ops.conv_umma_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
                 elif self.tile_dgrad:
                     ops.conv_tile_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)

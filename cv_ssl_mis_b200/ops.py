@@ -127,6 +127,39 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
               _pf(dw), _pf(db), int(accumulate), _st())
 
 
+# row-ring tcgen05 forward / data gradient (wide-image 2D 3x3 stride-1 pad-1, weights resident, BN statistics fused)
+def conv_row_supported(d, dgrad=False) -> int:
+    """Plane width (32 or 16 channels) of the reduction operand, or 0 when the row kernels do not serve this convolution."""
+    return int(_lib.query("b200_conv_row_supported", C.byref(d), int(dgrad)))
+
+
+def conv_row_packed_floats(O, I) -> int:
+    return int(_lib.query("b200_conv_row_packed_floats", O, I))
+
+
+def conv_row_pack_weights(w, out, dgrad, cpp, O, I):
+    _lib.call("b200_conv_row_pack_weights", _pf(w), _pf(out), int(dgrad), int(cpp), O, I, _st())
+
+
+def conv_row_stats_blocks(d) -> int:
+    return int(_lib.query("b200_conv_row_stats_blocks", C.byref(d)))
+
+
+def conv_row_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
+    """stats_part: workspace for conv_row_stats_blocks(d) x 2 x cout fp64 partial (sum, sum of squares) of dst, or None."""
+    _lib.call("b200_conv_row_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wpk), _pf(bias), _pf(dst), _p(stats_part), _st())
+
+
+def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
+    _lib.call("b200_conv_row_dgrad", C.byref(d), _pf(dy), _pf(wpk_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
+
+
+def bn_finalize(part, nblocks, M, C_, gamma, beta, eps, momentum, running_mean, running_var, state):
+    """second half of bn_stats_fwd on [nblocks][2][C] fp64 partials (e.g. from conv_row_fwd)"""
+    _lib.call("b200_bn_finalize", _p(part), int(nblocks), int(M), int(C_), _pf(gamma), _pf(beta), float(eps), float(momentum),
+              _pf(running_mean), _pf(running_var), _pf(state), _st())
+
+
 # row-ring tcgen05 weight gradient (2D 3x3 stride-1 pad-1)
 def conv_row_wgrad_supported(d) -> bool:
     return bool(_lib.query("b200_conv_row_wgrad_supported", C.byref(d)))

@@ -121,8 +121,24 @@ long long b200_conv_row_wgrad_workspace_bytes(const b200_conv_desc* d);
 int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
                         long long workspace_bytes, float* dw, float* db_zero, int accumulate, cudaStream_t stream);
 
+/* Row-ring tcgen05 forward / data gradient of the wide-image 2D 3x3 stride-1 pad-1 convolutions (csrc/conv_row.cu;
+ * code/networks/unet.py:37,41 at the 256^2 / 128^2 levels): width a multiple of 128, input channels a multiple of 32 or
+ * 16 (+16), 16 / 32 / 64 GEMM columns; weights resident in shared memory, image rows staged once by TMA.
+ * b200_conv_row_fwd can emit the per-channel (sum, sum of squares) of its output as b200_conv_row_stats_blocks(d) fp64
+ * partials [block][2][cout] for b200_bn_finalize -- the statistics pass of the following train-mode BatchNorm
+ * (code/networks/unet.py:38,42) without re-reading the output.  Packed weights: [tap][plane][column][k], TF32-rounded. */
+/* returns the plane width cpp (32 or 16 channels) of the reduction operand, or 0 when the convolution is not served */
+int b200_conv_row_supported(const b200_conv_desc* d, int dgrad);
+long long b200_conv_row_packed_floats(int O, int I);
+int b200_conv_row_pack_weights(const float* w, float* out, int dgrad, int cpp, int O, int I, cudaStream_t stream);
+long long b200_conv_row_stats_blocks(const b200_conv_desc* d);
+int b200_conv_row_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wpk, const float* bias,
+                      float* dst, double* stats_partials, cudaStream_t stream);
+int b200_conv_row_dgrad(const b200_conv_desc* d, const float* dy, const float* wpk_dgrad, float* dx0, float* dx1,
+                        int accumulate, cudaStream_t stream);
+
 /* One-launch weight packing for a whole network.  jobs_dev: DEVICE array of njobs x 8 int64:
- * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma), mode (generic: B200_PACK_*; tile/umma: dgrad flag), O, I, T, total]. */
+ * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma / 3 row), mode (generic: B200_PACK_*; tile/umma: dgrad flag; row: dgrad | 2 * (cpp == 16)), O, I, T, total]. */
 int b200_conv_pack_batch(const long long* jobs_dev, int njobs, int blocks_per_job, cudaStream_t stream);
 /* First layer of the CNNs (Cin = 1, 3x3 / 3x3x3 stride 1 pad 1, Cout in {16, 32}): HBM-bound FFMA kernels working on the
  * framework weight layout directly (code/networks/unet.py:37 with in_chns = 1, code/networks/vnet.py:152). */
@@ -141,6 +157,9 @@ long long b200_bn_workspace_bytes(long long M, int C);
 int b200_bn_stats_fwd(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
                       float* running_mean, float* running_var, float* state, void* workspace, long long workspace_bytes,
                       cudaStream_t stream);
+/* second half of b200_bn_stats_fwd: [nblocks][2][C] fp64 partial (sum, sum of squares) -> state + running statistics */
+int b200_bn_finalize(const double* partials, int nblocks, long long M, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* state, cudaStream_t stream);
 int b200_bn_eval_state(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
                        const float* running_var, float* state, cudaStream_t stream);
 int b200_bn_act_fwd(const float* y, const float* state, float* a, long long M, int C, float slope, float p_drop,

@@ -236,6 +236,78 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
     conv_wgrad(d, src0, src1, dy, ws, dw, db, accumulate)
 
 
+# ------------------------------------------------------------------ row-ring tcgen05 forward / data gradient
+def conv_row_supported(d, dgrad=False):
+    if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
+        return 0
+    if d.iw < 128 or d.iw % 128 or d.iw > 384:
+        return 0
+    a0, a1 = (d.cout, 0) if dgrad else (d.c0, d.c1)
+    n0, n1 = (d.c0, d.c1) if dgrad else (d.cout, 0)
+    if a0 > 0 and a0 % 32 == 0 and a1 % 32 == 0:
+        cpp, npl = 32, (a0 + a1) // 32
+    elif a0 == 16 and a1 in (0, 16):
+        cpp, npl = 16, (2 if a1 else 1)
+    else:
+        return 0
+    ncols = n0 + n1
+    if ncols not in (16, 32, 64) or (n1 != 0 and n1 != n0):
+        return 0
+    G = 32 if n0 >= 32 else 16
+    if n0 % G:
+        return 0
+    P = (d.iw + 2 + 7) // 8 * 8
+    if P > 256 and (a0 > cpp or a1 > cpp):
+        return 0
+    slot, wb, stage = npl * P * cpp * 4, 9 * npl * ncols * cpp * 4, 2 * (ncols // G) * 128 * G * 4
+    return cpp if 1024 + (wb + 1023) // 1024 * 1024 + 4 * slot + 1024 + stage <= 216 * 1024 else 0
+
+
+def conv_row_packed_floats(O, I):
+    return 9 * O * I
+
+
+def conv_row_pack_weights(w, out, dgrad, cpp, O, I):
+    W = w.detach().reshape(O, I, 9)
+    if dgrad:      # out[tap][plane][i][k] = W[plane*cpp+k][i][8-tap]
+        m, rows = W.flip(2).permute(2, 1, 0), O        # [tap][i][o]
+    else:          # out[tap][plane][o][k] = W[o][plane*cpp+k][tap]
+        m, rows = W.permute(2, 0, 1), I                # [tap][o][i]
+    cols = m.shape[1]
+    out.copy_(m.reshape(9, cols, rows // cpp, cpp).permute(0, 2, 1, 3).reshape(-1))
+
+
+def _row_unpack(wpk, dgrad, cpp, O, I):
+    rows, cols = (O, I) if dgrad else (I, O)
+    m = wpk.reshape(9, rows // cpp, cols, cpp).permute(0, 2, 1, 3).reshape(9, cols, rows)
+    if dgrad:
+        return m.permute(2, 1, 0).flip(2)              # [o][i][tap]
+    return m.permute(1, 2, 0)                          # [o][i][tap]
+
+
+def conv_row_stats_blocks(d):
+    return min(148, d.n * d.ih)
+
+
+def conv_row_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
+    W = _row_unpack(wpk, False, conv_row_supported(d, False), d.cout, d.c0 + d.c1).reshape(d.cout, d.c0 + d.c1, 1, 3, 3)
+    y = _ncdhw_to_cl(F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))).reshape(dst.shape)
+    dst.copy_(y)
+    if stats_part is not None:
+        nb = conv_row_stats_blocks(d)
+        part = torch.zeros(nb, 2, d.cout, dtype=torch.float64)
+        part[0, 0], part[0, 1] = y.double().sum(0), (y.double() ** 2).sum(0)
+        stats_part.view(torch.float64)[:part.numel()].copy_(part.reshape(-1))
+
+
+def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
+    cin = d.c0 + d.c1
+    W = _row_unpack(wpk_dgrad, True, conv_row_supported(d, True), d.cout, cin).reshape(d.cout, cin, 1, 3, 3)
+    g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
+    dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
+    _split_store(dx, d, dx0, dx1, accumulate)
+
+
 # ------------------------------------------------------------------ row-ring tcgen05 weight gradient
 def conv_row_wgrad_supported(d):
     if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
@@ -297,6 +369,8 @@ def conv_pack_batch(jobs_dev, njobs, blocks_per_job=16, jobs_py=None):
             conv_pack_weights(w, out, mode, O, I, T)
         elif kind == 1:
             conv_tile_pack_weights(w, out, bool(mode), O, I, T)
+        elif kind == 3:
+            conv_row_pack_weights(w, out, bool(mode & 1), 16 if mode & 2 else 32, O, I)
         else:
             conv_umma_pack_weights(w, out, bool(mode), O, I, T)
 
@@ -328,6 +402,21 @@ def bn_stats_fwd(y, M, C, gamma, beta, eps, momentum, running_mean, running_var,
     v = y.reshape(M, C).double()
     mean = v.mean(0)
     var = v.var(0, unbiased=False)
+    invstd = (1.0 / torch.sqrt(var + eps)).float()
+    mean = mean.float()
+    st = state.view(4, C)
+    st[0], st[1] = mean, invstd
+    st[2] = gamma.detach() * invstd
+    st[3] = beta.detach() - mean * gamma.detach() * invstd
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mean)
+        running_var.mul_(1 - momentum).add_(momentum * (var * M / max(M - 1, 1)).float())
+
+
+def bn_finalize(part, nblocks, M, C, gamma, beta, eps, momentum, running_mean, running_var, state):
+    pt = part.view(torch.float64)[:nblocks * 2 * C].reshape(nblocks, 2, C).sum(0)
+    mean = pt[0] / M
+    var = (pt[1] / M - mean * mean).clamp_min(0)
     invstd = (1.0 / torch.sqrt(var + eps)).float()
     mean = mean.float()
     st = state.view(4, C)

@@ -1,0 +1,97 @@
+"""Row-ring tcgen05 forward / data gradient (csrc/conv_row.cu) against torch fp64 convolutions on the CPU
+(code/networks/unet.py:37,41 and their backward at the 256^2 / 128^2 levels), including the fused BatchNorm statistics
+(code/networks/unet.py:38,42).  TF32 products with fp32 accumulation: tolerance = TF32 round-off of a 9*Cin long dot product."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cv_ssl_mis_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    # n, h, w, c0, c1, cout
+    (2, 5, 128, 32, 0, 32),
+    (1, 4, 128, 32, 32, 32),     # does not fit (two resident planes + 74 KB of weights): must report unsupported for fwd
+    (2, 3, 128, 16, 0, 32),
+    (2, 6, 256, 16, 0, 16),
+    (1, 7, 256, 16, 16, 16),
+    (3, 2, 128, 32, 0, 16),
+    (1, 3, 384, 16, 0, 16),
+]
+
+
+def _mk(case, seed=0):
+    n, h, w, c0, c1, cout = case
+    g = torch.Generator().manual_seed(seed + sum(case))
+    M, cin = n * h * w, c0 + c1
+    x0 = torch.randn(M, c0, generator=g)
+    x1 = torch.randn(M, c1, generator=g) if c1 else None
+    wgt = torch.randn(cout, cin, 3, 3, generator=g) * (cin * 9) ** -0.5
+    bias = torch.randn(cout, generator=g)
+    dy = torch.randn(M, cout, generator=g)
+    return x0, x1, wgt, bias, dy
+
+
+def _nchw(t, n, h, w, c):
+    return t.view(n, h, w, c).permute(0, 3, 1, 2).double()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_row_fwd_and_stats(case):
+    n, h, w, c0, c1, cout = case
+    d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    if not ops.conv_row_supported(d, False):
+        assert case == CASES[1]
+        return
+    x0, x1, wgt, bias, _ = _mk(case)
+    M, cin = n * h * w, c0 + c1
+    wpk = torch.empty(ops.conv_row_packed_floats(cout, cin), device=DEV)
+    ops.conv_row_pack_weights(wgt.to(DEV), wpk, False, ops.conv_row_supported(d, False), cout, cin)
+    y = torch.full((M, cout), float("nan"), device=DEV)
+    nb = ops.conv_row_stats_blocks(d)
+    part = torch.full((nb * 2 * cout,), float("nan"), dtype=torch.float64, device=DEV)
+    ops.conv_row_fwd(d, x0.to(DEV), None if x1 is None else x1.to(DEV), wpk, bias.to(DEV), y, part)
+    torch.cuda.synchronize()
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    ref = F.conv2d(_nchw(x, n, h, w, cin), wgt.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(M, cout)
+    torch.testing.assert_close(y.cpu().double(), ref, rtol=2e-2, atol=5e-3)
+    # the fused statistics are the exact sums of the values that were stored
+    s = part.view(nb, 2, cout).sum(0).cpu()
+    yd = y.cpu().double()
+    torch.testing.assert_close(s[0], yd.sum(0), rtol=1e-6, atol=1e-6 * M)
+    torch.testing.assert_close(s[1], (yd * yd).sum(0), rtol=1e-6, atol=1e-6 * M)
+    # and b200_bn_finalize turns them into the BatchNorm state torch computes
+    gamma, beta = torch.rand(cout) + 0.5, torch.randn(cout)
+    rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    state = torch.empty(4 * cout, device=DEV)
+    ops.bn_finalize(part, nb, M, cout, gamma.to(DEV), beta.to(DEV), 1e-5, 0.1, rm, rv, state)
+    mean, var = yd.mean(0), yd.var(0, unbiased=False)
+    st = state.view(4, cout).cpu().double()
+    torch.testing.assert_close(st[0], mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(st[1], 1 / torch.sqrt(var + 1e-5), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rm.cpu().double(), 0.1 * mean, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_row_dgrad(case):
+    n, h, w, c0, c1, cout = case
+    d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    if not ops.conv_row_supported(d, True):
+        pytest.skip("data gradient of this shape is served by another kernel")
+    _, _, wgt, _, dy = _mk(case, 1)
+    M, cin = n * h * w, c0 + c1
+    wpk = torch.empty(ops.conv_row_packed_floats(cout, cin), device=DEV)
+    ops.conv_row_pack_weights(wgt.to(DEV), wpk, True, ops.conv_row_supported(d, True), cout, cin)
+    dx0 = torch.full((M, c0), float("nan"), device=DEV)
+    dx1 = torch.full((M, c1), float("nan"), device=DEV) if c1 else None
+    ops.conv_row_dgrad(d, dy.to(DEV), wpk, dx0, dx1)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(_nchw(dy, n, h, w, cout), wgt.double(), padding=1).permute(0, 2, 3, 1).reshape(M, cin)
+    got = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
+    torch.testing.assert_close(got.double(), ref, rtol=2e-2, atol=5e-3)
+    # accumulate: TMA reduce-add on top of the stored result
+    ops.conv_row_dgrad(d, dy.to(DEV), wpk, dx0, dx1, accumulate=True)
+    got2 = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
+    torch.testing.assert_close(got2, 2 * got, rtol=1e-6, atol=1e-6)

@@ -6,8 +6,9 @@ import torch
 from cv_ssl_mis_b200 import ops
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["umma2", "umma1", "tile"]
-SHAPES = [(24, 256, 256, 16, 0, 16), (24, 256, 256, 16, 16, 16), (24, 128, 128, 32, 0, 32), (24, 64, 64, 64, 0, 64),
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["row", "umma2", "tile"]
+SHAPES = [(24, 256, 256, 16, 0, 16), (24, 256, 256, 16, 16, 16), (24, 128, 128, 16, 0, 32), (24, 128, 128, 32, 0, 32),
+          (24, 128, 128, 32, 0, 64), (24, 128, 128, 32, 0, 16), (24, 64, 64, 64, 0, 64),
           (24, 32, 32, 128, 0, 128), (24, 16, 16, 256, 0, 256), (24, 32, 32, 128, 128, 128)]
 for (n, h, w, c0, c1, cout) in SHAPES:
     d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
@@ -21,7 +22,14 @@ for (n, h, w, c0, c1, cout) in SHAPES:
     byts = 4.0 * (M * cin + M * cout)
     line = f"{n}x{h}x{w} {cin:3d}->{cout:3d}: "
     for name in which:
-        if name.startswith("umma"):
+        if name == "row":
+            if not ops.conv_row_supported(d, False):
+                continue
+            wt = torch.empty(ops.conv_row_packed_floats(cout, cin), device="cuda")
+            ops.conv_row_pack_weights(wgt, wt, False, ops.conv_row_supported(d, False), cout, cin)
+            part = torch.empty(ops.conv_row_stats_blocks(d) * 2 * cout, dtype=torch.float64, device="cuda")
+            fn = lambda: ops.conv_row_fwd(d, x0, x1, wt, bias, y, part)
+        elif name.startswith("umma"):
             ops.UMMA_V2 = name == "umma2"
             wt = torch.empty(ops.conv_umma_packed_floats(False, cout, cin, 9), device="cuda")
             ops.conv_umma_pack_weights(wgt, wt, False, cout, cin, 9)
@@ -34,9 +42,14 @@ for (n, h, w, c0, c1, cout) in SHAPES:
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g = torch.cuda.CUDAGraph()                       # graph replay: no host launch gaps in the timing
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            fn()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3
