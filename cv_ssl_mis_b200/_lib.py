@@ -70,8 +70,8 @@ SIGNATURES = {
     "b200_conv_row_wgrad_workspace_bytes": (_L, [_D]),
     "b200_conv_row_wgrad": (_I, [_D, _P, _P, _P, _P, _L, _P, _P, _I, _S]),
     "b200_conv_row_supported": (_I, [_D, _I]),
-    "b200_conv_row_packed_floats": (_L, [_I, _I]),
-    "b200_conv_row_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
+    "b200_conv_row_packed_floats": (_L, [_D, _I]),
+    "b200_conv_row_pack_weights": (_I, [_D, _I, _P, _P, _S]),
     "b200_conv_row_stats_blocks": (_L, [_D]),
     "b200_conv_row_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
     "b200_conv_row_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),

@@ -19,7 +19,17 @@
 //              written once per CTA as fp64 partials for bn_finalize (deterministic).
 // The data gradient is the same kernel on dy with flipped / transposed packed weights and up to two destinations
 // (the two sources of a virtual concat).
+//
+// 16-channel tensors (the 256^2 level) run in PIXEL-PAIR mode: a 64-byte pixel makes a 64-byte TMA box row, and the TMA
+// unit moves one box row per ~7 cycles whatever its length (measured: 1.9 TB/s over the chip, for loads and stores alike).
+// Two neighbouring pixels x 16 channels are one 128-byte row instead; the GEMM then runs on pairs: M = 128 pairs (a whole
+// 256-pixel row), K = (pixel parity pb, cin), N = (pixel parity pa, cout), and the horizontal taps become three pair
+// shifts s with kw = 2 (s - 1) + pb - pa + 1 baked into expanded weights (conv_row_pack.cuh); the k-steps whose weight
+// block is all zero (half of them for s = 0 and s = 2) are skipped.  The accumulator row (pa, cout) IS the output pair
+// in memory, so the epilogue is that of a 32-channel layer.
 #include "umma_common.cuh"
+#include "conv_row_pack.cuh"
+#include <cstdlib>
 #include <cstring>
 #include "../../include/b200ssl.h"
 
@@ -32,7 +42,8 @@ constexpr int MAX_R = 8;
 constexpr int NACC = 4;
 
 struct RowP {
-    int N, H, W, P;              // images, rows, columns; pixels per staged row (multiple of 8, >= W + 2)
+    int N, H, W, P;              // images, rows, k-pixels per row (pixels, or pixel pairs in pair mode); k-pixels per staged row
+                                 // (multiple of 8, >= W + 2)
     int NP, NP0;                 // planes in total / served by the first source
     int P1;                      // pixels of the first box of a row (a second box brings P - P1 when P > 256)
     int Cout;                    // GEMM columns (16 / 32 / 64)
@@ -40,12 +51,15 @@ struct RowP {
     int R;                       // ring rows
     int plane_bytes, slot_bytes, w_bytes;
     int G, ngrp, grp0;           // channels per output staging group (16 / 32), groups, groups going to the first destination
+    int fold;                    // statistics: column groups that are the same channel (2 in pair mode)
+    int bias_mask;               // bias index = column & bias_mask
     const float* bias;
     double* stats;               // [gridDim.x][2][Cout] or null
     int accumulate;
+    int debug;                   // profiling only: 1 no statistics, 2 no store, 4 epilogue releases the accumulator and nothing else, 8 no MMAs
 };
 
-template <int CPP>
+template <int CPP, bool PAIR>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_constant__ CUtensorMap tx0a,
                                                                  const __grid_constant__ CUtensorMap tx0b,
                                                                  const __grid_constant__ CUtensorMap tx1a,
@@ -60,7 +74,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_r[MAX_R], empty_r[MAX_R], w_full, acc_full[NACC], acc_empty[NACC];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ double sred[8][2][64];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
         if (leader) {
             tma_prefetch_desc(&tx0a); tma_prefetch_desc(&tw); tma_prefetch_desc(&ty0);
             mbar_expect_tx(smem_u32(&w_full), (uint32_t)p.w_bytes);
-            for (int i = 0; i < 9 * p.NP; ++i)
+            for (int i = 0; i < (PAIR ? 6 : 9) * p.NP; ++i)
                 tma_load_2d(w_base + (uint32_t)i * p.Cout * RB, &tw, 0, i * p.Cout, smem_u32(&w_full));
         }
         __syncwarp();
@@ -153,16 +166,18 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     uint64_t ap = (kh == 0 ? a0 : (kh == 1 ? a1 : a2)) + boff;
-                    uint64_t wp = wd0 + (uint64_t)(3 * kh) * wtap16;
+                    uint64_t wp = wd0 + (uint64_t)((PAIR ? 2 : 3) * kh) * wtap16;
 #pragma unroll 1
                     for (int pl = 0; pl < p.NP; ++pl, ap += plane16, wp += wplane16) {
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
+                            // pair mode: shift -1 only meets the odd input pixel (k-steps 2, 3), shift +1 only the even one
+                            constexpr int KLO[3] = {PAIR ? 2 : 0, 0, 0}, KHI[3] = {KS, KS, PAIR ? 2 : KS};
 #pragma unroll
-                            for (int ks = 0; ks < KS; ++ks) {
-                                if (leader)
-                                    mma_tf32(d, ap + (uint64_t)(kw * (RB >> 4) + 2 * ks), wp + (uint64_t)kw * wtap16 + (uint64_t)(2 * ks),
-                                             idesc, acc);
+                            for (int ks = KLO[kw]; ks < KHI[kw]; ++ks) {
+                                if (leader && !(p.debug & 8))
+                                    mma_tf32(d, ap + (uint64_t)(kw * (RB >> 4) + 2 * ks),
+                                             wp + (uint64_t)(PAIR ? (kw == 1 ? 0 : 1) : kw) * wtap16 + (uint64_t)(2 * ks), idesc, acc);
                                 acc = 1;
                             }
                         }
@@ -197,6 +212,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Nc);
                 const uint32_t sbase = stg + (uint32_t)sb * stg_bytes;
+                if (p.debug & 4) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+                    if (++buf == NACC) { buf = 0; fph ^= 1; }
+                    continue;
+                }
                 // staging buffer sb was handed to the TMA unit two blocks ago: its reads must be done
                 if (et == 0 && nstore >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -210,12 +232,16 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                         : "r"(taddr + (uint32_t)c0));
                     tmem_ld_wait();
                     const int gi = c0 / G, cg0 = c0 % G;                   // staging group and first channel within it
-                    const uint32_t rowb = sbase + (uint32_t)gi * (128u * G * 4u) + (uint32_t)et * (uint32_t)(G * 4);
-                    const int f = G == 32 ? (et & 7) : ((et >> 1) & 3);    // swizzle phase of this row
+                    // staging rows are 128 bytes with the 128-byte TMA swizzle: one pixel of a 32-channel group, or a pixel
+                    // PAIR of a 16-channel destination (row = et >> 1, the odd pixel in the upper 64 bytes)
+                    const uint32_t gbase = sbase + (uint32_t)gi * (128u * G * 4u);
+                    const int srow = G == 32 ? et : (et >> 1), cofs = G == 32 ? 0 : (et & 1) * 4;
+                    const uint32_t rowb = gbase + (uint32_t)srow * 128u;
+                    const int f = srow & 7;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b4 = p.bias ? ldg4(p.bias + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int chunk = (cg0 >> 2) + j;
+                        const float4 b4 = p.bias ? ldg4(p.bias + ((c0 + 4 * j) & p.bias_mask)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int chunk = cofs + (cg0 >> 2) + j;
                         const uint32_t dst = rowb + (uint32_t)((chunk ^ f) * 16);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
                                      "f"(__uint_as_float(rg[4 * j]) + b4.x), "f"(__uint_as_float(rg[4 * j + 1]) + b4.y),
@@ -229,13 +255,14 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (et == 0) {
-                    const int pix0 = (n * p.H + h) * p.W + 128 * b;
+                if (et == 0 && !(p.debug & 2)) {
+                    // G = 32: box {32 channels, 128 k-pixels}; G = 16: box {one 128-byte pixel pair, 64 pairs}
+                    const int pix0 = G == 32 ? (n * p.H + h) * p.W + 128 * b : ((n * p.H + h) * p.W + 128 * b) >> 1;
                     for (int gi = 0; gi < p.ngrp; ++gi) {
                         const uint32_t src = sbase + (uint32_t)gi * (128u * G * 4u);
                         const bool first = gi < p.grp0;
                         const CUtensorMap* tm = first ? &ty0 : &ty1;
-                        const int c = (first ? gi : gi - p.grp0) * G;
+                        const int c = G == 32 ? (first ? gi : gi - p.grp0) * G : 0;
                         if (p.accumulate)
                             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                                          ::"l"(tm), "r"(src), "r"(c), "r"(pix0) : "memory");
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                     tma_commit_group();
                     ++nstore;
                 }
-                if (p.stats) {
+                if (p.stats && !(p.debug & 1)) {
                     // channel sc over rows [ssub * Nc, ssub * Nc + Nc) of the staged tile (nsub * Nc == 128)
                     const int gi = sc / G, cg = sc % G;
                     const uint32_t gb = sbase + (uint32_t)gi * (128u * G * 4u) + (uint32_t)((cg & 3) * 4);
@@ -254,9 +281,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
 #pragma unroll 4
                     for (int i = 0; i < Nc; ++i) {
                         const int row = ssub * Nc + i;
-                        const int f = G == 32 ? (row & 7) : ((row >> 1) & 3);
+                        const int srow = G == 32 ? row : (row >> 1), chunk = (G == 32 ? 0 : (row & 1) * 4) + (cg >> 2);
                         float v;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(gb + (uint32_t)row * (uint32_t)(G * 4) + (uint32_t)(((cg >> 2) ^ f) * 16)));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(gb + (uint32_t)srow * 128u + (uint32_t)((chunk ^ (srow & 7)) * 16)));
                         s1 += v;
                         s2 += v * v;
                     }
@@ -269,14 +296,20 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
             if (++h == p.H) { h = 0; ++n; }
         }
         if (p.stats) {
-            sred[ssub][0][sc] = d1;
-            sred[ssub][1][sc] = d2;
+            // cross-thread reduction in the (now idle) first staging buffer: [sub][2][64] doubles = 8 KB
+            if (et == 0) tma_wait_group_read0();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            double* sred = reinterpret_cast<double*>(smem_raw + (stg - smem_u32(smem_raw)));
+            sred[(ssub * 2 + 0) * 64 + sc] = d1;
+            sred[(ssub * 2 + 1) * 64 + sc] = d2;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < 2 * Nc) {
-                const int which = et / Nc, c = et % Nc;
+            const int Cr = Nc / p.fold;                          // real channels (pair mode: columns (pa, c) fold onto c)
+            if (et < 2 * Cr) {
+                const int which = et / Cr, c = et % Cr;
                 double s = 0.0;
-                for (int k = 0; k < nsub; ++k) s += sred[k][which][c];
-                p.stats[(size_t)blockIdx.x * 2 * Nc + which * Nc + c] = s;
+                for (int k = 0; k < nsub; ++k)
+                    for (int fo = 0; fo < p.fold; ++fo) s += sred[(k * 2 + which) * 64 + fo * Cr + c];
+                p.stats[(size_t)blockIdx.x * 2 * Cr + which * Cr + c] = s;
             }
         }
         if (et == 0) tma_wait_group0();
@@ -286,78 +319,81 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// packed weights for the row kernels: out[tap][plane][col][k in CPP]; forward: col = cout, k = cin; data gradient:
-// col = cin, k = cout and the taps flipped.  TF32-rounded (round to nearest; the tensor core truncates).
-__global__ void __launch_bounds__(256) conv_row_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int dgrad, int cpp,
-                                                            int O, int I, int total) {
-    const int rows = dgrad ? O : I, cols = dgrad ? I : O, np = rows / cpp;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int k = idx % cpp;
-        int r = idx / cpp;
-        const int col = r % cols; r /= cols;
-        const int pl = r % np, tap = r / np;
-        const int row = pl * cpp + k;
-        const float v = dgrad ? w[((size_t)row * I + col) * 9 + (8 - tap)] : w[((size_t)col * I + row) * 9 + tap];
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        out[idx] = __uint_as_float(u);
-    }
+__global__ void __launch_bounds__(256) conv_row_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int mode, int O, int I,
+                                                            int total) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+        out[idx] = row_pack_elem(w, mode, O, I, idx);
 }
 
 struct RGeo {
-    int cpp, NP, NP0, Ncols, G, ngrp, grp0, P, P1, nblk, R, plane, slot, wbytes, smem;
+    int cpp, pair, NP, NP0, Ncols, G, ngrp, grp0, fold, Wk, P, P1, nblk, R, plane, slot, wbytes, smem, mode;
 };
 
 // dgrad = 0: A = [src0|src1] (c0 + c1 channels), columns = cout.  dgrad = 1: A = dy (cout channels), columns = c0 + c1.
 bool rgeometry(const b200_conv_desc* d, int dgrad, RGeo& g) {
     if (d->id != 1 || d->kd != 1 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->ph != 1 || d->pw != 1 || d->pd != 0) return false;
-    if (d->n < 1 || d->ih < 1 || d->iw < 128 || d->iw % 128 != 0 || d->iw > 384) return false;
+    if (d->n < 1 || d->ih < 1 || d->iw < 128) return false;
     const int a0 = dgrad ? d->cout : d->c0, a1 = dgrad ? 0 : d->c1;      // channels of the A-operand sources
     const int n0 = dgrad ? d->c0 : d->cout, n1 = dgrad ? d->c1 : 0;      // channels of the destinations
-    if (a0 % 32 == 0 && a1 % 32 == 0 && a0 > 0) { g.cpp = 32; g.NP0 = a0 / 32; g.NP = (a0 + a1) / 32; }
-    else if (a0 == 16 && (a1 == 0 || a1 == 16)) { g.cpp = 16; g.NP0 = 1; g.NP = a1 ? 2 : 1; }
-    else return false;
-    g.Ncols = n0 + n1;
-    if (g.Ncols != 16 && g.Ncols != 32 && g.Ncols != 64) return false;
     if (n1 != 0 && n1 != n0) return false;
-    g.G = n0 >= 32 ? 32 : 16;
-    if (n0 % g.G != 0) return false;
-    g.ngrp = g.Ncols / g.G;
-    g.grp0 = n0 / g.G;
-    g.P = (d->iw + 2 + 7) / 8 * 8;
+    g.pair = a0 == 16 && (a1 == 0 || a1 == 16) && n0 == 16 && d->iw % 256 == 0;
+    if (const char* e = getenv("B200_ROW_NOPAIR")) if (e[0] == '1') g.pair = 0;       // A/B runs only
+    if (g.pair) {
+        g.cpp = 32; g.NP0 = 1; g.NP = a1 ? 2 : 1;
+        g.Wk = d->iw / 2;
+        g.Ncols = 2 * (n0 + n1); g.G = 32; g.ngrp = g.Ncols / 32; g.grp0 = 1; g.fold = 2;
+    } else {
+        if (a0 % 32 == 0 && a1 % 32 == 0 && a0 > 0) { g.cpp = 32; g.NP0 = a0 / 32; g.NP = (a0 + a1) / 32; }
+        else if (a0 == 16 && (a1 == 0 || a1 == 16)) { g.cpp = 16; g.NP0 = 1; g.NP = a1 ? 2 : 1; }
+        else return false;
+        g.Wk = d->iw;
+        g.Ncols = n0 + n1;
+        if (g.Ncols != 16 && g.Ncols != 32 && g.Ncols != 64) return false;
+        g.G = n0 >= 32 ? 32 : 16;
+        if (n0 % g.G != 0) return false;
+        g.ngrp = g.Ncols / g.G; g.grp0 = n0 / g.G; g.fold = 1;
+    }
+    if (g.Wk % 128 != 0 || g.Wk > 384) return false;
+    g.mode = (dgrad ? 1 : 0) | (g.cpp == 16 ? 2 : 0) | (g.pair ? 4 : 0);
+    g.P = (g.Wk + 2 + 7) / 8 * 8;
     g.P1 = g.P <= 256 ? g.P : 136;
     if (g.P - g.P1 > 256) return false;
-    if (g.P1 < g.P && (a0 > g.cpp || a1 > g.cpp)) return false;     // a split row needs one plane per source
-    g.nblk = d->iw / 128;
+    const int pa0 = g.pair ? 32 : a0, pa1 = g.pair ? (a1 ? 32 : 0) : a1;           // channels per k-pixel of each source
+    if (g.P1 < g.P && (pa0 > g.cpp || pa1 > g.cpp)) return false;                 // a split row needs one plane per source
+    g.nblk = g.Wk / 128;
     const int RB = g.cpp * 4;
     g.plane = g.P * RB;
     g.slot = g.NP * g.plane;
-    g.wbytes = 9 * g.NP * g.Ncols * RB;
+    g.wbytes = (g.pair ? 6 : 9) * g.NP * g.Ncols * RB;
     const int stage = 2 * g.ngrp * 128 * g.G * 4;
     g.R = 0;
     for (int r = MAX_R; r >= 4; --r) {
         const int bytes = 1024 + ((g.wbytes + 1023) & ~1023) + r * g.slot + 1024 + stage;
-        if (bytes <= 216 * 1024) { g.R = r; g.smem = bytes; break; }      // + 8.4 KB of static shared memory
+        if (bytes <= 224 * 1024) { g.R = r; g.smem = bytes; break; }
     }
     return g.R != 0;
 }
 
 }  // namespace
 
-// channels per shared-memory plane of the A operand (32 or 16); 0 = this convolution is not served by the row kernels
+// 0 = this convolution is not served by the row kernels; otherwise 8 + the packing mode (bit 0 data gradient,
+// bit 1 16-channel planes, bit 2 pixel-pair mode) -- the mode goes into the batch packer's job table
 B200_API int b200_conv_row_supported(const b200_conv_desc* d, int dgrad) {
     RGeo g;
-    return (d && rgeometry(d, dgrad, g)) ? g.cpp : 0;
+    return (d && rgeometry(d, dgrad, g)) ? 8 + g.mode : 0;
 }
 
-B200_API long long b200_conv_row_packed_floats(int O, int I) { return 9ll * O * I; }
+B200_API long long b200_conv_row_packed_floats(const b200_conv_desc* d, int dgrad) {
+    RGeo g;
+    if (!d || !rgeometry(d, dgrad, g)) return 0;
+    return row_pack_total(g.mode, d->cout, d->c0 + d->c1);
+}
 
-B200_API int b200_conv_row_pack_weights(const float* w, float* out, int dgrad, int cpp, int O, int I, cudaStream_t st) {
-    B200_REQUIRE(w && out && O > 0 && I > 0 && (cpp == 16 || cpp == 32), "conv_row_pack_weights: bad arguments");
-    const int rows = dgrad ? O : I;
-    B200_REQUIRE(rows % cpp == 0, "conv_row_pack_weights: reduction channels must be a multiple of the plane width");
-    const int total = 9 * O * I;
-    conv_row_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, dgrad, cpp, O, I, total);
+B200_API int b200_conv_row_pack_weights(const b200_conv_desc* d, int dgrad, const float* w, float* out, cudaStream_t st) {
+    RGeo g;
+    B200_REQUIRE(d && w && out && rgeometry(d, dgrad, g), "conv_row_pack_weights: unsupported convolution");
+    const int total = (int)row_pack_total(g.mode, d->cout, d->c0 + d->c1);
+    conv_row_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, g.mode, d->cout, d->c0 + d->c1, total);
     B200_CHECK_LAUNCH("conv_row_pack_weights");
     return B200_OK;
 }
@@ -366,6 +402,14 @@ B200_API long long b200_conv_row_stats_blocks(const b200_conv_desc* d) {
     if (!d) return 0;
     const long long rows = (long long)d->n * d->ih;
     return rows < b200_num_sms() ? rows : b200_num_sms();
+}
+
+template <int CPP, bool PAIR>
+static void launch_row(int grid, int smem, cudaStream_t st, const CUtensorMap& tx0a, const CUtensorMap& tx0b, const CUtensorMap& tx1a,
+                       const CUtensorMap& tx1b, const CUtensorMap& tw, const CUtensorMap& ty0, const CUtensorMap& ty1, const RowP& p) {
+    static int attr = 0;                                       // per instantiation
+    if (smem > attr) { cudaFuncSetAttribute(conv_row_kernel<CPP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
+    conv_row_kernel<CPP, PAIR><<<grid, CR_THREADS, smem, st>>>(tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
 }
 
 static int run_row(const b200_conv_desc* d, int dgrad, const float* a0, const float* a1, const float* wpk, const float* bias,
@@ -379,10 +423,12 @@ static int run_row(const b200_conv_desc* d, int dgrad, const float* a0, const fl
     CUtensorMap tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1;
     const CUtensorMapSwizzle swz = g.cpp == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     auto make_in = [&](CUtensorMap* m, const float* base, int C, int boxp) -> int {
-        const int cg = C / g.cpp;
+        // channels-last [N][H][W][C] as {cpp floats, k-pixels of a row, planes, H, N}; pair mode: a k-pixel is 2 pixels x 16 channels
+        const int Ck = g.pair ? 32 : C;                       // floats per k-pixel
+        const int cg = Ck / g.cpp;
         const cuuint64_t rowb = (cuuint64_t)W * C * 4;
-        const cuuint64_t dims[5] = {(cuuint64_t)g.cpp, (cuuint64_t)W, (cuuint64_t)cg, (cuuint64_t)H, (cuuint64_t)N};
-        const cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)g.cpp * 4, rowb, rowb * H};
+        const cuuint64_t dims[5] = {(cuuint64_t)g.cpp, (cuuint64_t)g.Wk, (cuuint64_t)cg, (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint64_t strides[4] = {(cuuint64_t)Ck * 4, (cuuint64_t)g.cpp * 4, rowb, rowb * H};
         const cuuint32_t box[5] = {(cuuint32_t)g.cpp, (cuuint32_t)boxp, (cuuint32_t)cg, 1u, 1u};
         return make_tmap(m, base, 5, dims, strides, box, swz, who);
     };
@@ -396,17 +442,19 @@ static int run_row(const b200_conv_desc* d, int dgrad, const float* a0, const fl
         if (g.P1 < g.P) if (int rc = make_in(&tx1b, a1, ca1, g.P - g.P1)) return rc;
     }
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)g.cpp, (cuuint64_t)(9 * g.NP * g.Ncols)};
+        const cuuint64_t dims[2] = {(cuuint64_t)g.cpp, (cuuint64_t)((g.pair ? 6 : 9) * g.NP * g.Ncols)};
         const cuuint64_t strides[1] = {(cuuint64_t)g.cpp * 4};
         const cuuint32_t box[2] = {(cuuint32_t)g.cpp, (cuuint32_t)g.Ncols};
         if (int rc = make_tmap(&tw, wpk, 2, dims, strides, box, swz, who)) return rc;
     }
-    const CUtensorMapSwizzle oswz = g.G == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     auto make_out = [&](CUtensorMap* m, float* base, int C) -> int {
-        const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)N * H * W};
-        const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)g.G, 128u};
-        return make_tmap(m, base, 2, dims, strides, box, oswz, who);
+        // 16-channel destinations are stored through their pixel-pair view (128-byte rows): pair mode has 128 pairs per
+        // accumulator block, the plain modes 64
+        const bool pv = C == 16;
+        const cuuint64_t dims[2] = {(cuuint64_t)(pv ? 32 : C), (cuuint64_t)N * H * W / (pv ? 2 : 1)};
+        const cuuint64_t strides[1] = {(cuuint64_t)(pv ? 32 : C) * 4};
+        const cuuint32_t box[2] = {32u, (pv && !g.pair) ? 64u : 128u};
+        return make_tmap(m, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, who);
     };
     if (int rc = make_out(&ty0, dst0, cn0)) return rc;
     ty1 = ty0;
@@ -414,20 +462,15 @@ static int run_row(const b200_conv_desc* d, int dgrad, const float* a0, const fl
 
     RowP p;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.H = H; p.W = W; p.P = g.P; p.NP = g.NP; p.NP0 = g.NP0; p.P1 = g.P1; p.Cout = g.Ncols; p.nblk = g.nblk; p.R = g.R;
+    p.N = N; p.H = H; p.W = g.Wk; p.P = g.P; p.NP = g.NP; p.NP0 = g.NP0; p.P1 = g.P1; p.Cout = g.Ncols; p.nblk = g.nblk; p.R = g.R;
     p.plane_bytes = g.plane; p.slot_bytes = g.slot; p.w_bytes = g.wbytes; p.G = g.G; p.ngrp = g.ngrp; p.grp0 = g.grp0;
-    p.bias = bias; p.stats = stats; p.accumulate = accumulate;
+    p.bias = bias; p.stats = stats; p.accumulate = accumulate; p.fold = g.fold; p.bias_mask = (g.pair ? 16 : g.Ncols) - 1;
+    { const char* e = getenv("B200_ROW_DEBUG"); p.debug = e ? atoi(e) : 0; }
     const long long rows = (long long)N * H;
     const int grid = (int)(rows < b200_num_sms() ? rows : b200_num_sms());
-    if (g.cpp == 32) {
-        static int attr = 0;
-        if (g.smem > attr) { cudaFuncSetAttribute(conv_row_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
-        conv_row_kernel<32><<<grid, CR_THREADS, g.smem, st>>>(tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
-    } else {
-        static int attr = 0;
-        if (g.smem > attr) { cudaFuncSetAttribute(conv_row_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
-        conv_row_kernel<16><<<grid, CR_THREADS, g.smem, st>>>(tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
-    }
+    if (g.pair) launch_row<32, true>(grid, g.smem, st, tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
+    else if (g.cpp == 32) launch_row<32, false>(grid, g.smem, st, tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
+    else launch_row<16, false>(grid, g.smem, st, tx0a, tx0b, tx1a, tx1b, tw, ty0, ty1, p);
     B200_CHECK_LAUNCH(who);
     return B200_OK;
 }

@@ -4,6 +4,7 @@
 //     4*Cout B per pixel), so plain FFMA kernels with coalesced 16-byte stores beat any tensor-core formulation
 //     (code/networks/unet.py:37 with in_chns = 1; code/networks/vnet.py:152 block_one).
 #include "conv_common.cuh"
+#include "conv_row_pack.cuh"
 #include "../../include/b200ssl.h"
 
 // ---------------------------------------------------------------------------------------------------- batched packing
@@ -33,16 +34,7 @@ __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind
     }
     const int dgrad = mode & 1;
     const int rows = dgrad ? O : I, cols = dgrad ? I : O;
-    if (kind == 3) {            // row-ring kernels: [tap][plane][col][k in cpp] (same layout as conv_row_pack_kernel); mode bit 1: cpp = 16
-        const int cpp = (mode & 2) ? 16 : 32, np = rows / cpp;
-        const int k = idx % cpp;
-        int r = idx / cpp;
-        const int col = r % cols; r /= cols;
-        const int pl = r % np, tap = r / np;
-        const int row = pl * cpp + k;
-        const float v = dgrad ? w[((size_t)row * I + col) * T + (T - 1 - tap)] : w[((size_t)col * I + row) * T + tap];
-        return __uint_as_float(f2tf32(v));
-    }
+    if (kind == 3) return row_pack_elem(w, mode, O, I, idx);      // row-ring kernels (conv_row_pack.cuh)
     const int colsP = (cols + 15) / 16 * 16;
     int row, col, tap;
     if (kind == 1) {            // [chunk][tap][colsP][16]

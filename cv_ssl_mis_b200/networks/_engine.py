@@ -141,7 +141,7 @@ class ConvLayer:
         # wide images (W % 128 == 0: the 16 / 32-channel levels): row-ring tcgen05 kernel, weights resident in shared
         # memory, BatchNorm statistics taken in the epilogue.  B200_CONV_ROW=0 keeps the older kernels for A/B runs.
         want_row = is_conv and not rt.exact and os.environ.get("B200_CONV_ROW", "1") != "0"
-        self.row_fwd = ops.conv_row_supported(self.desc, False) if (want_row and not self.out_nchw) else 0     # plane width or 0
+        self.row_fwd = ops.conv_row_supported(self.desc, False) if (want_row and not self.out_nchw) else 0     # 8 + pack mode, or 0
         self.row_dgrad = ops.conv_row_supported(self.desc, True) if (want_row and need_grad) else 0
         self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False) and not self.row_fwd
                          and (self.out_nchw or self.cout % 4 == 0))
@@ -157,7 +157,7 @@ class ConvLayer:
         if self.row_fwd and self.has_act:
             self.stats_blocks = ops.conv_row_stats_blocks(self.desc)
             rt.need_scratch(self.stats_blocks * 2 * self.cout * 8)
-        nfwd = (ops.conv_row_packed_floats(O, I) if self.row_fwd else
+        nfwd = (ops.conv_row_packed_floats(self.desc, False) if self.row_fwd else
                 ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
                 ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
         self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
@@ -174,7 +174,7 @@ class ConvLayer:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            nbwd = (ops.conv_row_packed_floats(O, I) if self.row_dgrad else
+            nbwd = (ops.conv_row_packed_floats(self.desc, True) if self.row_dgrad else
                     ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
                     ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
@@ -188,7 +188,7 @@ class ConvLayer:
             return jobs
         if not self.c1:
             if self.row_fwd:
-                jobs.append((w, self.wp_fwd, 3, 0 | (2 if self.row_fwd == 16 else 0), O, I, T))
+                jobs.append((w, self.wp_fwd, 3, self.row_fwd - 8, O, I, T))
             elif self.umma_fwd:
                 jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
             elif self.tile_fwd:
@@ -197,7 +197,7 @@ class ConvLayer:
                 jobs.append((w, self.wp_fwd, 0, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, T))
         if need_dgrad and self.wp_bwd is not None:
             if self.row_dgrad:
-                jobs.append((w, self.wp_bwd, 3, 1 | (2 if self.row_dgrad == 16 else 0), O, I, T))
+                jobs.append((w, self.wp_bwd, 3, self.row_dgrad - 8, O, I, T))
             elif self.umma_dgrad:
                 jobs.append((w, self.wp_bwd, 2, 1, O, I, T))
             elif self.tile_dgrad:
@@ -213,7 +213,7 @@ class ConvLayer:
         if self.c1:
             pass
         elif self.row_fwd:
-            ops.conv_row_pack_weights(self.conv.weight, self.wp_fwd, False, self.row_fwd, O, I)
+            ops.conv_row_pack_weights(self.desc, False, self.conv.weight, self.wp_fwd)
         elif self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
@@ -222,7 +222,7 @@ class ConvLayer:
             ops.conv_pack_weights(self.conv.weight, self.wp_fwd, PACK_CONV_FWD if self.kind == "conv" else PACK_DECONV_FWD, O, I, self.T)
         if need_dgrad and self.wp_bwd is not None:
             if self.row_dgrad:
-                ops.conv_row_pack_weights(self.conv.weight, self.wp_bwd, True, self.row_dgrad, O, I)
+                ops.conv_row_pack_weights(self.desc, True, self.conv.weight, self.wp_bwd)
             elif self.umma_dgrad:
                 ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.tile_dgrad:

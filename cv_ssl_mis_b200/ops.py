@@ -129,16 +129,16 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
 
 # row-ring tcgen05 forward / data gradient (wide-image 2D 3x3 stride-1 pad-1, weights resident, BN statistics fused)
 def conv_row_supported(d, dgrad=False) -> int:
-    """Plane width (32 or 16 channels) of the reduction operand, or 0 when the row kernels do not serve this convolution."""
+    """0 when the row kernels do not serve this convolution, else 8 + the weight-packing mode (conv_pack_batch kind 3)."""
     return int(_lib.query("b200_conv_row_supported", C.byref(d), int(dgrad)))
 
 
-def conv_row_packed_floats(O, I) -> int:
-    return int(_lib.query("b200_conv_row_packed_floats", O, I))
+def conv_row_packed_floats(d, dgrad=False) -> int:
+    return int(_lib.query("b200_conv_row_packed_floats", C.byref(d), int(dgrad)))
 
 
-def conv_row_pack_weights(w, out, dgrad, cpp, O, I):
-    _lib.call("b200_conv_row_pack_weights", _pf(w), _pf(out), int(dgrad), int(cpp), O, I, _st())
+def conv_row_pack_weights(d, dgrad, w, out):
+    _lib.call("b200_conv_row_pack_weights", C.byref(d), int(dgrad), _pf(w), _pf(out), _st())
 
 
 def conv_row_stats_blocks(d) -> int:

@@ -127,10 +127,11 @@ int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, const float*
  * b200_conv_row_fwd can emit the per-channel (sum, sum of squares) of its output as b200_conv_row_stats_blocks(d) fp64
  * partials [block][2][cout] for b200_bn_finalize -- the statistics pass of the following train-mode BatchNorm
  * (code/networks/unet.py:38,42) without re-reading the output.  Packed weights: [tap][plane][column][k], TF32-rounded. */
-/* returns the plane width cpp (32 or 16 channels) of the reduction operand, or 0 when the convolution is not served */
+/* 0 when the convolution is not served; otherwise 8 + the weight-packing mode (bit 0 data gradient, bit 1 16-channel
+ * planes, bit 2 pixel-pair mode for 16-channel tensors) -- the mode is what b200_conv_pack_batch jobs of kind 3 carry */
 int b200_conv_row_supported(const b200_conv_desc* d, int dgrad);
-long long b200_conv_row_packed_floats(int O, int I);
-int b200_conv_row_pack_weights(const float* w, float* out, int dgrad, int cpp, int O, int I, cudaStream_t stream);
+long long b200_conv_row_packed_floats(const b200_conv_desc* d, int dgrad);
+int b200_conv_row_pack_weights(const b200_conv_desc* d, int dgrad, const float* w, float* out, cudaStream_t stream);
 long long b200_conv_row_stats_blocks(const b200_conv_desc* d);
 int b200_conv_row_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wpk, const float* bias,
                       float* dst, double* stats_partials, cudaStream_t stream);
@@ -138,7 +139,7 @@ int b200_conv_row_dgrad(const b200_conv_desc* d, const float* dy, const float* w
                         int accumulate, cudaStream_t stream);
 
 /* One-launch weight packing for a whole network.  jobs_dev: DEVICE array of njobs x 8 int64:
- * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma / 3 row), mode (generic: B200_PACK_*; tile/umma: dgrad flag; row: dgrad | 2 * (cpp == 16)), O, I, T, total]. */
+ * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma / 3 row), mode (generic: B200_PACK_*; tile/umma: dgrad flag; row: b200_conv_row_supported() - 8), O, I, T, total]. */
 int b200_conv_pack_batch(const long long* jobs_dev, int njobs, int blocks_per_job, cudaStream_t stream);
 /* First layer of the CNNs (Cin = 1, 3x3 / 3x3x3 stride 1 pad 1, Cout in {16, 32}): HBM-bound FFMA kernels working on the
  * framework weight layout directly (code/networks/unet.py:37 with in_chns = 1, code/networks/vnet.py:152). */

@@ -237,52 +237,104 @@ def conv_tile_wgrad(d, src0, src1, dy, ws, dw, db, accumulate=False):
 
 
 # ------------------------------------------------------------------ row-ring tcgen05 forward / data gradient
-def conv_row_supported(d, dgrad=False):
+def _row_geo(d, dgrad):
+    """(mode, planes, columns, plane width) of csrc/conv_row.cu:rgeometry, or None."""
     if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
-        return 0
-    if d.iw < 128 or d.iw % 128 or d.iw > 384:
-        return 0
+        return None
+    if d.iw < 128:
+        return None
     a0, a1 = (d.cout, 0) if dgrad else (d.c0, d.c1)
     n0, n1 = (d.c0, d.c1) if dgrad else (d.cout, 0)
-    if a0 > 0 and a0 % 32 == 0 and a1 % 32 == 0:
-        cpp, npl = 32, (a0 + a1) // 32
-    elif a0 == 16 and a1 in (0, 16):
-        cpp, npl = 16, (2 if a1 else 1)
+    if n1 != 0 and n1 != n0:
+        return None
+    pair = a0 == 16 and a1 in (0, 16) and n0 == 16 and d.iw % 256 == 0
+    if pair:
+        cpp, npl, wk, ncols, G = 32, (2 if a1 else 1), d.iw // 2, 2 * (n0 + n1), 32
     else:
-        return 0
-    ncols = n0 + n1
-    if ncols not in (16, 32, 64) or (n1 != 0 and n1 != n0):
-        return 0
-    G = 32 if n0 >= 32 else 16
-    if n0 % G:
-        return 0
-    P = (d.iw + 2 + 7) // 8 * 8
-    if P > 256 and (a0 > cpp or a1 > cpp):
-        return 0
+        if a0 > 0 and a0 % 32 == 0 and a1 % 32 == 0:
+            cpp, npl = 32, (a0 + a1) // 32
+        elif a0 == 16 and a1 in (0, 16):
+            cpp, npl = 16, (2 if a1 else 1)
+        else:
+            return None
+        wk, ncols = d.iw, n0 + n1
+        if ncols not in (16, 32, 64):
+            return None
+        G = 32 if n0 >= 32 else 16
+        if n0 % G:
+            return None
+    if wk % 128 or wk > 384:
+        return None
+    P = (wk + 2 + 7) // 8 * 8
+    pa0, pa1 = (32, 32 if a1 else 0) if pair else (a0, a1)
+    if P > 256 and (pa0 > cpp or pa1 > cpp):
+        return None
     slot, wb, stage = npl * P * cpp * 4, 9 * npl * ncols * cpp * 4, 2 * (ncols // G) * 128 * G * 4
-    return cpp if 1024 + (wb + 1023) // 1024 * 1024 + 4 * slot + 1024 + stage <= 216 * 1024 else 0
+    if pair:
+        wb = wb * 2 // 3
+    if 1024 + (wb + 1023) // 1024 * 1024 + 4 * slot + 1024 + stage > 224 * 1024:
+        return None
+    return (1 if dgrad else 0) | (2 if cpp == 16 else 0) | (4 if pair else 0)
 
 
-def conv_row_packed_floats(O, I):
-    return 9 * O * I
+def conv_row_supported(d, dgrad=False):
+    m = _row_geo(d, dgrad)
+    return 0 if m is None else 8 + m
 
 
-def conv_row_pack_weights(w, out, dgrad, cpp, O, I):
-    W = w.detach().reshape(O, I, 9)
-    if dgrad:      # out[tap][plane][i][k] = W[plane*cpp+k][i][8-tap]
-        m, rows = W.flip(2).permute(2, 1, 0), O        # [tap][i][o]
-    else:          # out[tap][plane][o][k] = W[o][plane*cpp+k][tap]
-        m, rows = W.permute(2, 0, 1), I                # [tap][o][i]
-    cols = m.shape[1]
-    out.copy_(m.reshape(9, cols, rows // cpp, cpp).permute(0, 2, 1, 3).reshape(-1))
+def conv_row_packed_floats(d, dgrad=False):
+    m = _row_geo(d, dgrad)
+    return d.cout * (d.c0 + d.c1) * (24 if m & 4 else 9)
 
 
-def _row_unpack(wpk, dgrad, cpp, O, I):
+def _row_pack_index(mode, O, I):
+    """csrc/conv_row_pack.cuh:row_pack_elem as index arithmetic: (flat source index into w[O][I][9], validity) per output element."""
+    dgrad = mode & 1
     rows, cols = (O, I) if dgrad else (I, O)
-    m = wpk.reshape(9, rows // cpp, cols, cpp).permute(0, 2, 1, 3).reshape(9, cols, rows)
-    if dgrad:
-        return m.permute(2, 1, 0).flip(2)              # [o][i][tap]
-    return m.permute(1, 2, 0)                          # [o][i][tap]
+    if not mode & 4:
+        cpp = 16 if mode & 2 else 32
+        npl = rows // cpp
+        idx = torch.arange(9 * O * I)
+        k, r = idx % cpp, idx // cpp
+        col, r = r % cols, r // cols
+        pl, tap = r % npl, r // npl
+        row = pl * cpp + k
+        src = (row * I + col) * 9 + (8 - tap) if dgrad else (col * I + row) * 9 + tap
+        return src, torch.ones_like(src, dtype=torch.bool)
+    npl = rows // 16
+    idx = torch.arange(6 * O * I * 4)
+    k, r = idx & 31, idx >> 5
+    col, r = r % (2 * cols), r // (2 * cols)
+    pl, t = r % npl, r // npl
+    kh, j = t >> 1, t & 1
+    pb, arow = k >> 4, pl * 16 + (k & 15)
+    s_ = torch.where(j == 0, torch.ones_like(j), torch.where(pb == 1, torch.zeros_like(j), 2 * torch.ones_like(j)))
+    dst, pa, ncol = col >> 5, (col >> 4) & 1, (col >> 5) * 16 + (col & 15)
+    kw = 2 * (s_ - 1) + pb - pa + 1
+    ok = (kw >= 0) & (kw <= 2)
+    kwc = kw.clamp(0, 2)
+    src = (arow * I + ncol) * 9 + (2 - kh) * 3 + (2 - kwc) if dgrad else (ncol * I + arow) * 9 + kh * 3 + kwc
+    return src, ok
+
+
+def _tf32_rna(v):
+    b = v.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def conv_row_pack_weights(d, dgrad, w, out):
+    O, I = d.cout, d.c0 + d.c1
+    src, ok = _row_pack_index(_row_geo(d, dgrad), O, I)
+    out.copy_(torch.where(ok, _tf32_rna(w.detach().reshape(-1))[src], torch.zeros(())))
+
+
+def _row_unpack(d, dgrad, wpk):
+    """Framework-layout weights [O][I][9] back from the packed array (every tap appears at least once)."""
+    O, I = d.cout, d.c0 + d.c1
+    src, ok = _row_pack_index(_row_geo(d, dgrad), O, I)
+    W = torch.zeros(O * I * 9)
+    W[src[ok]] = wpk.reshape(-1)[ok]
+    return W.reshape(O, I, 1, 3, 3)
 
 
 def conv_row_stats_blocks(d):
@@ -290,7 +342,7 @@ def conv_row_stats_blocks(d):
 
 
 def conv_row_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
-    W = _row_unpack(wpk, False, conv_row_supported(d, False), d.cout, d.c0 + d.c1).reshape(d.cout, d.c0 + d.c1, 1, 3, 3)
+    W = _row_unpack(d, False, wpk)
     y = _ncdhw_to_cl(F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))).reshape(dst.shape)
     dst.copy_(y)
     if stats_part is not None:
@@ -301,8 +353,7 @@ def conv_row_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
 
 
 def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
-    cin = d.c0 + d.c1
-    W = _row_unpack(wpk_dgrad, True, conv_row_supported(d, True), d.cout, cin).reshape(d.cout, cin, 1, 3, 3)
+    W = _row_unpack(d, True, wpk_dgrad)
     g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
     dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
     _split_store(dx, d, dx0, dx1, accumulate)
@@ -370,7 +421,8 @@ def conv_pack_batch(jobs_dev, njobs, blocks_per_job=16, jobs_py=None):
         elif kind == 1:
             conv_tile_pack_weights(w, out, bool(mode), O, I, T)
         elif kind == 3:
-            conv_row_pack_weights(w, out, bool(mode & 1), 16 if mode & 2 else 32, O, I)
+            src, ok = _row_pack_index(mode, O, I)
+            out.copy_(torch.where(ok, _tf32_rna(w.detach().reshape(-1))[src], torch.zeros(())))
         else:
             conv_umma_pack_weights(w, out, bool(mode), O, I, T)
 

@@ -19,6 +19,9 @@ CASES = [
     (1, 7, 256, 16, 16, 16),
     (3, 2, 128, 32, 0, 16),
     (1, 3, 384, 16, 0, 16),
+    (2, 150, 256, 16, 0, 16),    # ~2 rows per CTA: rolling window across image boundaries
+    (1, 320, 256, 16, 16, 16),
+    (3, 130, 128, 32, 0, 32),
 ]
 
 
@@ -47,8 +50,8 @@ def test_row_fwd_and_stats(case):
         return
     x0, x1, wgt, bias, _ = _mk(case)
     M, cin = n * h * w, c0 + c1
-    wpk = torch.empty(ops.conv_row_packed_floats(cout, cin), device=DEV)
-    ops.conv_row_pack_weights(wgt.to(DEV), wpk, False, ops.conv_row_supported(d, False), cout, cin)
+    wpk = torch.empty(ops.conv_row_packed_floats(d, False), device=DEV)
+    ops.conv_row_pack_weights(d, False, wgt.to(DEV), wpk)
     y = torch.full((M, cout), float("nan"), device=DEV)
     nb = ops.conv_row_stats_blocks(d)
     part = torch.full((nb * 2 * cout,), float("nan"), dtype=torch.float64, device=DEV)
@@ -82,8 +85,8 @@ def test_row_dgrad(case):
         pytest.skip("data gradient of this shape is served by another kernel")
     _, _, wgt, _, dy = _mk(case, 1)
     M, cin = n * h * w, c0 + c1
-    wpk = torch.empty(ops.conv_row_packed_floats(cout, cin), device=DEV)
-    ops.conv_row_pack_weights(wgt.to(DEV), wpk, True, ops.conv_row_supported(d, True), cout, cin)
+    wpk = torch.empty(ops.conv_row_packed_floats(d, True), device=DEV)
+    ops.conv_row_pack_weights(d, True, wgt.to(DEV), wpk)
     dx0 = torch.full((M, c0), float("nan"), device=DEV)
     dx1 = torch.full((M, c1), float("nan"), device=DEV) if c1 else None
     ops.conv_row_dgrad(d, dy.to(DEV), wpk, dx0, dx1)
@@ -95,3 +98,28 @@ def test_row_dgrad(case):
     ops.conv_row_dgrad(d, dy.to(DEV), wpk, dx0, dx1, accumulate=True)
     got2 = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
     torch.testing.assert_close(got2, 2 * got, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[3], CASES[4], CASES[5]])
+@pytest.mark.parametrize("dgrad", [False, True])
+def test_row_pack_batch_equals_single_and_restatement(case, dgrad):
+    """The one-launch batch packer (kind 3), the stand-alone packer and the index restatement in tests/fake_ops.py agree."""
+    from tests import fake_ops
+    n, h, w, c0, c1, cout = case
+    d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    m = ops.conv_row_supported(d, dgrad)
+    if not m:
+        pytest.skip("not served by the row kernels")
+    assert m == fake_ops.conv_row_supported(d, dgrad)
+    wgt = torch.randn(cout, c0 + c1, 3, 3, generator=torch.Generator().manual_seed(1))
+    nf = ops.conv_row_packed_floats(d, dgrad)
+    assert nf == fake_ops.conv_row_packed_floats(d, dgrad)
+    single, batch = torch.empty(nf, device=DEV), torch.empty(nf, device=DEV)
+    wd = wgt.to(DEV)
+    ops.conv_row_pack_weights(d, dgrad, wd, single)
+    table = torch.tensor([[wd.data_ptr(), batch.data_ptr(), 3, m - 8, cout, c0 + c1, 9, nf]], dtype=torch.int64, device=DEV)
+    ops.conv_pack_batch(table, 1, 8)
+    restated = torch.empty(nf)
+    fake_ops.conv_row_pack_weights(d, dgrad, wgt, restated)
+    assert torch.equal(single, batch)
+    assert torch.equal(single.cpu(), restated)

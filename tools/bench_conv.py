@@ -25,8 +25,8 @@ for (n, h, w, c0, c1, cout) in SHAPES:
         if name == "row":
             if not ops.conv_row_supported(d, False):
                 continue
-            wt = torch.empty(ops.conv_row_packed_floats(cout, cin), device="cuda")
-            ops.conv_row_pack_weights(wgt, wt, False, ops.conv_row_supported(d, False), cout, cin)
+            wt = torch.empty(ops.conv_row_packed_floats(d, False), device="cuda")
+            ops.conv_row_pack_weights(d, False, wgt, wt)
             part = torch.empty(ops.conv_row_stats_blocks(d) * 2 * cout, dtype=torch.float64, device="cuda")
             fn = lambda: ops.conv_row_fwd(d, x0, x1, wt, bias, y, part)
         elif name.startswith("umma"):
