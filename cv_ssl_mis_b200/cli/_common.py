@@ -51,7 +51,7 @@ def base_parser(exp, model, batch_size, patch_size, labeled_bs, labeled_num, roo
 
 def add_swin_flags(p):
     """Flags of the Swin-UNet scripts (code/train_cross_teaching_between_cnn_transformer_2D.py:66-92); accepted for
-    launch-line compatibility, only --cfg / --opts reach the model."""
+    launch-line compatibility; --cfg / --opts reach the model through build_swin_config."""
     p.add_argument('--cfg', type=str, default="../code/configs/swin_tiny_patch4_window7_224_lite.yaml", help='path to config file')
     p.add_argument("--opts", help="Modify config options by adding 'KEY VALUE' pairs. ", default=None, nargs='+')
     p.add_argument('--zip', action='store_true', help='use zipped dataset instead of folder dataset')
@@ -114,6 +114,65 @@ def synthetic_batches(batch_size, patch, num_classes, seed, pinned=True):
         yield {"image": x, "label": y.contiguous()}
 
 
+class _Node(dict):
+    """Attribute-style nested config node (the slice of yacs.CfgNode the Swin-UNet reads)."""
+    __getattr__ = dict.__getitem__
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def build_swin_config(args):
+    """The reference's `get_config(args)` (code/config.py:28-74,176-220) for the keys the Swin-UNet reads: code defaults,
+    then the yaml at --cfg (if the file exists; the lite yaml's values are the built-in fallback), then --opts KEY VALUE
+    pairs.  Returns a yacs-like object for `net_factory(config=...)` and `SwinUnet.load_from(config)`."""
+    import ast
+    cfg = _Node(DATA=_Node(IMG_SIZE=224),
+                MODEL=_Node(TYPE="swin", NAME="swin_tiny_patch4_window7_224", DROP_RATE=0.0, DROP_PATH_RATE=0.1,
+                            PRETRAIN_CKPT="./pretrained_ckpt/swin_tiny_patch4_window7_224.pth",
+                            SWIN=_Node(PATCH_SIZE=4, IN_CHANS=3, EMBED_DIM=96, DEPTHS=[2, 2, 6, 2], DECODER_DEPTHS=[2, 2, 6, 2],
+                                       NUM_HEADS=[3, 6, 12, 24], WINDOW_SIZE=7, MLP_RATIO=4.0, QKV_BIAS=True, QK_SCALE=None,
+                                       APE=False, PATCH_NORM=True, FINAL_UPSAMPLE="expand_first")))
+    lite = {"MODEL": {"DROP_PATH_RATE": 0.2, "PRETRAIN_CKPT": "../code/pretrained_ckpt/swin_tiny_patch4_window7_224.pth",
+                      "SWIN": {"DEPTHS": [2, 2, 2, 2], "DECODER_DEPTHS": [2, 2, 2, 1]}}}
+
+    def merge(node, upd):
+        for k, v in upd.items():
+            if isinstance(v, dict):
+                merge(node.setdefault(k, _Node()), v)
+            else:
+                node[k] = v
+
+    path = getattr(args, "cfg", None)
+    if path and os.path.exists(path):
+        import yaml
+        with open(path) as f:
+            merge(cfg, yaml.safe_load(f) or {})
+    else:
+        if path and os.path.basename(path) != "swin_tiny_patch4_window7_224_lite.yaml":
+            raise SystemExit(f"--cfg {path}: file not found")
+        merge(cfg, lite)           # the reference's default yaml, restated
+    opts = getattr(args, "opts", None) or []
+    if len(opts) % 2:
+        raise SystemExit("--opts takes KEY VALUE pairs")
+    for key, val in zip(opts[0::2], opts[1::2]):
+        node = cfg
+        *parents, leaf = key.split(".")
+        for k in parents:
+            if k not in node:
+                raise SystemExit(f"--opts {key}: unknown config key")
+            node = node[k]
+        if leaf not in node:
+            raise SystemExit(f"--opts {key}: unknown config key")
+        try:
+            node[leaf] = ast.literal_eval(val)
+        except (ValueError, SyntaxError):
+            node[leaf] = val
+    if getattr(args, "batch_size", None):
+        cfg.DATA.BATCH_SIZE = args.batch_size
+    return cfg
+
+
 def snapshot_dir(args):
     path = "../model/{}_{}_labeled/{}".format(args.exp, args.labeled_num, args.model)      # reference: train_*.py __main__
     os.makedirs(path, exist_ok=True)
@@ -131,16 +190,23 @@ def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0):
     models: {checkpoint prefix: module}; fmt(iter_num, losses) -> log line."""
     it0 = trainer.iter_num
     t0 = time.time()
-    for batch in loader:
-        log = args.log_every and (trainer.iter_num + 1) % args.log_every == 0
-        out = trainer.step(batch["image"], batch["label"], read_loss=bool(log))
-        if log and rank == 0:
-            logging.info(fmt(trainer.iter_num, out))
-        if rank == 0 and args.save_every and trainer.iter_num % args.save_every == 0:
-            for prefix, m in models.items():
-                torch.save(m.state_dict(), os.path.join(snapshot_path, f"{prefix}iter_{trainer.iter_num}.pth"))
-        if trainer.iter_num >= args.max_iterations:
-            break
+    # the reference wraps its loader in `for epoch_num in range(max_iterations // len(trainloader) + 1)`
+    # (code/train_mean_teacher_2D.py:199-201,296-301): a finite loader is re-iterated until max_iterations is reached
+    while trainer.iter_num < args.max_iterations:
+        seen = 0
+        for batch in loader:
+            seen += 1
+            log = args.log_every and (trainer.iter_num + 1) % args.log_every == 0
+            out = trainer.step(batch["image"], batch["label"], read_loss=bool(log))
+            if log and rank == 0:
+                logging.info(fmt(trainer.iter_num, out))
+            if rank == 0 and args.save_every and trainer.iter_num % args.save_every == 0:
+                for prefix, m in models.items():
+                    torch.save(m.state_dict(), os.path.join(snapshot_path, f"{prefix}iter_{trainer.iter_num}.pth"))
+            if trainer.iter_num >= args.max_iterations:
+                break
+        if seen == 0:
+            raise ValueError("the data loader yielded no batches")
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     dt = time.time() - t0

@@ -2,8 +2,8 @@
 code/train_cross_pseudo_supervision_2D.py."""
 import sys
 
-from ._common import (add_swin_flags, base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir,
-                      synthetic_batches)
+from ._common import (add_swin_flags, base_parser, build_swin_config, process_group, run_loop, seed_everything, setup_logging,
+                      snapshot_dir, synthetic_batches)
 
 
 def main(argv=None, loader=None):
@@ -18,9 +18,21 @@ def main(argv=None, loader=None):
     from ..trainers import CrossTeachingTrainer
     pg, rank = process_group()
     model1 = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)              # :134-141
-    model2 = net_factory(net_type=args.model2, in_chns=1, class_num=args.num_classes)             # :142-144 (ViT_seg)
+    config = build_swin_config(args) if args.model2 == "ViT_Seg" else None                        # config.py:get_config(args)
+    model2 = net_factory(net_type=args.model2, in_chns=1, class_num=args.num_classes, config=config,
+                         img_size=args.patch_size)                                                # :142-144 (ViT_seg)
     if model1 is None or model2 is None:
         raise SystemExit("--model / --model2: not built (available: unet, ViT_Seg)")
+    if config is not None:
+        # :145 `model2.load_from(config)`: ImageNet-pretrained Swin encoder, copied into the decoder as well.  The
+        # reference dies without the checkpoint; here a missing file is reported and the Swin-UNet starts from its
+        # random initialisation (the synthetic benchmarks have no checkpoint).
+        import os
+        if os.path.exists(config.MODEL.PRETRAIN_CKPT):
+            model2.load_from(config)
+            model2._flat, model2._plans = None, {}         # parameters were replaced: re-home them on first use
+        else:
+            print(f"pretrained checkpoint {config.MODEL.PRETRAIN_CKPT} not found: Swin-UNet trains from scratch")
     if pg is not None:
         import torch.distributed as dist
         for m in (model1, model2):

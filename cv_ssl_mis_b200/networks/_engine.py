@@ -64,6 +64,10 @@ class Runtime:
 
     def alloc_scratch(self):
         if self.scratch is None or self.scratch.numel() * 4 < self.scratch_bytes:
+            # a captured CUDA graph has the old scratch pointers baked in: keep every superseded buffer alive so that its
+            # replays never write into memory the caching allocator has handed to someone else
+            if self.scratch is not None:
+                self._retired = getattr(self, "_retired", []) + [self.scratch, self.scratch_side]
             self.scratch = torch.empty((self.scratch_bytes + 3) // 4 + 4, dtype=torch.float32, device=self.device)
             self.scratch_side = torch.empty_like(self.scratch) if self.overlap else self.scratch
 
@@ -126,7 +130,7 @@ class ConvLayer:
         self.gemm = (is_conv and self.k == 1 and self.stride == 1 and not rt.exact and not self.out_nchw
                      and self.cout >= 32 and self.cin >= 32 and ops.linear_supported(self.M, self.cout, c0, c1))
         if self.gemm:
-            self.umma_fwd = self.umma_dgrad = self.c1 = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = self.row_wgrad = False
+            self.umma_fwd = self.umma_dgrad = self.use_c1_kernel = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = self.row_wgrad = False
             self.row_fwd = self.row_dgrad = False
             self.wp_fwd = self.wp_bwd = None
             if need_grad:
@@ -146,7 +150,7 @@ class ConvLayer:
         self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False) and not self.row_fwd
                          and (self.out_nchw or self.cout % 4 == 0))
         self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True) and not self.row_dgrad
-        self.c1 = is_conv and not rt.exact and ops.conv_c1_supported(self.desc)       # first layer: FFMA kernels
+        self.use_c1_kernel = is_conv and not rt.exact and ops.conv_c1_supported(self.desc)       # first layer: FFMA kernels
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
         self.tile_wgrad = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, True)
@@ -165,7 +169,7 @@ class ConvLayer:
         if need_grad:
             if is_conv:
                 self.bwd_mode = PACK_CONV_DGRAD if self.stride == 1 else PACK_CONV_DGRAD_D2S
-                rt.need_scratch(ops.conv_c1_wgrad_workspace_bytes(self.desc) if self.c1 else
+                rt.need_scratch(ops.conv_c1_wgrad_workspace_bytes(self.desc) if self.use_c1_kernel else
                                 max(ops.conv_row_wgrad_workspace_bytes(self.desc), ops.colsum_workspace_bytes(self.M, self.cout))
                                 if self.row_wgrad else
                                 ops.conv_tile_wgrad_workspace_bytes(self.desc) if self.tile_wgrad
@@ -186,7 +190,7 @@ class ConvLayer:
         jobs = []
         if self.gemm:
             return jobs
-        if not self.c1:
+        if not self.use_c1_kernel:
             if self.row_fwd:
                 jobs.append((w, self.wp_fwd, 3, self.row_fwd - 8, O, I, T))
             elif self.umma_fwd:
@@ -210,7 +214,7 @@ class ConvLayer:
         O, I = self.cout, self.cin
         if self.gemm:
             return
-        if self.c1:
+        if self.use_c1_kernel:
             pass
         elif self.row_fwd:
             ops.conv_row_pack_weights(self.desc, False, self.conv.weight, self.wp_fwd)
@@ -236,7 +240,7 @@ class ConvLayer:
         self.bn_train = train
         if self.gemm:
             ops.linear_fwd(src0, src1, self.conv.weight.view(self.cout, self.cin), self.conv.bias, self.y, self.M, self.cout)
-        elif self.c1:
+        elif self.use_c1_kernel:
             ops.conv_c1_fwd(self.desc, src0, self.conv.weight, self.conv.bias, self.y)
         elif self.row_fwd:
             fused_stats = self.has_act and train
@@ -292,7 +296,7 @@ class ConvLayer:
         elif self.kind == "conv":
             with rt.side_stream():
                 ws = rt.scratch_side
-                if self.c1:
+                if self.use_c1_kernel:
                     ops.conv_c1_wgrad(self.desc, src0, dy, ws, conv.weight.grad, bias_grad, accumulate_w)
                 elif self.row_wgrad:
                     # a bias in front of a train-mode BatchNorm has an identically zero gradient (the BatchNorm backward

@@ -61,7 +61,7 @@ class MeanTeacherTrainer:
         self.s_off = model._rt.seed_off
         self.t_off = ema_model._rt.seed_off if ema_model is not None else None
         pin = dev.type == "cuda"
-        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if pin else torch.zeros(8)
+        self.hp_ring = PinnedRing(8, dev)
         self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
         S = 1
         for v in self.patch:
@@ -101,7 +101,7 @@ class MeanTeacherTrainer:
     def _set_hparams(self):
         it = self.iter_num
         alpha = min(1 - 1 / (it + 1), self.ema_decay)
-        h = self.hp_host
+        h = [0.0] * 8
         h[HP_LR] = self.lr
         h[HP_MOMENTUM] = self.momentum
         h[HP_WD] = self.weight_decay
@@ -110,7 +110,7 @@ class MeanTeacherTrainer:
         h[HP_GRAD_SCALE] = 1.0 / self.world
         h[HP_WCONS] = self.consistency_weight(it)
         h[HP_THRESHOLD] = self.uncertainty_threshold(it)
-        self.hp.copy_(h, non_blocking=True)
+        self.hp_ring.push(h, self.hp)
 
     # ---- the device-side schedule (graph-capturable)
     def _device_step(self):
@@ -252,7 +252,7 @@ class ICTTrainer(MeanTeacherTrainer):
         dev, h = self.dev, self.h
         self.x_in = torch.empty((self.B_in, 1, *self.patch), dtype=torch.float32, device=dev)
         self.y_in = torch.empty((self.B_in, *self.patch), dtype=self.y.dtype, device=dev)
-        self.mix_host = torch.zeros(h, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(h)
+        self.mix_ring = PinnedRing(h, dev)
         self.mix = torch.zeros((h, 1, 1, 1), dtype=torch.float32, device=dev)
         self.p0 = torch.empty((h, self.C, self.S), dtype=torch.float32, device=dev)
         self.p1 = torch.empty_like(self.p0)
@@ -293,8 +293,7 @@ class ICTTrainer(MeanTeacherTrainer):
         (default: numpy Beta(ict_alpha, ict_alpha) draws, :155-158)."""
         if mix_factors is None:
             mix_factors = self.mix_rng.beta(self.ict_alpha, self.ict_alpha, size=(self.h,))
-        self.mix_host.copy_(torch.as_tensor(mix_factors, dtype=torch.float32).reshape(self.h))
-        self.mix.view(self.h).copy_(self.mix_host, non_blocking=True)
+        self.mix_ring.push(mix_factors, self.mix.view(self.h))
         self.x_in.copy_(images, non_blocking=True)
         self.y_in.copy_(labels, non_blocking=True)
         self._set_hparams()
@@ -311,6 +310,32 @@ class ICTTrainer(MeanTeacherTrainer):
             torch.cuda.current_stream().synchronize() if self.dev.type == "cuda" else None
             return self.loss_host.tolist()
         return self.lossbuf
+
+
+class PinnedRing:
+    """Per-step host scalars go to the device through a ring of pinned buffers, each guarded by a CUDA event: the CPU
+    runs many graph replays ahead of the GPU, so ONE reused pinned buffer could be overwritten with the values of a
+    later iteration before the DMA of an earlier one has read it (lr / EMA alpha / consistency weight of the wrong step)."""
+
+    def __init__(self, n, device, slots=8):
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.zeros(n, dtype=torch.float32).pin_memory() if self.cuda else torch.zeros(n) for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+
+    def push(self, values, dst):
+        """values: sequence / tensor of floats -> dst (device tensor) with an async copy on the current stream."""
+        k = self.i
+        self.i = (k + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()              # the copy that last used this slot has completed
+        buf = self.bufs[k]
+        buf.copy_(torch.as_tensor(values, dtype=torch.float32).reshape(buf.shape))
+        dst.copy_(buf, non_blocking=True)
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[k] = ev
 
 
 def _plan_for(model, B, patch, need_grad):
@@ -348,7 +373,7 @@ class CrossTeachingTrainer:
         self.momentum_bufs = [torch.zeros_like(f.data) for f in self.flats]
         self.offs = [m._rt.seed_off for m in self.models]
         pin = dev.type == "cuda"
-        self.hp_host = torch.zeros(8, dtype=torch.float32).pin_memory() if pin else torch.zeros(8)
+        self.hp_ring = PinnedRing(8, dev)
         self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
         self.S = self.patch[0] * self.patch[1]
         self.x = torch.empty((self.B, 1, *self.patch), dtype=torch.float32, device=dev)
@@ -368,14 +393,14 @@ class CrossTeachingTrainer:
         return self.consistency * ramps.sigmoid_rampup(iter_num // 150, self.consistency_rampup)
 
     def _set_hparams(self):
-        h = self.hp_host
+        h = [0.0] * 8
         h[HP_LR] = self.lr
         h[HP_MOMENTUM] = self.momentum
         h[HP_WD] = self.weight_decay
         h[HP_ALPHA], h[HP_ONE_MINUS_ALPHA] = 1.0, 0.0
         h[HP_GRAD_SCALE] = 1.0 / self.world
         h[HP_WCONS] = self.consistency_weight(self.iter_num)
-        self.hp.copy_(h, non_blocking=True)
+        self.hp_ring.push(h, self.hp)
 
     def _device_step(self):
         for m, off in zip(self.models, self.offs):

@@ -70,3 +70,37 @@ def test_ict_cli(cpu_env):
     from cv_ssl_mis_b200.cli import train_interpolation_consistency_training_2D as cli
     assert cli.main(["--batch_size", "8", "--labeled_bs", "4", "--patch_size", "32", "32", "--ict_alpha", "1"] + COMMON) \
         == "Training Finished!"
+
+
+def test_finite_loader_is_reiterated_until_max_iterations(cpu_env):
+    """The reference loops `for epoch_num in range(max_iterations // len(trainloader) + 1)` over its DataLoader
+    (code/train_mean_teacher_2D.py:199-201): a 2-batch loader must still run max_iterations = 5 steps."""
+    from cv_ssl_mis_b200.cli import train_mean_teacher_2D as cli
+    from cv_ssl_mis_b200.cli._common import synthetic_batches
+    gen = synthetic_batches(4, (32, 32), 4, 3, pinned=False)
+    batches = [next(gen) for _ in range(2)]
+    out = cli.main(["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32", "--max_iterations", "5", "--log_every", "1",
+                    "--save_every", "0", "--no_graph", "--seed", "7"], loader=batches)
+    assert out == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Mean_Teacher_7_labeled" / "unet"
+    assert (snap / "iter_5.pth").exists() and "iteration 5 :" in (snap / "log.txt").read_text()
+
+
+def test_swin_config_from_cfg_and_opts(tmp_path):
+    """--cfg / --opts reach the Swin-UNet (code/config.py:get_config): yaml over the code defaults, then KEY VALUE pairs."""
+    import argparse
+    from cv_ssl_mis_b200.cli._common import build_swin_config
+    from cv_ssl_mis_b200.networks.swin_unet import _read_config
+    ns = argparse.Namespace(cfg="../code/configs/swin_tiny_patch4_window7_224_lite.yaml", opts=None, batch_size=16)
+    cfg = build_swin_config(ns)                       # file absent: the lite yaml restated
+    assert cfg.MODEL.DROP_PATH_RATE == 0.2 and cfg.MODEL.SWIN.DEPTHS == [2, 2, 2, 2] and cfg.DATA.IMG_SIZE == 224
+    assert _read_config(cfg)["drop_path_rate"] == 0.2 and _read_config(cfg)["depths"] == (2, 2, 2, 2)
+    y = tmp_path / "my.yaml"
+    y.write_text("MODEL:\n  DROP_PATH_RATE: 0.3\n  SWIN:\n    DEPTHS: [2, 2, 6, 2]\n")
+    ns = argparse.Namespace(cfg=str(y), opts=["MODEL.DROP_PATH_RATE", "0.05", "MODEL.PRETRAIN_CKPT", "none.pth"], batch_size=8)
+    cfg = build_swin_config(ns)
+    assert cfg.MODEL.DROP_PATH_RATE == 0.05 and cfg.MODEL.SWIN.DEPTHS == [2, 2, 6, 2] and cfg.MODEL.PRETRAIN_CKPT == "none.pth"
+    with pytest.raises(SystemExit):
+        build_swin_config(argparse.Namespace(cfg=str(y), opts=["MODEL.NOPE", "1"], batch_size=8))
+    with pytest.raises(SystemExit):
+        build_swin_config(argparse.Namespace(cfg=str(tmp_path / "missing.yaml"), opts=None, batch_size=8))
