@@ -104,6 +104,13 @@ SIGNATURES = {
     "b200_ct_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _F, _P, _I, _S]),
     "b200_cps_loss_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
     "b200_cps_loss_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _L, _P, _F, _P, _I, _S]),
+    "b200_loss_dropin_workspace_bytes": (_L, [_I, _L]),
+    "b200_dice_fwd": (_I, [_P, _I, _P, _I, _I, _I, _L, _P, _P, _P, _L, _S]),
+    "b200_dice_bwd": (_I, [_P, _I, _P, _I, _I, _I, _L, _P, _P, _P, _P, _S]),
+    "b200_softmax_mse_fwd": (_I, [_P, _P, _I, _I, _L, _P, _S]),
+    "b200_softmax_mse_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _S]),
+    "b200_softmax_kl_fwd": (_I, [_P, _P, _I, _I, _L, _P, _P, _L, _S]),
+    "b200_softmax_kl_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _S]),
     "b200_linear_supported": (_I, [_L, _I, _I, _I]),
     "b200_linear_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _L, _I, _S]),
     "b200_linear_dgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _L, _I, _S]),

@@ -452,6 +452,45 @@ def sgd_ema_step(params, grads, momentum_buf, ema_params, hparams, zero_grad=Fal
               _pf(hparams), int(zero_grad), _st())
 
 
+# ------------------------------------------------------------------ stand-alone losses (utils/losses.py drop-ins)
+def loss_dropin_workspace_bytes(B, S) -> int:
+    return int(_lib.query("b200_loss_dropin_workspace_bytes", int(B), int(S)))
+
+
+def _label_dtype(labels):
+    if labels.dtype == torch.uint8:
+        return _lib.LABEL_U8
+    if labels.dtype == torch.int64:
+        return _lib.LABEL_I64
+    raise B200Error(f"labels must be uint8 or int64, got {labels.dtype}")
+
+
+def dice_fwd(x, use_softmax, labels, B, C_, S, weight, out, ws):
+    _lib.call("b200_dice_fwd", _pf(x), int(use_softmax), _p(labels), _label_dtype(labels), B, C_, S, _pf(weight), _pf(out), _p(ws),
+              ws.numel() * ws.element_size(), _st())
+
+
+def dice_bwd(x, use_softmax, labels, B, C_, S, weight, fwd_out, grad_out, dx):
+    _lib.call("b200_dice_bwd", _pf(x), int(use_softmax), _p(labels), _label_dtype(labels), B, C_, S, _pf(weight), _pf(fwd_out),
+              _pf(grad_out), _pf(dx), _st())
+
+
+def softmax_mse_fwd(a, b, B, C_, S, out):
+    _lib.call("b200_softmax_mse_fwd", _pf(a), _pf(b), B, C_, S, _pf(out), _st())
+
+
+def softmax_mse_bwd(a, b, grad_out, B, C_, S, da):
+    _lib.call("b200_softmax_mse_bwd", _pf(a), _pf(b), _pf(grad_out), B, C_, S, _pf(da), _st())
+
+
+def softmax_kl_fwd(a, b, B, C_, S, out, ws):
+    _lib.call("b200_softmax_kl_fwd", _pf(a), _pf(b), B, C_, S, _pf(out), _p(ws), ws.numel() * ws.element_size(), _st())
+
+
+def softmax_kl_bwd(a, b, grad_out, B, C_, S, da):
+    _lib.call("b200_softmax_kl_bwd", _pf(a), _pf(b), _pf(grad_out), B, C_, S, _pf(da), _st())
+
+
 def ema_update(ema_params, params, hparams):
     _lib.call("b200_ema_update", _pf(ema_params), _pf(params), params.numel(), _pf(hparams), _st())
 

@@ -297,6 +297,28 @@ int b200_cps_loss_bwd(const float* logits, int layout_nhwc, const float* other_l
  * hparams_dev (DEVICE, 6 floats): [0] lr [1] momentum [2] weight_decay [3] ema_alpha [4] 1-ema_alpha [5] grad_scale */
 int b200_sgd_ema_step(float* params, float* grads, float* momentum_buf, float* ema_params, long long n,
                       const float* hparams_dev, int zero_grad, cudaStream_t stream);
+/* Stand-alone losses behind the reference's own signatures (code/utils/losses.py:74-113,165-201), forward / backward
+ * halves for torch.autograd.Functions (cv_ssl_mis_b200/utils/losses.py).  Tensors [B][C][S] fp32, C <= 8.
+ *   dice:  out[0] = loss, out[1..1+C) = class-wise dice, out[9..33) = per-class (I, Z, Y) sums kept for the backward;
+ *          x = probabilities, or logits with use_softmax = 1; labels [B][S] uint8 / int64; weight[C] or NULL;
+ *   softmax_mse: element-wise (softmax(input) - softmax(target))^2, gradient to the input logits only;
+ *   softmax_kl:  F.kl_div(log_softmax(input), softmax(target), reduction='mean') (mean over all B*C*S elements).
+ * grad_out of dice / kl is a DEVICE scalar (the upstream gradient). */
+long long b200_loss_dropin_workspace_bytes(int B, long long S);
+int b200_dice_fwd(const float* x, int use_softmax, const void* labels, int label_dtype, int B, int C, long long S,
+                  const float* weight, float* out, void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b200_dice_bwd(const float* x, int use_softmax, const void* labels, int label_dtype, int B, int C, long long S,
+                  const float* weight, const float* fwd_out, const float* grad_out, float* dx, cudaStream_t stream);
+int b200_softmax_mse_fwd(const float* input_logits, const float* target_logits, int B, int C, long long S, float* out,
+                         cudaStream_t stream);
+int b200_softmax_mse_bwd(const float* input_logits, const float* target_logits, const float* grad_out, int B, int C,
+                         long long S, float* d_input, cudaStream_t stream);
+int b200_softmax_kl_fwd(const float* input_logits, const float* target_logits, int B, int C, long long S, float* out,
+                        void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b200_softmax_kl_bwd(const float* input_logits, const float* target_logits, const float* grad_out, int B, int C,
+                        long long S, float* d_input, cudaStream_t stream);
+/* teacher = alpha * teacher + (1 - alpha) * student with (alpha, 1 - alpha) read from hparams_dev[3], [4]
+ * (code/train_mean_teacher_2D.py:124-128 update_ema_variables) */
 int b200_ema_update(float* ema_params, const float* params, long long n, const float* hparams_dev, cudaStream_t stream);
 int b200_noise_add(const float* x, float* out, long long n, float sigma, float clip, unsigned long long seed,
                    const unsigned long long* seed_offset_dev, unsigned rng_stream, cudaStream_t stream);

@@ -886,6 +886,59 @@ def ema_update(ema_params, params, hparams):
         ema_params.mul_(float(hparams[3])).add_(params, alpha=float(hparams[4]))
 
 
+# ------------------------------------------------------------------ stand-alone losses (utils/losses.py drop-ins)
+def loss_dropin_workspace_bytes(B, S):
+    return 64
+
+
+def _dice_terms(x, use_softmax, labels, B, C, S):
+    p = x.reshape(B, C, S).double()
+    if use_softmax:
+        p = torch.softmax(p, dim=1)
+    t = F.one_hot(labels.reshape(B, S).long(), C).permute(0, 2, 1).double()
+    return p, t, (p * t).sum((0, 2)), (p * p).sum((0, 2)), (t * t).sum((0, 2))
+
+
+def dice_fwd(x, use_softmax, labels, B, C, S, weight, out, ws):
+    p, t, I, Z, Y = _dice_terms(x, use_softmax, labels, B, C, S)
+    d = 1 - (2 * I + 1e-5) / (Z + Y + 1e-5)
+    w = torch.ones(C, dtype=torch.float64) if weight is None else weight.double()
+    out.zero_()
+    out[0] = float((d * w).sum() / C)
+    out[1:1 + C] = (1 - d).float()
+    out[9:9 + C], out[17:17 + C], out[25:25 + C] = I.float(), Z.float(), Y.float()
+
+
+def dice_bwd(x, use_softmax, labels, B, C, S, weight, fwd_out, grad_out, dx):
+    p, t, I, Z, Y = _dice_terms(x, use_softmax, labels, B, C, S)
+    w = (torch.ones(C, dtype=torch.float64) if weight is None else weight.double()) / C
+    N, D = (2 * I + 1e-5).view(1, C, 1), (Z + Y + 1e-5).view(1, C, 1)
+    g = -w.view(1, C, 1) * (2 * t * D - N * 2 * p) / (D * D)
+    if use_softmax:
+        g = p * (g - (p * g).sum(1, keepdim=True))
+    dx.copy_((g * float(grad_out.reshape(-1)[0])).float().reshape(dx.shape))
+
+
+def softmax_mse_fwd(a, b, B, C, S, out):
+    out.copy_(((torch.softmax(a.reshape(B, C, S), 1) - torch.softmax(b.reshape(B, C, S), 1)) ** 2).reshape(out.shape))
+
+
+def softmax_mse_bwd(a, b, grad_out, B, C, S, da):
+    pa, pb = torch.softmax(a.reshape(B, C, S).double(), 1), torch.softmax(b.reshape(B, C, S).double(), 1)
+    q = 2 * (pa - pb) * grad_out.reshape(B, C, S).double()
+    da.copy_((pa * (q - (pa * q).sum(1, keepdim=True))).float().reshape(da.shape))
+
+
+def softmax_kl_fwd(a, b, B, C, S, out, ws):
+    la, lb = torch.log_softmax(a.reshape(B, C, S).double(), 1), torch.log_softmax(b.reshape(B, C, S).double(), 1)
+    out[0] = float((lb.exp() * (lb - la)).mean())
+
+
+def softmax_kl_bwd(a, b, grad_out, B, C, S, da):
+    pa, pb = torch.softmax(a.reshape(B, C, S).double(), 1), torch.softmax(b.reshape(B, C, S).double(), 1)
+    da.copy_(((pa - pb) * float(grad_out.reshape(-1)[0]) / (B * C * S)).float().reshape(da.shape))
+
+
 def noise_add(x, out, sigma, clip, seed, seed_off=None, rng_stream=0):
     s = seed + (int(seed_off.item()) if seed_off is not None else 0)
     nz = torch.from_numpy(philox.clamp_noise(s, rng_stream, out.numel(), sigma, clip)).reshape(out.shape)

@@ -105,6 +105,47 @@ def losses_fixture():
     print("losses: ", {k: float(v["total"]) for k, v in out.items()})
 
 
+def losses_dropin_fixture():
+    """The stand-alone entry points of code/utils/losses.py driven the way the reference trainers drive them, plus
+    `update_ema_variables` (code/train_mean_teacher_2D.py:124-128, restated: the script itself needs tensorboardX/medpy
+    at import) -- checked by tests/test_losses_dropin_gpu.py against cv_ssl_mis_b200/utils/losses.py."""
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for name, (B, C, shape, dt) in {"2d": (3, 4, (12, 20), torch.uint8), "3d": (2, 2, (6, 8, 10), torch.int64)}.items():
+        logits = torch.randn(B, C, *shape, generator=g, requires_grad=True)
+        tlogits = torch.randn(B, C, *shape, generator=g)
+        y = torch.randint(0, C, (B, *shape), generator=g).to(dt)
+        weight = [0.5 + 0.25 * i for i in range(C)]
+        dl = ref_losses.DiceLoss(C)
+        dice_sm = dl(logits, y.unsqueeze(1), weight=weight, softmax=True)                       # logits in, softmax inside
+        (g_dice_sm,) = torch.autograd.grad(1.7 * dice_sm, logits)
+        probs = torch.softmax(logits.detach(), dim=1).requires_grad_(True)
+        dice_p = dl(probs, y.unsqueeze(1))                                                      # probabilities in (:214-215)
+        (g_dice_p,) = torch.autograd.grad(dice_p, probs)
+        mse = ref_losses.softmax_mse_loss(logits, tlogits)                                      # element-wise
+        up = torch.rand(mse.shape, generator=g)
+        (g_mse,) = torch.autograd.grad((mse * up).sum(), logits)
+        with __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            kl = ref_losses.softmax_kl_loss(logits, tlogits)                                    # scalar, reduction='mean'
+        (g_kl,) = torch.autograd.grad(0.3 * kl, logits)
+        out[name] = dict(logits=logits.detach(), teacher=tlogits, y=y, weight=weight, dice_sm=dice_sm.detach(), g_dice_sm=g_dice_sm,
+                         probs=probs.detach(), dice_p=dice_p.detach(), g_dice_p=g_dice_p, mse=mse.detach(), up=up, g_mse=g_mse,
+                         kl=kl.detach(), g_kl=g_kl)
+    # update_ema_variables, three consecutive global steps on a small parameter list
+    student = [torch.randn(5, 3, generator=g), torch.randn(7, generator=g)]
+    teacher = [torch.randn(5, 3, generator=g), torch.randn(7, generator=g)]
+    ema = dict(student=[t.clone() for t in student], teacher0=[t.clone() for t in teacher], alpha=0.99, steps=[0, 1, 250], teacher=[])
+    for step in ema["steps"]:
+        alpha = min(1 - 1 / (step + 1), 0.99)                                                   # :126
+        for ema_param, param in zip(teacher, student):
+            ema_param.mul_(alpha).add_(param, alpha=1 - alpha)                                  # :127-128
+        ema["teacher"].append([t.clone() for t in teacher])
+    out["ema"] = ema
+    torch.save(out, os.path.join(HERE, "losses_dropin.pt"))
+    print("losses_dropin:", {k: (float(v["dice_sm"]), float(v["kl"])) for k, v in out.items() if k != "ema"})
+
+
 def ramps_fixture():
     pts = [(0, 200), (1, 200), (6, 200.0), (50, 200.0), (199, 200), (200, 200), (500, 200), (3, 0), (10, 40.0)]
     vals = [ref_ramps.sigmoid_rampup(c, l) for c, l in pts]
@@ -272,12 +313,20 @@ def _install_timm_shim(keep_source):
     probability, identity in eval mode.  The keep draws come from `keep_source(module_index, call_index, batch)` so the
     CUDA path's Philox draws can be replayed through the reference's own block code."""
     import types
+    global _TIMM_SHIM
+    if _TIMM_SHIM is not None:
+        # the reference's Swin module was imported against the first shim's DropPath class: keep that class and only
+        # swap its draw source (a second class would never be seen by the already-imported module)
+        _TIMM_SHIM.keep_source = staticmethod(keep_source)
+        _TIMM_SHIM.count = 0
+        return _TIMM_SHIM
     timm = types.ModuleType("timm")
     models = types.ModuleType("timm.models")
     layers = types.ModuleType("timm.models.layers")
 
     class DropPath(torch.nn.Module):
         count = 0
+        keep_source = None
 
         def __init__(self, drop_prob=0.0):
             super().__init__()
@@ -288,16 +337,20 @@ def _install_timm_shim(keep_source):
             call, self.calls = self.calls, self.calls + 1
             if self.drop_prob == 0.0 or not self.training:
                 return x
-            keep = keep_source(self.index, call, x.shape[0], self.drop_prob)
+            keep = DropPath.keep_source(self.index, call, x.shape[0], self.drop_prob)
             return x * (keep / (1.0 - self.drop_prob)).view(-1, *([1] * (x.dim() - 1)))
 
+    DropPath.keep_source = staticmethod(keep_source)
     layers.DropPath = DropPath
     layers.to_2tuple = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)
     layers.trunc_normal_ = torch.nn.init.trunc_normal_
     timm.models, models.layers = models, layers
     sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+    _TIMM_SHIM = DropPath
     return DropPath
 
+
+_TIMM_SHIM = None
 
 SWIN_SMALL = dict(img_size=64, patch_size=4, in_chans=3, embed_dim=32, depths=(2, 2, 2, 2), num_heads=(1, 2, 4, 8),
                   window_size=4, mlp_ratio=4.0, qkv_bias=True, drop_path_rate=0.2, patch_norm=True)
@@ -655,7 +708,8 @@ def uamt2d_fixture():
 
 
 if __name__ == "__main__":
-    fixtures = dict(uamt2d=uamt2d_fixture, mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
+    fixtures = dict(uamt2d=uamt2d_fixture, mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture,
+                    losses_dropin=losses_dropin_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
                     vnet=vnet_fixture, swin=swin_fixture, cps_ict=cps_ict_fixture)
     for name in (sys.argv[1:] or list(fixtures)):
         fixtures[name]()

@@ -208,8 +208,13 @@ def test_swin_cross_teaching_matches_reference_fixture(golden, monkeypatch):
     for n, p in unet.named_parameters():
         want = g["grad_norm1"][n]
         assert abs(float(p.grad.norm()) - want) <= 1e-2 * want + 1e-6, (n, float(p.grad.norm()), want)
-    torch.testing.assert_close(swin.swin_unet.layers[0].blocks[1].attn.relative_position_bias_table.grad.cpu(), g["table_grad"],
-                               rtol=5e-3, atol=1e-6)
+    # the bias-table gradient is tiny in absolute terms (max |.| ~ 1.7e-7 in this fixture), so a fixed atol would make
+    # the check vacuous: compare relative to the fixture's own scale
+    tg = swin.swin_unet.layers[0].blocks[1].attn.relative_position_bias_table.grad.cpu()
+    scale = float(g["table_grad"].abs().max())
+    assert scale > 0
+    assert float((tg - g["table_grad"]).abs().max()) <= 2e-2 * scale, (float((tg - g["table_grad"]).abs().max()), scale)
+    assert abs(float(tg.norm()) - float(g["table_grad"].norm())) <= 5e-3 * float(g["table_grad"].norm())
     for flat, mom in zip(tr.flats, tr.momentum_bufs):
         ops.sgd_ema_step(flat.data, flat.grad, mom, None, tr.hp)
     torch.testing.assert_close(swin.swin_unet.output.weight.detach().cpu(), g["out_w2"], rtol=1e-4, atol=1e-6)
