@@ -147,7 +147,8 @@ _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`
 
 # optional per-call device timing (bench.py / profiling only): when `profile` is a list, every call is
-# bracketed by CUDA events on the current stream and (entry point, tag, start, end) is appended to it
+# bracketed by CUDA events on the current stream and (entry point, tag, start, end, (algorithmic bytes, flops) or None)
+# is appended to it
 profile = None
 tag = ""
 
@@ -182,7 +183,8 @@ def call(name: str, *args):
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        profile.append((name, tag, e0, e1))
+        from . import _costs
+        profile.append((name, tag, e0, e1, _costs.cost_of(name, args)))
     else:
         rc = getattr(lib, name)(*args)
     if name in _NON_STATUS or SIGNATURES[name][0] is not _I:

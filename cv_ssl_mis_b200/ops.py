@@ -457,14 +457,6 @@ def loss_dropin_workspace_bytes(B, S) -> int:
     return int(_lib.query("b200_loss_dropin_workspace_bytes", int(B), int(S)))
 
 
-def _label_dtype(labels):
-    if labels.dtype == torch.uint8:
-        return _lib.LABEL_U8
-    if labels.dtype == torch.int64:
-        return _lib.LABEL_I64
-    raise B200Error(f"labels must be uint8 or int64, got {labels.dtype}")
-
-
 def dice_fwd(x, use_softmax, labels, B, C_, S, weight, out, ws):
     _lib.call("b200_dice_fwd", _pf(x), int(use_softmax), _p(labels), _label_dtype(labels), B, C_, S, _pf(weight), _pf(out), _p(ws),
               ws.numel() * ws.element_size(), _st())
