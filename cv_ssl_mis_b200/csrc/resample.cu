@@ -89,75 +89,93 @@ __device__ __forceinline__ void bil_src(int o, float scale, int in, int& i0, int
     l0 = 1.f - l1;
 }
 
+// One block per (n, output row, segment of the row): the row's vertical source rows / weights are block-uniform, the
+// horizontal ones are computed once per thread (no 64-bit divisions, no per-element index decoding); the four taps of
+// neighbouring outputs overlap, so the low-resolution rows are served by L1/L2 and HBM sees x once and y once.
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
                                                              int H, int W, int C, float sh, float sw) {
     const int CQ = C >> 2, OH = 2 * H, OW = 2 * W;
-    const long long total = (long long)N * OH * OW * CQ;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(q % CQ);
-        long long r = q / CQ;
-        const int ow = (int)(r % OW); r /= OW;
-        const int oh = (int)(r % OH);
-        const int n = (int)(r / OH);
-        int h0, h1, w0, w1;
-        float lh0, lh1, lw0, lw1;
-        bil_src(oh, sh, H, h0, h1, lh0, lh1);
+    const int rowq = OW * CQ;                                   // float4 elements of one output row
+    const int row = blockIdx.x;                                 // n * OH + oh
+    const int n = row / OH, oh = row - n * OH;
+    int h0, h1;
+    float lh0, lh1;
+    bil_src(oh, sh, H, h0, h1, lh0, lh1);
+    const float* r0 = x + ((long long)n * H + h0) * W * C;
+    const float* r1 = x + ((long long)n * H + h1) * W * C;
+    float* yo = y + (long long)row * OW * C;
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < rowq; q += gridDim.y * blockDim.x) {
+        const int ow = q / CQ, cq = q - ow * CQ;
+        int w0, w1;
+        float lw0, lw1;
         bil_src(ow, sw, W, w0, w1, lw0, lw1);
-        const float* b = x + (long long)n * H * W * C + cq * 4;
-        const float4 v00 = ldg4(b + ((long long)h0 * W + w0) * C), v01 = ldg4(b + ((long long)h0 * W + w1) * C);
-        const float4 v10 = ldg4(b + ((long long)h1 * W + w0) * C), v11 = ldg4(b + ((long long)h1 * W + w1) * C);
+        const float4 v00 = ldg4(r0 + w0 * C + cq * 4), v01 = ldg4(r0 + w1 * C + cq * 4);
+        const float4 v10 = ldg4(r1 + w0 * C + cq * 4), v11 = ldg4(r1 + w1 * C + cq * 4);
         float4 o;
         o.x = lh0 * (lw0 * v00.x + lw1 * v01.x) + lh1 * (lw0 * v10.x + lw1 * v11.x);
         o.y = lh0 * (lw0 * v00.y + lw1 * v01.y) + lh1 * (lw0 * v10.y + lw1 * v11.y);
         o.z = lh0 * (lw0 * v00.z + lw1 * v01.z) + lh1 * (lw0 * v10.z + lw1 * v11.z);
         o.w = lh0 * (lw0 * v00.w + lw1 * v01.w) + lh1 * (lw0 * v10.w + lw1 * v11.w);
-        stg4(y + q * 4, o);
+        stg4(yo + q * 4, o);
     }
 }
 
-// gather form of the transpose (deterministic, no atomics): every low-res pixel sums the <= 4x4 high-res
-// pixels whose interpolation footprint touches it.
+// gather form of the transpose (deterministic, no atomics): every low-res pixel sums the <= 6 x 6 high-res pixels whose
+// interpolation footprint touches it, in a fixed order.  One block per (n, low-res row, segment): the vertical weights
+// of the candidate output rows are block-uniform (shared memory), the horizontal ones are computed once per thread --
+// not once per (row, column) pair as before (49 source-index evaluations per element).
+constexpr int UPS_K = 7;      // candidate outputs per dimension: src = scale * o in (h - 1, h + 1), scale ~ 1/2, +-1 slack
+
+__device__ __forceinline__ void ups_candidates(int i, float scale, int in, int out, int& lo, float (&wt)[UPS_K]) {
+    lo = scale > 0.f ? (int)floorf((float)(i - 1) / scale) - 1 : 0;
+    int hi = scale > 0.f ? (int)ceilf((float)(i + 1) / scale) + 1 : out - 1;
+    lo = max(lo, 0);
+    hi = min(hi, out - 1);
+#pragma unroll
+    for (int k = 0; k < UPS_K; ++k) {
+        const int o = lo + k;
+        float w = 0.f;
+        if (o <= hi) {
+            int i0, i1;
+            float l0, l1;
+            bil_src(o, scale, in, i0, i1, l0, l1);
+            if (i0 == i) w += l0;
+            if (i1 == i) w += l1;
+        }
+        wt[k] = w;
+    }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N,
                                                              int H, int W, int C, float sh, float sw, int accumulate) {
     const int CQ = C >> 2, OH = 2 * H, OW = 2 * W;
-    const long long total = (long long)N * H * W * CQ;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(q % CQ);
-        long long r = q / CQ;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H);
-        const int n = (int)(r / H);
-        // candidate output rows/cols: src = scale*o in (h-1, h+1)
-        int oh_lo = sh > 0.f ? (int)floorf((float)(h - 1) / sh) - 1 : 0;
-        int oh_hi = sh > 0.f ? (int)ceilf((float)(h + 1) / sh) + 1 : OH - 1;
-        int ow_lo = sw > 0.f ? (int)floorf((float)(w - 1) / sw) - 1 : 0;
-        int ow_hi = sw > 0.f ? (int)ceilf((float)(w + 1) / sw) + 1 : OW - 1;
-        oh_lo = max(oh_lo, 0); ow_lo = max(ow_lo, 0);
-        oh_hi = min(oh_hi, OH - 1); ow_hi = min(ow_hi, OW - 1);
+    const int rowq = W * CQ;
+    const int row = blockIdx.x;                                 // n * H + h
+    const int n = row / H, h = row - n * H;
+    int oh_lo;
+    float wh[UPS_K];
+    ups_candidates(h, sh, H, OH, oh_lo, wh);
+    const float* b = dy + (long long)n * OH * OW * C;
+    float* dxo = dx + (long long)row * W * C;
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < rowq; q += gridDim.y * blockDim.x) {
+        const int w = q / CQ, cq = q - w * CQ;
+        int ow_lo;
+        float ww[UPS_K];
+        ups_candidates(w, sw, W, OW, ow_lo, ww);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* b = dy + (long long)n * OH * OW * C + cq * 4;
-        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-            int h0, h1;
-            float lh0, lh1;
-            bil_src(oh, sh, H, h0, h1, lh0, lh1);
-            float wh = 0.f;
-            if (h0 == h) wh += lh0;
-            if (h1 == h) wh += lh1;
-            if (wh == 0.f) continue;
-            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-                int w0, w1;
-                float lw0, lw1;
-                bil_src(ow, sw, W, w0, w1, lw0, lw1);
-                float ww = 0.f;
-                if (w0 == w) ww += lw0;
-                if (w1 == w) ww += lw1;
-                if (ww == 0.f) continue;
-                const float4 g = ldg4(b + ((long long)oh * OW + ow) * C);
-                const float f = wh * ww;
+#pragma unroll
+        for (int i = 0; i < UPS_K; ++i) {
+            if (wh[i] == 0.f) continue;
+            const float* br = b + ((long long)(oh_lo + i) * OW) * C + cq * 4;
+#pragma unroll
+            for (int j = 0; j < UPS_K; ++j) {
+                if (ww[j] == 0.f) continue;
+                const float4 g = ldg4(br + (ow_lo + j) * C);
+                const float f = wh[i] * ww[j];
                 acc.x += f * g.x; acc.y += f * g.y; acc.z += f * g.z; acc.w += f * g.w;
             }
         }
-        float* d = dx + q * 4;
+        float* d = dxo + q * 4;
         if (accumulate) {
             const float4 old = *reinterpret_cast<const float4*>(d);
             acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
@@ -288,16 +306,17 @@ static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1)
 
 B200_API int b200_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, cudaStream_t st) {
     B200_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample2x_fwd: bad arguments");
-    upsample2x_fwd_kernel<<<ew_grid((long long)N * 4 * H * W * (C / 4)), 256, 0, st>>>(x, y, N, H, W, C, ac_scale(H, 2 * H),
-                                                                                      ac_scale(W, 2 * W));
+    const int rowq = 2 * W * (C / 4);
+    upsample2x_fwd_kernel<<<dim3(N * 2 * H, (rowq + 1023) / 1024), 256, 0, st>>>(x, y, N, H, W, C, ac_scale(H, 2 * H), ac_scale(W, 2 * W));
     B200_CHECK_LAUNCH("upsample2x_fwd");
     return B200_OK;
 }
 
 B200_API int b200_upsample2x_bwd(const float* dy, float* dx, int N, int H, int W, int C, int accumulate, cudaStream_t st) {
     B200_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample2x_bwd: bad arguments");
-    upsample2x_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, st>>>(dy, dx, N, H, W, C, ac_scale(H, 2 * H),
-                                                                                  ac_scale(W, 2 * W), accumulate);
+    const int rowq = W * (C / 4);
+    upsample2x_bwd_kernel<<<dim3(N * H, (rowq + 511) / 512), 256, 0, st>>>(dy, dx, N, H, W, C, ac_scale(H, 2 * H), ac_scale(W, 2 * W),
+                                                                           accumulate);
     B200_CHECK_LAUNCH("upsample2x_bwd");
     return B200_OK;
 }
