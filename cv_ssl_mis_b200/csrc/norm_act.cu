@@ -184,6 +184,22 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __re
 }
 
 // ---------------------------------------------------------------- elementwise sweeps
+// Both sweeps are pure HBM streams.  The grid-stride (blocks * 256 float4) is a multiple of C / 4 whenever C / 4 divides
+// 256 (every channel count of the reference networks), so a thread keeps the SAME four channels for its whole life:
+// the per-channel constants are loaded once, and each trip issues U independent 16-byte loads before the first use
+// (one outstanding load per thread caps a 2048-thread SM near 4 TB/s; measured 3.7 -> see profiles/).
+constexpr int EW_U = 4;
+
+__device__ __forceinline__ void drop_keep(bool (&keep)[4], int drop_mode, unsigned long long seed, unsigned stream, long long q,
+                                          int CQ, int cq, int C, long long spatial, float p_drop) {
+    keep[0] = keep[1] = keep[2] = keep[3] = true;
+    if (drop_mode == 1) dropout_keep4(seed, stream, (unsigned long long)q, p_drop, keep);
+    else if (drop_mode == 2) {
+        const long long m = q / CQ;
+        dropout_keep4(seed, stream, (unsigned long long)(((m / spatial) * C + cq * 4) >> 2), p_drop, keep);
+    }
+}
+
 // forward: a = dropout(act(y * scale + shift))
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ state,
                                                          float* __restrict__ a, long long total4, int C, float slope,
@@ -193,23 +209,36 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     if (seed_off) seed += *seed_off;
     const float keep_scale = drop_mode != 0 ? 1.f / (1.f - p_drop) : 1.f;
     const int CQ = C >> 2;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(q % CQ);
-        const float4 sc = ldg4(BN_SCALE(state, C) + cq * 4), sh = ldg4(BN_SHIFT(state, C) + cq * 4);
-        const float4 v = ldg4_stream(y + q * 4);
-        float z[4] = {v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w};
-        bool keep[4] = {true, true, true, true};
-        if (drop_mode == 1) dropout_keep4(seed, stream, (unsigned long long)q, p_drop, keep);
-        else if (drop_mode == 2) {
-            const long long m = q / CQ;
-            dropout_keep4(seed, stream, (unsigned long long)(((m / spatial) * C + cq * 4) >> 2), p_drop, keep);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool fixed = (stride % CQ) == 0;                  // this thread always sees the same four channels
+    int cq = (int)(q0 % CQ);
+    float4 sc = ldg4(BN_SCALE(state, C) + cq * 4), sh = ldg4(BN_SHIFT(state, C) + cq * 4);
+    for (long long qb = q0; qb < total4; qb += EW_U * stride) {
+        float4 v[EW_U];
+#pragma unroll
+        for (int u = 0; u < EW_U; ++u) {
+            const long long q = qb + u * stride;
+            if (q < total4) v[u] = ldg4_stream(y + q * 4);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float r = z[i] > 0.f ? z[i] : z[i] * slope;
-            z[i] = keep[i] ? r * keep_scale : 0.f;
+        for (int u = 0; u < EW_U; ++u) {
+            const long long q = qb + u * stride;
+            if (q >= total4) break;
+            if (!fixed) {
+                cq = (int)(q % CQ);
+                sc = ldg4(BN_SCALE(state, C) + cq * 4); sh = ldg4(BN_SHIFT(state, C) + cq * 4);
+            }
+            float z[4] = {v[u].x * sc.x + sh.x, v[u].y * sc.y + sh.y, v[u].z * sc.z + sh.z, v[u].w * sc.w + sh.w};
+            bool keep[4];
+            drop_keep(keep, drop_mode, seed, stream, q, CQ, cq, C, spatial, p_drop);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float r = z[i] > 0.f ? z[i] : z[i] * slope;
+                z[i] = keep[i] ? r * keep_scale : 0.f;
+            }
+            stg4(a + q * 4, make_float4(z[0], z[1], z[2], z[3]));
         }
-        stg4(a + q * 4, make_float4(z[0], z[1], z[2], z[3]));
     }
 }
 
@@ -223,32 +252,49 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict
     if (seed_off) seed += *seed_off;
     const float keep_scale = drop_mode != 0 ? 1.f / (1.f - p_drop) : 1.f;
     const int CQ = C >> 2;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(q % CQ);
-        const float4 sc4 = ldg4(BN_SCALE(state, C) + cq * 4), sh4 = ldg4(BN_SHIFT(state, C) + cq * 4);
-        const float4 mu4 = ldg4(BN_MEAN(state, C) + cq * 4), is4 = ldg4(BN_INVSTD(state, C) + cq * 4);
-        const float4 c14 = ldg4(coef + cq * 4), c24 = ldg4(coef + C + cq * 4);
-        const float4 v = ldg4_stream(y + q * 4), gv = ldg4_stream(da + q * 4);
-        const float a[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
-        const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-        const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, is[4] = {is4.x, is4.y, is4.z, is4.w};
-        const float c1[4] = {c14.x, c14.y, c14.z, c14.w}, c2[4] = {c24.x, c24.y, c24.z, c24.w};
-        bool keep[4] = {true, true, true, true};
-        if (drop_mode == 1) dropout_keep4(seed, stream, (unsigned long long)q, p_drop, keep);
-        else if (drop_mode == 2) {
-            const long long m = q / CQ;
-            dropout_keep4(seed, stream, (unsigned long long)(((m / spatial) * C + cq * 4) >> 2), p_drop, keep);
-        }
-        float o[4];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool fixed = (stride % CQ) == 0;
+    int cq = (int)(q0 % CQ);
+    float sc[4], sh[4], mu[4], is[4], c1[4], c2[4];
+    auto load_consts = [&](int c) {
+        const float4 sc4 = ldg4(BN_SCALE(state, C) + c * 4), sh4 = ldg4(BN_SHIFT(state, C) + c * 4);
+        const float4 mu4 = ldg4(BN_MEAN(state, C) + c * 4), is4 = ldg4(BN_INVSTD(state, C) + c * 4);
+        const float4 c14 = ldg4(coef + c * 4), c24 = ldg4(coef + C + c * 4);
+        sc[0] = sc4.x; sc[1] = sc4.y; sc[2] = sc4.z; sc[3] = sc4.w;
+        sh[0] = sh4.x; sh[1] = sh4.y; sh[2] = sh4.z; sh[3] = sh4.w;
+        mu[0] = mu4.x; mu[1] = mu4.y; mu[2] = mu4.z; mu[3] = mu4.w;
+        is[0] = is4.x; is[1] = is4.y; is[2] = is4.z; is[3] = is4.w;
+        c1[0] = c14.x; c1[1] = c14.y; c1[2] = c14.z; c1[3] = c14.w;
+        c2[0] = c24.x; c2[1] = c24.y; c2[2] = c24.z; c2[3] = c24.w;
+    };
+    load_consts(cq);
+    for (long long qb = q0; qb < total4; qb += EW_U * stride) {
+        float4 v[EW_U], gv[EW_U];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float z = a[i] * sc[i] + sh[i];
-            float gz = keep[i] ? gg[i] * keep_scale : 0.f;
-            gz = z > 0.f ? gz : gz * slope;
-            const float xhat = (a[i] - mu[i]) * is[i];
-            o[i] = sc[i] * (gz - c1[i] - xhat * c2[i]);
+        for (int u = 0; u < EW_U; ++u) {
+            const long long q = qb + u * stride;
+            if (q < total4) { v[u] = ldg4_stream(y + q * 4); gv[u] = ldg4_stream(da + q * 4); }
         }
-        stg4(dy + q * 4, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int u = 0; u < EW_U; ++u) {
+            const long long q = qb + u * stride;
+            if (q >= total4) break;
+            if (!fixed) { cq = (int)(q % CQ); load_consts(cq); }
+            const float a[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+            bool keep[4];
+            drop_keep(keep, drop_mode, seed, stream, q, CQ, cq, C, spatial, p_drop);
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float z = a[i] * sc[i] + sh[i];
+                float gz = keep[i] ? gg[i] * keep_scale : 0.f;
+                gz = z > 0.f ? gz : gz * slope;
+                const float xhat = (a[i] - mu[i]) * is[i];
+                o[i] = sc[i] * (gz - c1[i] - xhat * c2[i]);
+            }
+            stg4(dy + q * 4, make_float4(o[0], o[1], o[2], o[3]));
+        }
     }
 }
 
@@ -274,6 +320,12 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ m
 static inline int ew_grid(long long work) {
     long long blocks = (work + 255) / 256;
     long long cap = (long long)b200_num_sms() * 16;
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+// the unrolled sweeps: one resident wave (8 blocks of 256 threads per SM), EW_U float4 per thread and trip
+static inline int sweep_grid(long long total4) {
+    long long blocks = (total4 + 256 * EW_U - 1) / (256 * EW_U);
+    long long cap = (long long)b200_num_sms() * 8;
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
@@ -333,7 +385,7 @@ B200_API int b200_bn_act_fwd(const float* y, const float* state, float* a, long 
     B200_REQUIRE(drop_mode >= 0 && drop_mode <= 2 && p_drop >= 0.f && p_drop < 1.f, "bn_act_fwd: bad dropout arguments");
     if (p_drop == 0.f) drop_mode = 0;
     const long long total4 = M * (C >> 2);
-    bn_act_fwd_kernel<<<ew_grid(total4), 256, 0, st>>>(y, state, a, total4, C, slope, p_drop, drop_mode, seed, stream,
+    bn_act_fwd_kernel<<<sweep_grid(total4), 256, 0, st>>>(y, state, a, total4, C, slope, p_drop, drop_mode, seed, stream,
                                                        spatial > 0 ? spatial : 1, seed_offset_dev);
     B200_CHECK_LAUNCH("bn_act_fwd");
     return B200_OK;
@@ -359,7 +411,7 @@ B200_API int b200_bn_act_bwd(const float* y, const float* da, const float* state
     bn_bwd_finalize_kernel<<<C, 256, 0, st>>>(part, grid, M, C, dgamma, dbeta, accumulate, coef);
     B200_CHECK_LAUNCH("bn_bwd_finalize");
     const long long total4 = M * (C >> 2);
-    bn_act_bwd_kernel<<<ew_grid(total4), 256, 0, st>>>(y, da, state, coef, dy, total4, C, slope, p_drop, drop_mode, seed,
+    bn_act_bwd_kernel<<<sweep_grid(total4), 256, 0, st>>>(y, da, state, coef, dy, total4, C, slope, p_drop, drop_mode, seed,
                                                        stream, spatial, seed_offset_dev);
     B200_CHECK_LAUNCH("bn_act_bwd_apply");
     return B200_OK;
