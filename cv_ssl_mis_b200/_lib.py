@@ -75,6 +75,11 @@ SIGNATURES = {
     "b200_conv_row_stats_blocks": (_L, [_D]),
     "b200_conv_row_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
     "b200_conv_row_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_conv_blk_supported": (_I, [_D, _I]),
+    "b200_conv_blk_stats_blocks": (_L, [_D]),
+    "b200_conv_blk_pack_weights": (_I, [_P, _P, _I, _I, _I, _S]),
+    "b200_conv_blk_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
+    "b200_conv_blk_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_bn_finalize": (_I, [_P, _I, _L, _I, _P, _P, _F, _F, _P, _P, _P, _S]),
     "b200_conv_pack_batch": (_I, [_P, _I, _I, _S]),
     "b200_conv_c1_supported": (_I, [_D]),
@@ -141,7 +146,7 @@ SIGNATURES = {
 
 # entry points whose int return value is NOT a status code
 _NON_STATUS = {"b200_abi_version", "b200_device_sm", "b200_conv_tile_supported", "b200_conv_umma_supported",
-               "b200_conv_c1_supported", "b200_linear_supported", "b200_conv_row_wgrad_supported", "b200_conv_row_supported"}
+               "b200_conv_c1_supported", "b200_linear_supported", "b200_conv_row_wgrad_supported", "b200_conv_row_supported", "b200_conv_blk_supported"}
 
 _lib = None
 launch_count = 0         # number of status-returning (kernel-launching) calls made through `call`

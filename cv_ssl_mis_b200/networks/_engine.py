@@ -131,7 +131,7 @@ class ConvLayer:
                      and self.cout >= 32 and self.cin >= 32 and ops.linear_supported(self.M, self.cout, c0, c1))
         if self.gemm:
             self.umma_fwd = self.umma_dgrad = self.use_c1_kernel = self.tile_fwd = self.tile_dgrad = self.tile_wgrad = self.row_wgrad = False
-            self.row_fwd = self.row_dgrad = False
+            self.row_fwd = self.row_dgrad = self.blk_fwd = self.blk_dgrad = False
             self.wp_fwd = self.wp_bwd = None
             if need_grad:
                 rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(self.M, self.cout, self.cin),
@@ -147,9 +147,15 @@ class ConvLayer:
         want_row = is_conv and not rt.exact and os.environ.get("B200_CONV_ROW", "1") != "0"
         self.row_fwd = ops.conv_row_supported(self.desc, False) if (want_row and not self.out_nchw) else 0     # 8 + pack mode, or 0
         self.row_dgrad = ops.conv_row_supported(self.desc, True) if (want_row and need_grad) else 0
+        # narrow images (the 64^2 / 32^2 / 16^2 levels): halo-block tcgen05 kernel (TMA halo planes, all accumulator
+        # blocks of an item in TMEM, statistics in the epilogue).  B200_CONV_BLK=0 keeps conv_umma2 for A/B runs.
+        want_blk = want_row and os.environ.get("B200_CONV_BLK", "1") != "0"
+        self.blk_fwd = want_blk and not self.row_fwd and not self.out_nchw and ops.conv_blk_supported(self.desc, False)
+        self.blk_dgrad = want_blk and need_grad and not self.row_dgrad and ops.conv_blk_supported(self.desc, True)
         self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False) and not self.row_fwd
-                         and (self.out_nchw or self.cout % 4 == 0))
-        self.umma_dgrad = want_umma and wide and ops.conv_umma_supported(self.desc, True) and not self.row_dgrad
+                         and not self.blk_fwd and (self.out_nchw or self.cout % 4 == 0))
+        self.umma_dgrad = (want_umma and wide and ops.conv_umma_supported(self.desc, True) and not self.row_dgrad
+                           and not self.blk_dgrad)
         self.use_c1_kernel = is_conv and not rt.exact and ops.conv_c1_supported(self.desc)       # first layer: FFMA kernels
         self.tile_fwd = is_conv and not rt.exact and ops.conv_tile_supported(self.desc, False)
         self.tile_dgrad = self.tile_fwd and self.cout % 4 == 0 and c0 % 2 == 0 and c1 % 2 == 0
@@ -158,10 +164,10 @@ class ConvLayer:
         self.row_wgrad = (is_conv and not rt.exact and need_grad and os.environ.get("B200_WGRAD", "row") == "row"
                           and ops.conv_row_wgrad_supported(self.desc))
         fwd_mode = PACK_CONV_FWD if is_conv else PACK_DECONV_FWD
-        if self.row_fwd and self.has_act:
-            self.stats_blocks = ops.conv_row_stats_blocks(self.desc)
+        if (self.row_fwd or self.blk_fwd) and self.has_act:
+            self.stats_blocks = ops.conv_row_stats_blocks(self.desc) if self.row_fwd else ops.conv_blk_stats_blocks(self.desc)
             rt.need_scratch(self.stats_blocks * 2 * self.cout * 8)
-        nfwd = (ops.conv_row_packed_floats(self.desc, False) if self.row_fwd else
+        nfwd = (ops.conv_row_packed_floats(self.desc, False) if self.row_fwd else 9 * O * I if self.blk_fwd else
                 ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
                 ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
         self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
@@ -178,7 +184,7 @@ class ConvLayer:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            nbwd = (ops.conv_row_packed_floats(self.desc, True) if self.row_dgrad else
+            nbwd = (ops.conv_row_packed_floats(self.desc, True) if self.row_dgrad else 9 * O * I if self.blk_dgrad else
                     ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
                     ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
@@ -193,6 +199,8 @@ class ConvLayer:
         if not self.use_c1_kernel:
             if self.row_fwd:
                 jobs.append((w, self.wp_fwd, 3, self.row_fwd - 8, O, I, T))
+            elif self.blk_fwd:
+                jobs.append((w, self.wp_fwd, 3, 0, O, I, T))
             elif self.umma_fwd:
                 jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
             elif self.tile_fwd:
@@ -202,6 +210,8 @@ class ConvLayer:
         if need_dgrad and self.wp_bwd is not None:
             if self.row_dgrad:
                 jobs.append((w, self.wp_bwd, 3, self.row_dgrad - 8, O, I, T))
+            elif self.blk_dgrad:
+                jobs.append((w, self.wp_bwd, 3, 1, O, I, T))
             elif self.umma_dgrad:
                 jobs.append((w, self.wp_bwd, 2, 1, O, I, T))
             elif self.tile_dgrad:
@@ -218,6 +228,8 @@ class ConvLayer:
             pass
         elif self.row_fwd:
             ops.conv_row_pack_weights(self.desc, False, self.conv.weight, self.wp_fwd)
+        elif self.blk_fwd:
+            ops.conv_blk_pack_weights(self.conv.weight, self.wp_fwd, False, O, I)
         elif self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
@@ -227,6 +239,8 @@ class ConvLayer:
         if need_dgrad and self.wp_bwd is not None:
             if self.row_dgrad:
                 ops.conv_row_pack_weights(self.desc, True, self.conv.weight, self.wp_bwd)
+            elif self.blk_dgrad:
+                ops.conv_blk_pack_weights(self.conv.weight, self.wp_bwd, True, O, I)
             elif self.umma_dgrad:
                 ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.tile_dgrad:
@@ -245,6 +259,9 @@ class ConvLayer:
         elif self.row_fwd:
             fused_stats = self.has_act and train
             ops.conv_row_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, rt.scratch if fused_stats else None)
+        elif self.blk_fwd:
+            fused_stats = self.has_act and train
+            ops.conv_blk_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, rt.scratch if fused_stats else None)
         elif self.umma_fwd:
             ops.conv_umma_fwd(self.desc, src0, src1, self.wp_fwd, self.conv.bias, self.y, self.out_nchw)
         elif self.tile_fwd:
@@ -256,7 +273,7 @@ class ConvLayer:
         if not self.has_act:
             return self.y
         bn = self.bn
-        if train and self.row_fwd:
+        if train and (self.row_fwd or self.blk_fwd):
             # the statistics pass happened in the convolution's epilogue: only the per-channel finalize is left
             ops.bn_finalize(rt.scratch, self.stats_blocks, self.M, self.cout, bn.weight, bn.bias, bn.eps, bn.momentum,
                             bn.running_mean, bn.running_var, self.state)
@@ -313,6 +330,8 @@ class ConvLayer:
             if dx0 is not None:
                 if self.row_dgrad:
                     ops.conv_row_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
+                elif self.blk_dgrad:
+                    ops.conv_blk_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
                 elif self.umma_dgrad:
                     ops.conv_umma_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx)
                 elif self.tile_dgrad:

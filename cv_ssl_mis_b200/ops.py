@@ -160,6 +160,27 @@ def bn_finalize(part, nblocks, M, C_, gamma, beta, eps, momentum, running_mean, 
               _pf(running_mean), _pf(running_var), _pf(state), _st())
 
 
+# halo-block tcgen05 forward / data gradient (narrow-image 2D 3x3 stride-1 pad-1: the 64^2 / 32^2 / 16^2 levels)
+def conv_blk_supported(d, dgrad=False) -> bool:
+    return bool(_lib.query("b200_conv_blk_supported", C.byref(d), int(dgrad)))
+
+
+def conv_blk_stats_blocks(d) -> int:
+    return int(_lib.query("b200_conv_blk_stats_blocks", C.byref(d)))
+
+
+def conv_blk_pack_weights(w, out, dgrad, O, I):
+    _lib.call("b200_conv_blk_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, _st())
+
+
+def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
+    _lib.call("b200_conv_blk_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wpk), _pf(bias), _pf(dst), _p(stats_part), _st())
+
+
+def conv_blk_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
+    _lib.call("b200_conv_blk_dgrad", C.byref(d), _pf(dy), _pf(wpk_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
+
+
 # row-ring tcgen05 weight gradient (2D 3x3 stride-1 pad-1)
 def conv_row_wgrad_supported(d) -> bool:
     return bool(_lib.query("b200_conv_row_wgrad_supported", C.byref(d)))

@@ -138,6 +138,19 @@ int b200_conv_row_fwd(const b200_conv_desc* d, const float* src0, const float* s
 int b200_conv_row_dgrad(const b200_conv_desc* d, const float* dy, const float* wpk_dgrad, float* dx0, float* dx1,
                         int accumulate, cudaStream_t stream);
 
+/* Halo-block tcgen05 forward / data gradient of the narrow-image 2D 3x3 stride-1 pad-1 convolutions (csrc/conv_blk.cu;
+ * code/networks/unet.py:37,41 at the 64^2 / 32^2 / 16^2 levels): width <= 96, input channels a multiple of 32, GEMM
+ * columns a multiple of 32.  Packed weights: the row-kernel layout [tap][plane][column][32] (b200_conv_pack_batch kind 3
+ * with mode = data-gradient flag, or b200_conv_blk_pack_weights).  b200_conv_blk_fwd can emit the BatchNorm (sum, sum of
+ * squares) of its output as b200_conv_blk_stats_blocks(d) fp64 partials [block][2][cout] for b200_bn_finalize. */
+int b200_conv_blk_supported(const b200_conv_desc* d, int dgrad);
+long long b200_conv_blk_stats_blocks(const b200_conv_desc* d);
+int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, cudaStream_t stream);
+int b200_conv_blk_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wpk, const float* bias,
+                      float* dst, double* stats_partials, cudaStream_t stream);
+int b200_conv_blk_dgrad(const b200_conv_desc* d, const float* dy, const float* wpk_dgrad, float* dx0, float* dx1,
+                        int accumulate, cudaStream_t stream);
+
 /* One-launch weight packing for a whole network.  jobs_dev: DEVICE array of njobs x 8 int64:
  * [src ptr, dst ptr, kind (0 generic / 1 tile / 2 umma / 3 row), mode (generic: B200_PACK_*; tile/umma: dgrad flag; row: b200_conv_row_supported() - 8), O, I, T, total]. */
 int b200_conv_pack_batch(const long long* jobs_dev, int njobs, int blocks_per_job, cudaStream_t stream);

@@ -317,7 +317,12 @@ def _row_pack_index(mode, O, I):
     return src, ok
 
 
-def _tf32_rna(v):
+TF32_ROUND = False      # the real packers round the weights to TF32; the host-logic tests keep them exact
+
+
+def _tf32_rna(v, force=False):
+    if not (TF32_ROUND or force):
+        return v.contiguous()
     b = v.contiguous().view(torch.int32)
     return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
 
@@ -354,6 +359,54 @@ def conv_row_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
 
 def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
     W = _row_unpack(d, True, wpk_dgrad)
+    g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
+    dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
+    _split_store(dx, d, dx0, dx1, accumulate)
+
+
+# ------------------------------------------------------------------ halo-block tcgen05 forward / data gradient
+def conv_blk_supported(d, dgrad=False):
+    if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
+        return False
+    if d.iw < 4 or d.iw > 96:
+        return False
+    a0, a1 = (d.cout, 0) if dgrad else (d.c0, d.c1)
+    n0, n1 = (d.c0, d.c1) if dgrad else (d.cout, 0)
+    if a0 <= 0 or a0 % 32 or a1 % 32 or (n0 + n1) % 32:
+        return False
+    nt = 64 if (n0 + n1) % 64 == 0 and (n1 == 0 or n0 % 64 == 0) else 32
+    return not (n1 != 0 and n0 % nt)
+
+
+def conv_blk_stats_blocks(d):
+    return d.n * d.ih          # (any upper bound of the real block count works for the stand-in: unused rows stay zero)
+
+
+def conv_blk_pack_weights(w, out, dgrad, O, I):
+    src, ok = _row_pack_index(1 if dgrad else 0, O, I)
+    out.copy_(_tf32_rna(w.detach().reshape(-1))[src])
+
+
+def _blk_unpack(wpk, dgrad, O, I):
+    src, _ = _row_pack_index(1 if dgrad else 0, O, I)
+    W = torch.zeros(O * I * 9)
+    W[src] = wpk.reshape(-1)
+    return W.reshape(O, I, 1, 3, 3)
+
+
+def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
+    W = _blk_unpack(wpk, False, d.cout, d.c0 + d.c1)
+    y = _ncdhw_to_cl(F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))).reshape(dst.shape)
+    dst.copy_(y)
+    if stats_part is not None:
+        nb = conv_blk_stats_blocks(d)
+        part = torch.zeros(nb, 2, d.cout, dtype=torch.float64)
+        part[0, 0], part[0, 1] = y.double().sum(0), (y.double() ** 2).sum(0)
+        stats_part.view(torch.float64)[:part.numel()].copy_(part.reshape(-1))
+
+
+def conv_blk_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
+    W = _blk_unpack(wpk_dgrad, True, d.cout, d.c0 + d.c1)
     g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
     dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
     _split_store(dx, d, dx0, dx1, accumulate)

@@ -120,6 +120,71 @@ def test_row_pack_batch_equals_single_and_restatement(case, dgrad):
     table = torch.tensor([[wd.data_ptr(), batch.data_ptr(), 3, m - 8, cout, c0 + c1, 9, nf]], dtype=torch.int64, device=DEV)
     ops.conv_pack_batch(table, 1, 8)
     restated = torch.empty(nf)
-    fake_ops.conv_row_pack_weights(d, dgrad, wgt, restated)
+    fake_ops.TF32_ROUND = True
+    try:
+        fake_ops.conv_row_pack_weights(d, dgrad, wgt, restated)
+    finally:
+        fake_ops.TF32_ROUND = False
     assert torch.equal(single, batch)
     assert torch.equal(single.cpu(), restated)
+
+
+# ------------------------------------------------------------------------------------------------ halo-block kernel
+BLK_CASES = [
+    # n, h, w, c0, c1, cout
+    (2, 64, 64, 32, 0, 64),
+    (3, 64, 64, 64, 0, 64),
+    (1, 64, 64, 64, 64, 64),
+    (2, 32, 32, 64, 0, 128),
+    (2, 32, 32, 128, 128, 128),
+    (3, 16, 16, 128, 0, 256),
+    (2, 16, 16, 256, 0, 256),
+    (2, 8, 8, 32, 0, 32),
+    (1, 20, 24, 32, 32, 96),
+    (2, 14, 14, 64, 0, 32),
+]
+
+
+@pytest.mark.parametrize("case", BLK_CASES)
+def test_blk_fwd_and_stats(case):
+    n, h, w, c0, c1, cout = case
+    d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    assert ops.conv_blk_supported(d, False)
+    x0, x1, wgt, bias, _ = _mk(case)
+    M, cin = n * h * w, c0 + c1
+    wpk = torch.empty(9 * cout * cin, device=DEV)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, False, cout, cin)
+    y = torch.full((M, cout), float("nan"), device=DEV)
+    nb = ops.conv_blk_stats_blocks(d)
+    part = torch.full((nb * 2 * cout,), float("nan"), dtype=torch.float64, device=DEV)
+    ops.conv_blk_fwd(d, x0.to(DEV), None if x1 is None else x1.to(DEV), wpk, bias.to(DEV), y, part)
+    torch.cuda.synchronize()
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    ref = F.conv2d(_nchw(x, n, h, w, cin), wgt.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(M, cout)
+    torch.testing.assert_close(y.cpu().double(), ref, rtol=2e-2, atol=5e-3)
+    s = part.view(nb, 2, cout).sum(0).cpu()
+    yd = y.cpu().double()
+    torch.testing.assert_close(s[0], yd.sum(0), rtol=1e-5, atol=1e-5 * M)
+    torch.testing.assert_close(s[1], (yd * yd).sum(0), rtol=1e-5, atol=1e-5 * M)
+
+
+@pytest.mark.parametrize("case", BLK_CASES)
+def test_blk_dgrad(case):
+    n, h, w, c0, c1, cout = case
+    d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
+    if not ops.conv_blk_supported(d, True):
+        pytest.skip("data gradient of this shape is served by another kernel")
+    _, _, wgt, _, dy = _mk(case, 1)
+    M, cin = n * h * w, c0 + c1
+    wpk = torch.empty(9 * cout * cin, device=DEV)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, True, cout, cin)
+    dx0 = torch.full((M, c0), float("nan"), device=DEV)
+    dx1 = torch.full((M, c1), float("nan"), device=DEV) if c1 else None
+    ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx0, dx1)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(_nchw(dy, n, h, w, cout), wgt.double(), padding=1).permute(0, 2, 3, 1).reshape(M, cin)
+    got = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
+    torch.testing.assert_close(got.double(), ref, rtol=2e-2, atol=5e-3)
+    ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx0, dx1, accumulate=True)
+    got2 = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
+    torch.testing.assert_close(got2, 2 * got, rtol=1e-6, atol=1e-6)

@@ -6,9 +6,10 @@ import torch
 from cv_ssl_mis_b200 import ops
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["row", "umma2", "tile"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["row", "blk", "umma2", "tile"]
 SHAPES = [(24, 256, 256, 16, 0, 16), (24, 256, 256, 16, 16, 16), (24, 128, 128, 16, 0, 32), (24, 128, 128, 32, 0, 32),
-          (24, 128, 128, 32, 0, 64), (24, 128, 128, 32, 0, 16), (24, 64, 64, 64, 0, 64),
+          (24, 128, 128, 32, 0, 64), (24, 128, 128, 32, 0, 16), (24, 64, 64, 32, 0, 64), (24, 64, 64, 64, 0, 64), (24, 64, 64, 64, 64, 64),
+          (24, 32, 32, 64, 0, 128),
           (24, 32, 32, 128, 0, 128), (24, 16, 16, 256, 0, 256), (24, 32, 32, 128, 128, 128)]
 for (n, h, w, c0, c1, cout) in SHAPES:
     d = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)
@@ -29,6 +30,13 @@ for (n, h, w, c0, c1, cout) in SHAPES:
             ops.conv_row_pack_weights(d, False, wgt, wt)
             part = torch.empty(ops.conv_row_stats_blocks(d) * 2 * cout, dtype=torch.float64, device="cuda")
             fn = lambda: ops.conv_row_fwd(d, x0, x1, wt, bias, y, part)
+        elif name == "blk":
+            if not ops.conv_blk_supported(d, False):
+                continue
+            wt = torch.empty(9 * cout * cin, device="cuda")
+            ops.conv_blk_pack_weights(wgt, wt, False, cout, cin)
+            part = torch.empty(ops.conv_blk_stats_blocks(d) * 2 * cout, dtype=torch.float64, device="cuda")
+            fn = lambda: ops.conv_blk_fwd(d, x0, x1, wt, bias, y, part)
         elif name.startswith("umma"):
             ops.UMMA_V2 = name == "umma2"
             wt = torch.empty(ops.conv_umma_packed_floats(False, cout, cin, 9), device="cuda")
