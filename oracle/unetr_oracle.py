@@ -7,6 +7,11 @@ UnetrPrUpBlock, UnetrUpBlock}`, `dynunet_block.{UnetResBlock, UnetOutBlock}`), w
 keyword limits it to roughly 0.6 - 1.3).  The reference holds no test or golden vector for this network.  The functions
 below restate MONAI's published block definitions (cited per function) and are anchored on the reference's own call
 site (unetr.py:88-181 constructor arguments, :215-230 forward); state_dict keys follow MONAI's module names.
+What is pinned instead (tests/test_unetr_oracle_crosscheck.py): every block below against the stock torch.nn module
+of the same published definition with mapped weights -- the transformer blocks against nn.TransformerEncoderLayer
+(norm_first, gelu, zero in_proj bias), the residual / transposed-convolution blocks against nn.Conv3d,
+nn.InstanceNorm3d, nn.ConvTranspose3d.  That removes "the restatement mis-implements a block" but not "MONAI's
+version differs from the published definition", so the header stays "unpinned".
 """
 import torch
 import torch.nn.functional as F
