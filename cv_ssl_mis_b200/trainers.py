@@ -27,7 +27,64 @@ HP_LR, HP_MOMENTUM, HP_WD, HP_ALPHA, HP_ONE_MINUS_ALPHA, HP_GRAD_SCALE, HP_WCONS
 NOISE_STREAM = 1000
 
 
-class MeanTeacherTrainer:
+class PendingLoss:
+    """Handle returned by `submit`: the step's losses, available once ITS read-back (not the whole queue) has landed."""
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+        return self._host.tolist()
+
+
+class _Pipelined:
+    """`submit(images, labels)` is `step(..., read_loss=True)` without the stall: the pinned host batch goes up on a copy
+    stream into one of two device staging pairs while the previous step is still running, the step is enqueued behind
+    it, and the 16/32-byte loss read-back gets its own event.  A loop that calls `result()` of step i after `submit` of
+    step i+1 keeps the GPU busy back to back; the host batch must stay untouched until its `result()` has returned."""
+    _pipe = None
+
+    def _loss_sources(self):
+        return [self.lossbuf]
+
+    def submit(self, images, labels, **kw):
+        cuda = self.dev.type == "cuda"
+        if self._pipe is None:
+            n = 4 * len(self._loss_sources())
+            self._pipe = {"i": 0, "copy": torch.cuda.Stream(device=self.dev) if cuda else None, "slots": [
+                {"x": None, "y": None, "free": None, "host": torch.zeros(n).pin_memory() if cuda else torch.zeros(n)} for _ in range(2)]}
+        pipe = self._pipe
+        slot = pipe["slots"][pipe["i"] % 2]
+        pipe["i"] += 1
+        if cuda and not images.is_cuda:
+            if slot["x"] is None:
+                slot["x"] = torch.empty(images.shape, dtype=images.dtype, device=self.dev)
+                slot["y"] = torch.empty(labels.shape, dtype=labels.dtype, device=self.dev)
+            main, copy = torch.cuda.current_stream(), pipe["copy"]
+            if slot["free"] is not None:
+                copy.wait_event(slot["free"])              # the step that last read this staging pair has been enqueued past it
+            with torch.cuda.stream(copy):
+                slot["x"].copy_(images, non_blocking=True)
+                slot["y"].copy_(labels, non_blocking=True)
+            main.wait_stream(copy)
+            images, labels = slot["x"], slot["y"]
+        self.step(images, labels, **kw)
+        ev = None
+        if cuda:
+            slot["free"] = torch.cuda.Event()
+            slot["free"].record()
+        host = slot["host"]
+        for j, src in enumerate(self._loss_sources()):
+            host[4 * j:4 * j + 4].copy_(src[:4], non_blocking=True)
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+        return PendingLoss(host, ev)
+
+
+class MeanTeacherTrainer(_Pipelined):
     def __init__(self, model, ema_model=None, *, batch_size=24, labeled_bs=12, patch_size=(256, 256), num_classes=4,
                  base_lr=0.01, max_iterations=30000, ema_decay=0.99, consistency=0.1, consistency_rampup=200.0,
                  momentum=0.9, weight_decay=1e-4, start_iter=0, consistency_gate_iters=1000, uncertainty_T=0,
@@ -134,11 +191,10 @@ class MeanTeacherTrainer:
                          self.lossbuf, self.loss_ws, psum, float(self.T), thr)
         ops.ssl_loss_bwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
                          self.lossbuf, 1.0, self.s_plan.g_logits, True, psum, float(self.T), thr)
-        if self.world > 1 and hasattr(self.s_plan, "decoder_grad_offset") and os.environ.get("B200_DP_BUCKETS", "0") == "1":
-            # opt-in: two gradient buckets -- the decoder's (produced first) is all-reduced on a communication stream while
-            # the encoder's backward is still running; the encoder's follows on the main stream.  Measured at 2 GPUs:
-            # 6.48 ms/step either way (the 7.3 MB exchange costs a fixed NCCL launch latency, not bandwidth), so the
-            # single all-reduce below stays the default.
+        if self.world > 1 and hasattr(self.s_plan, "decoder_grad_offset") and os.environ.get("B200_DP_BUCKETS", "1") == "1":
+            # two gradient buckets -- the decoder's (produced first) is all-reduced on a communication stream while the
+            # encoder's backward is still running; the encoder's follows on the main stream (B200_DP_BUCKETS=0: one
+            # all-reduce after the whole backward).
             off = self.s_plan.decoder_grad_offset()
             cuda = self.dev.type == "cuda"
             if cuda and self.comm is None:
@@ -345,7 +401,7 @@ def _plan_for(model, B, patch, need_grad):
     return model._get_plan(B, *patch, need_grad)
 
 
-class CrossTeachingTrainer:
+class CrossTeachingTrainer(_Pipelined):
     """Cross Teaching between CNN and Transformer (code/train_cross_teaching_between_cnn_transformer_2D.py:221-262).
 
     Per iteration: both models see the whole batch; each is trained with 0.5 (CE + Dice) on the labeled half plus
@@ -461,6 +517,9 @@ class CrossTeachingTrainer:
             self.loss_host[4:].copy_(self.lossbufs[1][:4], non_blocking=True)
             torch.cuda.current_stream().synchronize() if self.dev.type == "cuda" else None
             return self.loss_host.tolist()
+        return self.lossbufs
+
+    def _loss_sources(self):
         return self.lossbufs
 
     def _state_tensors(self):

@@ -352,7 +352,9 @@ def test_unetr_fully_supervised_trainer_step(fake):
     x = torch.randn(2, 1, 32, 32, 32, generator=g)
     y = torch.randint(0, 2, (2, 32, 32, 32), generator=g)
     tr = MeanTeacherTrainer(net, None, batch_size=2, labeled_bs=2, patch_size=(32, 32, 32), num_classes=2, base_lr=0.01)
-    ce, dice, cons, total = tr.step(x, y)[:4].tolist()
+    pending = tr.submit(x, y)                                             # pipelined form of step(..., read_loss=True)
+    ce, dice, cons, total = pending.result()
+    assert tr.iter_num == 1 and [ce, dice, cons, total] == tr.lossbuf[:4].tolist()
     leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     loss, _ = UO.fully_supervised_loss(leaf, x, y, 2, 2)
     loss.backward()

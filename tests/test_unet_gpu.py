@@ -142,6 +142,33 @@ def test_full_size_step_properties():
     assert trg.kernel_launches_per_step and trg.kernel_launches_per_step > 100
 
 
+def test_pipelined_submit_equals_blocking_steps():
+    """`submit` (upload on the copy stream into two staging pairs, deferred loss read) must give exactly the losses and
+    parameters of `step(..., read_loss=True)` on the same sequence of DIFFERENT host batches."""
+    B, Lb, H, W = 8, 4, 64, 64
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.rand(B, 1, H, W, generator=g).pin_memory(), torch.randint(0, 4, (B, H, W), generator=g).to(torch.uint8).pin_memory())
+               for _ in range(5)]
+
+    def run(pipelined):
+        s, t = unet_mod.UNet(1, 4, seed=1).cuda(), unet_mod.UNet(1, 4, seed=2).cuda()
+        tr = MeanTeacherTrainer(s, t, batch_size=B, labeled_bs=Lb, patch_size=(H, W), start_iter=1500, use_cuda_graph=True)
+        if not pipelined:
+            return [tr.step(x, y, read_loss=True) for x, y in batches], tr.flat.data.clone()
+        out, pending = [], []
+        for x, y in batches:
+            pending.append(tr.submit(x, y))
+            if len(pending) > 1:
+                out.append(pending.pop(0).result())
+        out.append(pending.pop(0).result())
+        return out, tr.flat.data.clone()
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert l0 == l1 and torch.equal(p0, p1)
+    assert len({tuple(l) for l in l0}) == len(l0)          # the batches really differ
+
+
 def test_net_factory_surface():
     net = net_factory(net_type="unet", in_chns=1, class_num=4)
     assert isinstance(net, unet_mod.UNet) and next(net.parameters()).is_cuda
