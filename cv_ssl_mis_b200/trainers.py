@@ -464,7 +464,7 @@ class CrossTeachingTrainer(_Pipelined):
             m.train()
         p1, p2 = self.plans
         # the two networks are independent except at the loss: model 1 runs on an auxiliary stream next to model 2
-        overlap = self.dev.type == "cuda" and self.world == 1
+        overlap = self.dev.type == "cuda"
         if overlap and self.aux is None:
             self.aux = torch.cuda.Stream(device=self.dev)
         main = torch.cuda.current_stream() if overlap else None
@@ -487,15 +487,21 @@ class CrossTeachingTrainer(_Pipelined):
                           mine.g_logits, True)
 
         def update(i):
-            plan, flat, mom = self.plans[i], self.flats[i], self.momentum_bufs[i]
-            plan.backward(None)                                            # :252-255 (loss = model1_loss + model2_loss)
-            if self.world > 1:
-                torch.distributed.all_reduce(flat.grad, group=self.pg)
-            ops.sgd_ema_step(flat.data, flat.grad, mom, None, self.hp)     # :257-258
+            self.plans[i].backward(None)                                   # :252-255 (loss = model1_loss + model2_loss)
+            if self.world == 1:
+                ops.sgd_ema_step(self.flats[i].data, self.flats[i].grad, self.momentum_bufs[i], None, self.hp)     # :257-258
 
         on_aux(lambda: update(0))
         update(1)
-        if overlap:
+        if self.world > 1:
+            # one communicator: its collectives stay on ONE stream, in the same order on every rank -- model 2's
+            # gradient goes first while model 1's backward is still running on the auxiliary stream
+            for i in (1, 0):
+                if i == 0 and overlap:
+                    main.wait_stream(self.aux)
+                torch.distributed.all_reduce(self.flats[i].grad, group=self.pg)
+                ops.sgd_ema_step(self.flats[i].data, self.flats[i].grad, self.momentum_bufs[i], None, self.hp)
+        elif overlap:
             main.wait_stream(self.aux)
 
     def step(self, images, labels, read_loss=False):

@@ -151,6 +151,7 @@ def test_pipelined_submit_equals_blocking_steps():
                for _ in range(5)]
 
     def run(pipelined):
+        torch.manual_seed(9)
         s, t = unet_mod.UNet(1, 4, seed=1).cuda(), unet_mod.UNet(1, 4, seed=2).cuda()
         tr = MeanTeacherTrainer(s, t, batch_size=B, labeled_bs=Lb, patch_size=(H, W), start_iter=1500, use_cuda_graph=True)
         if not pipelined:
