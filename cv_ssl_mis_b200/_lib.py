@@ -77,7 +77,7 @@ SIGNATURES = {
     "b200_conv_row_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_blk_supported": (_I, [_D, _I]),
     "b200_conv_blk_stats_blocks": (_L, [_D]),
-    "b200_conv_blk_pack_weights": (_I, [_P, _P, _I, _I, _I, _S]),
+    "b200_conv_blk_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
     "b200_conv_blk_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
     "b200_conv_blk_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_bn_finalize": (_I, [_P, _I, _L, _I, _P, _P, _F, _F, _P, _P, _P, _S]),

@@ -16,6 +16,12 @@
 //              pixels (two destinations for the data gradient of a virtual concat); BatchNorm (sum, sum^2) of the tile from
 //              the staged values, written per item as fp64 partials for b200_bn_finalize (code/networks/unet.py:38,42)
 // Packed weights: the row-kernel layout [tap][plane][column][32] (conv_row_pack.cuh, mode = data-gradient flag).
+//
+// 3D (code/networks/vnet.py:28, 3x3x3 stride 1 pad 1, >= 32 channels): the same kernel with a depth axis on the halo --
+// an item is (volume, TD output planes, TR output rows, 64 channels), its halo box is (TD + 2) x (TR + 2) x (W + 2)
+// positions, position q = (dd (TR + 2) + r) (W + 2) + c, and tap (kd, kh, kw) is the start-address shift
+// (kd (TR + 2) + kh) (W + 2) + kw; weight chunks arrive per (plane, kd, kh).  (TD, TR) per layer come from a small cost
+// model (tensor-pipe cycles of the accumulator blocks against the TMA bytes of halo + weights, times the number of waves).
 #include "umma_common.cuh"
 #include "conv_row_pack.cuh"
 #include <cstdlib>
@@ -31,7 +37,8 @@ constexpr int MAX_NW = 4;
 constexpr int MAX_NB = 3;
 
 struct BlkP {
-    int N, H, W, P;              // images, rows, columns, halo pitch W + 2
+    int N, D, H, W, P;           // images, planes (1 in 2D), rows, columns, halo pitch W + 2
+    int KD, TD, tiles_d, R2;     // depth taps (1 or 3), output planes per item, plane blocks, halo rows per plane TR + 2
     int TR, tiles_r, nb;         // output rows per item, row blocks per image, 128-position accumulator blocks per item
     int NP, NP0;                 // 32-channel planes of the reduction operand in total / served by the first source
     int Nt, ntiles_n, Ntot;      // GEMM columns per item, column tiles, total GEMM columns
@@ -42,9 +49,10 @@ struct BlkP {
     float* dst1;
     int D0, D1;                  // channels of the destinations (columns [0, D0) -> dst0, the rest -> dst1)
     int accumulate;
-    double* stats;               // [N * tiles_r][2][Ntot] or null
-    int debug;                   // profiling only: 1 no MMAs, 2 epilogue only releases the accumulator, 4 no TMA loads / waits
-    FastDiv fdP;
+    double* stats;               // [N * tiles_d * tiles_r][2][Ntot] or null
+    int debug;                   // profiling only: 1 no MMAs, 2 epilogue only releases the accumulator, 4 no TMA loads / waits,
+                                 // 8 every tap reads the unshifted halo (wrong results: cost of atom-misaligned A operands)
+    FastDiv fdP, fdR2;
 };
 
 __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_constant__ CUtensorMap tx0,
@@ -55,12 +63,13 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
     __shared__ uint32_t tmem_base_smem;
     __shared__ float sred[4][2][64];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: the role branches and their loops run on the uniform datapath
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_ring = smem0;
     const uint32_t w_ring = a_ring + 2u * p.a_bytes;
     const uint32_t stg = w_ring + (uint32_t)p.NW * p.w_bytes;
-    const int nitems = p.N * p.tiles_r * p.ntiles_n;
+    const int nitems = p.N * p.tiles_d * p.tiles_r * p.ntiles_n;
 
     // the accumulator blocks read past the halo box (junk rows): those bytes must be finite, and no box ever writes them
     {
@@ -91,20 +100,21 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
         if (leader) { tma_prefetch_desc(&tx0); tma_prefetch_desc(&tx1); tma_prefetch_desc(&tw); }
         int as = 0, aph = 0, acnt = 0, ws = 0, wph = 0, wcnt = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int nt = item % p.ntiles_n, t = item / p.ntiles_n, tr = t % p.tiles_r, n = t / p.tiles_r;
-            const int h0 = tr * p.TR;
+            const int nt = item % p.ntiles_n, t = item / p.ntiles_n, tr = t % p.tiles_r, t2 = t / p.tiles_r;
+            const int td = t2 % p.tiles_d, n = t2 / p.tiles_d;
+            const int h0 = tr * p.TR, z0 = td * p.TD - (p.KD == 3 ? 1 : 0);
             for (int pl = 0; pl < p.NP; ++pl) {
                 if (acnt >= 2) mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
                 if (leader && !(p.debug & 4)) {
                     const uint32_t fb = smem_u32(&a_full[as]);
                     mbar_expect_tx(fb, (uint32_t)p.a_box_bytes);
-                    if (pl < p.NP0) tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx0, 0, -1, pl, h0 - 1, n, fb);
-                    else tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx1, 0, -1, pl - p.NP0, h0 - 1, n, fb);
+                    if (pl < p.NP0) tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx0, 32 * pl, -1, h0 - 1, z0, n, fb);
+                    else tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx1, 32 * (pl - p.NP0), -1, h0 - 1, z0, n, fb);
                 }
                 __syncwarp();
                 ++acnt;
                 if (++as == 2) { as = 0; aph ^= 1; }
-                for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < 3 * p.KD; ++kh) {              // (kd, kh) filter rows
                     if (wcnt >= p.NW) mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
                     if (leader && !(p.debug & 4)) {
                         const uint32_t fb = smem_u32(&w_full[ws]);
@@ -134,21 +144,23 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
             for (int pl = 0; pl < p.NP; ++pl) {
                 if (!(p.debug & 4)) mbar_wait(smem_u32(&a_full[as]), aph);
                 const uint64_t ad0 = smem_desc(a_ring + (uint32_t)as * p.a_bytes, 16, 1024, 2);
-                for (int kh = 0; kh < 3; ++kh) {
+                for (int kk = 0, kd = 0, kh = 0; kk < 3 * p.KD; ++kk) {
                     if (!(p.debug & 4)) mbar_wait(smem_u32(&w_full[ws]), wph);
                     tc_fence_after();
                     const uint64_t wd0 = smem_desc(w_ring + (uint32_t)ws * p.w_bytes, 16, 1024, 2);
-                    const uint32_t first = (pl | kh) == 0 ? 0u : 1u;
+                    const uint32_t first = (pl | kk) == 0 ? 0u : 1u;
+                    const uint64_t tap16 = (p.debug & 8) ? 0ull : (uint64_t)(kd * p.R2 + kh) * row16;
+                    if (++kh == 3) { kh = 0; ++kd; }
 #pragma unroll 1
                     for (int b = 0; b < p.nb; ++b) {
-                        const uint64_t ab = ad0 + (uint64_t)(b * 1024) + (uint64_t)kh * row16;      // 128 positions = 1024 units
+                        const uint64_t ab = ad0 + (uint64_t)(b * 1024) + tap16;                     // 128 positions = 1024 units
                         const uint32_t d = d0 + (uint32_t)(b * p.Nt);
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 if (leader && !(p.debug & 1))
-                                    mma_tf32(d, ab + (uint64_t)(kw * 8 + 2 * ks), wd0 + (uint64_t)kw * wtap16 + (uint64_t)(2 * ks), idesc,
+                                    mma_tf32(d, ab + (uint64_t)(((p.debug & 8) ? 0 : kw * 8) + 2 * ks), wd0 + (uint64_t)kw * wtap16 + (uint64_t)(2 * ks), idesc,
                                              (kw | ks) == 0 ? first : 1u);
                             }
                         }
@@ -178,8 +190,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
         const int et = ew * 32 + lane;
         int il = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++il) {
-            const int nt = item % p.ntiles_n, t = item / p.ntiles_n, tr = t % p.tiles_r, n = t / p.tiles_r;
-            const int h0 = tr * p.TR, buf = il & 1;
+            const int nt = item % p.ntiles_n, t = item / p.ntiles_n, tr = t % p.tiles_r, t2 = t / p.tiles_r;
+            const int td = t2 % p.tiles_d, n = t2 / p.tiles_d;
+            const int h0 = tr * p.TR, z0 = td * p.TD, buf = il & 1;
             const int col0 = nt * Nt;
             const bool second = col0 >= p.D0;
             float* dst = second ? p.dst1 : p.dst0;
@@ -226,18 +239,21 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
 #pragma unroll 1
                 for (int it = 0; it < 32; it += 4 * RPI) {
                     float4 v[4];
-                    uint32_t rr[4], cc[4];
+                    uint32_t rr[4], cc[4], dd[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int row = it + u * RPI + rsub;
-                        p.fdP.divmod(pos0 + (uint32_t)row, rr[u], cc[u]);
+                        uint32_t hr;
+                        p.fdP.divmod(pos0 + (uint32_t)row, hr, cc[u]);
+                        p.fdR2.divmod(hr, dd[u], rr[u]);
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
                                      : "r"(stw + (uint32_t)row * rowb + (uint32_t)((chunk ^ (row & (TPP - 1) & 7)) * 16)));
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (it + u * RPI + rsub < 32 && (int)cc[u] < p.W && (int)rr[u] < p.TR && h0 + (int)rr[u] < p.H) {
-                            float* o = dst + ((size_t)(n * p.H + h0 + (int)rr[u]) * p.W + cc[u]) * ldc + cofs;
+                        if (it + u * RPI + rsub < 32 && (int)cc[u] < p.W && (int)rr[u] < p.TR && h0 + (int)rr[u] < p.H &&
+                            (int)dd[u] < p.TD && z0 + (int)dd[u] < p.D) {
+                            float* o = dst + (((size_t)(n * p.D + z0 + (int)dd[u]) * p.H + h0 + (int)rr[u]) * p.W + cc[u]) * ldc + cofs;
                             if (p.accumulate) {
                                 const float4 old = *reinterpret_cast<const float4*>(o);
                                 v[u].x += old.x; v[u].y += old.y; v[u].z += old.z; v[u].w += old.w;
@@ -281,22 +297,45 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
 }
 
 __global__ void __launch_bounds__(256) conv_blk_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int mode, int O, int I,
-                                                            int total) {
+                                                            int T, int total) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
-        out[idx] = row_pack_elem(w, mode, O, I, idx);
+        out[idx] = row_pack_elem(w, mode, O, I, T, idx);
 }
 
 struct BGeo {
-    int P, TR, tiles_r, nb, NP, NP0, Nt, ntiles_n, Ntot, a_bytes, a_box, w_bytes, NW, smem, D0, D1;
+    int KD, P, TD, tiles_d, R2, TR, tiles_r, nb, NP, NP0, Nt, ntiles_n, Ntot, a_bytes, a_box, w_bytes, NW, smem, D0, D1;
 };
+
+// shared-memory plan of one (TD, TR) candidate; false when it does not fit
+bool bfit(BGeo& g, int KD, int W, int TD, int TR) {
+    g.TD = TD; g.TR = TR; g.R2 = TR + 2;
+    const int span = ((TD - 1) * g.R2 + TR - 1) * g.P + W;           // halo-linear positions from the first to the last output
+    g.nb = (span + 127) / 128;
+    if (g.nb * g.Nt > 256) return false;                             // TMEM: two item buffers of 256 columns
+    const int box_pos = (KD == 3 ? TD + 2 : 1) * g.R2 * g.P;
+    if (g.R2 > 256 || TD + 2 > 256) return false;
+    g.a_box = box_pos * 128;
+    const int need = g.nb * 128 + ((KD == 3 ? 2 * g.R2 : 0) + 2) * g.P + 2;      // positions an accumulator block may touch
+    g.a_bytes = ((need > box_pos ? need : box_pos) * 128 + 1023) & ~1023;
+    const int stage = 128 * g.Nt * 4;
+    g.NW = 0;
+    for (int nw = 3; nw >= 2; --nw) {
+        const int bytes = 1024 + 2 * g.a_bytes + nw * g.w_bytes + stage;
+        if (bytes <= 222 * 1024) { g.NW = nw; g.smem = bytes; break; }
+    }
+    return g.NW != 0;
+}
 
 // dgrad = 0: A = [src0|src1], columns = cout.  dgrad = 1: A = dy (cout channels), columns = c0 + c1 (two destinations).
 bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
-    if (d->id != 1 || d->kd != 1 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->ph != 1 || d->pw != 1 || d->pd != 0) return false;
+    const bool is3 = d->kd == 3 && d->pd == 1 && d->id >= 1;
+    const bool is2 = d->kd == 1 && d->pd == 0 && d->id == 1;
+    if ((!is2 && !is3) || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->ph != 1 || d->pw != 1) return false;
     if (d->n < 1 || d->ih < 1 || d->iw < 4 || d->iw > 96) return false;
     const int a0 = dgrad ? d->cout : d->c0, a1 = dgrad ? 0 : d->c1;
     const int n0 = dgrad ? d->c0 : d->cout, n1 = dgrad ? d->c1 : 0;
     if (a0 <= 0 || a0 % 32 != 0 || a1 % 32 != 0) return false;
+    g.KD = is3 ? 3 : 1;
     g.NP0 = a0 / 32; g.NP = (a0 + a1) / 32;
     g.Ntot = n0 + n1; g.D0 = n0; g.D1 = n1;
     if (g.Ntot % 32 != 0) return false;
@@ -305,29 +344,39 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
     g.ntiles_n = g.Ntot / g.Nt;
     g.P = d->iw + 2;
     g.w_bytes = 3 * g.Nt * 128;
-    const int stage = 128 * g.Nt * 4;
-    // rows per item: best fraction of real outputs among the accumulator rows, at most 3 blocks (TMEM: 2 x 3 x 64 columns)
-    double best = -1;
-    g.TR = 0;
-    for (int tr = 1; tr <= d->ih; ++tr) {
-        const int nb = (tr * g.P + 127) / 128;
-        if (nb > MAX_NB) break;
-        const int tiles = (d->ih + tr - 1) / tr;
-        const double eff = (double)d->ih * d->iw / ((double)tiles * nb * 128);
-        if (eff > best + 1e-9) { best = eff; g.TR = tr; }
+    BGeo best = g;
+    double best_cost = -1;
+    if (!is3) {
+        // rows per item: best fraction of real outputs among the accumulator rows, at most 3 blocks
+        for (int tr = 1; tr <= d->ih; ++tr) {
+            BGeo c = g;
+            if (!bfit(c, 1, d->iw, 1, tr) || c.nb > MAX_NB) break;
+            const int tiles = (d->ih + tr - 1) / tr;
+            const double cost = (double)tiles * c.nb * 128 / ((double)d->ih * d->iw);      // accumulator rows per real output
+            if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = c; }
+        }
+    } else {
+        // cost model per item: tensor-pipe cycles of its accumulator blocks (27 taps x 4 k-steps per plane; ~45 / 48 cycles
+        // per N = 32 / 64 instruction) against the TMA bytes of halo and weight chunks (~14 B / cycle / SM, the measured
+        // 28 GB/s streaming cap), plus a fixed hand-off; items run in waves over the SMs
+        const double cyc = g.Nt == 64 ? 48.0 : 45.0, sms = (double)b200_num_sms();
+        for (int td = 1; td <= d->id && td <= 16; ++td)
+            for (int tr = 1; tr <= d->ih; ++tr) {
+                BGeo c = g;
+                if (!bfit(c, 3, d->iw, td, tr)) break;
+                const double mma = (double)c.nb * 27 * 4 * c.NP * cyc;
+                const double tma = (double)c.NP * (c.a_box + 9.0 * c.w_bytes) / 14.0;
+                const double items = (double)d->n * ((d->id + td - 1) / td) * ((d->ih + tr - 1) / tr) * c.ntiles_n;
+                const double waves = items <= sms ? 1.0 : items / sms;
+                const double cost = waves * ((mma > tma ? mma : tma) + 3000.0);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+            }
     }
-    if (!g.TR) return false;
+    if (best_cost < 0) return false;
+    g = best;
     g.tiles_r = (d->ih + g.TR - 1) / g.TR;
-    g.nb = (g.TR * g.P + 127) / 128;
-    g.a_box = (g.TR + 2) * g.P * 128;
-    const int need = g.nb * 128 + 2 * g.P + 2;                    // positions an accumulator block may touch
-    g.a_bytes = ((need > (g.TR + 2) * g.P ? need : (g.TR + 2) * g.P) * 128 + 1023) & ~1023;
-    g.NW = 0;
-    for (int nw = 3; nw >= 2; --nw) {
-        const int bytes = 1024 + 2 * g.a_bytes + nw * g.w_bytes + stage;
-        if (bytes <= 222 * 1024) { g.NW = nw; g.smem = bytes; break; }
-    }
-    return g.NW != 0;
+    g.tiles_d = is3 ? (d->id + g.TD - 1) / g.TD : 1;
+    return true;
 }
 
 }  // namespace
@@ -340,13 +389,13 @@ B200_API int b200_conv_blk_supported(const b200_conv_desc* d, int dgrad) {
 B200_API long long b200_conv_blk_stats_blocks(const b200_conv_desc* d) {
     BGeo g;
     if (!d || !bgeometry(d, 0, g)) return 0;
-    return (long long)d->n * g.tiles_r;
+    return (long long)d->n * g.tiles_d * g.tiles_r;
 }
 
-B200_API int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, cudaStream_t st) {
-    B200_REQUIRE(w && out && O > 0 && I > 0 && (dgrad ? O : I) % 32 == 0, "conv_blk_pack_weights: bad arguments");
-    const int total = 9 * O * I;
-    conv_blk_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, dgrad ? 1 : 0, O, I, total);
+B200_API int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, int taps, cudaStream_t st) {
+    B200_REQUIRE(w && out && O > 0 && I > 0 && (dgrad ? O : I) % 32 == 0 && (taps == 9 || taps == 27), "conv_blk_pack_weights: bad arguments");
+    const int total = taps * O * I;
+    conv_blk_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, dgrad ? 1 : 0, O, I, taps, total);
     B200_CHECK_LAUNCH("conv_blk_pack_weights");
     return B200_OK;
 }
@@ -355,36 +404,38 @@ static int run_blk(const b200_conv_desc* d, int dgrad, const float* a0, const fl
                    float* dst0, float* dst1, double* stats, int accumulate, cudaStream_t st, const char* who) {
     BGeo g;
     B200_REQUIRE(d && bgeometry(d, dgrad, g), "%s: unsupported convolution", who);
-    const int N = d->n, H = d->ih, W = d->iw;
+    const int N = d->n, D = d->id, H = d->ih, W = d->iw;
     const int ca0 = dgrad ? d->cout : d->c0, ca1 = dgrad ? 0 : d->c1;
     B200_REQUIRE(a0 && wpk && dst0 && (ca1 == 0 || a1) && (g.D1 == 0 || dst1), "%s: null pointer", who);
     CUtensorMap tx0, tx1, tw;
     auto make_in = [&](CUtensorMap* m, const float* base, int C) -> int {
         const cuuint64_t rowb = (cuuint64_t)W * C * 4;
-        const cuuint64_t dims[5] = {32u, (cuuint64_t)W, (cuuint64_t)(C / 32), (cuuint64_t)H, (cuuint64_t)N};
-        const cuuint64_t strides[4] = {(cuuint64_t)C * 4, 128u, rowb, rowb * H};
-        const cuuint32_t box[5] = {32u, (cuuint32_t)g.P, 1u, (cuuint32_t)(g.TR + 2), 1u};
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t strides[4] = {(cuuint64_t)C * 4, rowb, rowb * H, rowb * H * D};
+        const cuuint32_t box[5] = {32u, (cuuint32_t)g.P, (cuuint32_t)g.R2, (cuuint32_t)(g.KD == 3 ? g.TD + 2 : 1), 1u};
         return make_tmap(m, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, who);
     };
     if (int rc = make_in(&tx0, a0, ca0)) return rc;
     tx1 = tx0;
     if (ca1) if (int rc = make_in(&tx1, a1, ca1)) return rc;
     {
-        const cuuint64_t dims[2] = {32u, (cuuint64_t)(9 * g.NP * g.Ntot)};
+        const cuuint64_t dims[2] = {32u, (cuuint64_t)(9 * g.KD * g.NP * g.Ntot)};
         const cuuint64_t strides[1] = {128u};
         const cuuint32_t box[2] = {32u, (cuuint32_t)g.Nt};
         if (int rc = make_tmap(&tw, wpk, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
     }
     BlkP p;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.H = H; p.W = W; p.P = g.P; p.TR = g.TR; p.tiles_r = g.tiles_r; p.nb = g.nb; p.NP = g.NP; p.NP0 = g.NP0;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.P = g.P; p.KD = g.KD; p.TD = g.TD; p.tiles_d = g.tiles_d; p.R2 = g.R2;
+    p.TR = g.TR; p.tiles_r = g.tiles_r; p.nb = g.nb; p.NP = g.NP; p.NP0 = g.NP0;
     p.Nt = g.Nt; p.ntiles_n = g.ntiles_n; p.Ntot = g.Ntot; p.a_bytes = g.a_bytes; p.a_box_bytes = g.a_box; p.w_bytes = g.w_bytes; p.NW = g.NW;
     p.bias = bias; p.dst0 = dst0; p.dst1 = dst1; p.D0 = g.D0; p.D1 = g.D1; p.accumulate = accumulate; p.stats = stats;
     p.fdP.init(g.P);
+    p.fdR2.init(g.R2);
     { const char* e = getenv("B200_BLK_DEBUG"); p.debug = e ? atoi(e) : 0; }
     static int attr = 0;
     if (g.smem > attr) { cudaFuncSetAttribute(conv_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
-    const long long items = (long long)N * g.tiles_r * g.ntiles_n;
+    const long long items = (long long)N * g.tiles_d * g.tiles_r * g.ntiles_n;
     const int grid = (int)(items < b200_num_sms() ? items : b200_num_sms());
     conv_blk_kernel<<<grid, CB_THREADS, g.smem, st>>>(tx0, tx1, tw, p);
     B200_CHECK_LAUNCH(who);

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
     __shared__ __align__(8) uint64_t full_r[MAX_R], empty_r[MAX_R], w_full, acc_full[NACC], acc_empty[NACC];
     __shared__ uint32_t tmem_base_smem;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_base = smem0;
     const uint32_t ring = w_base + (uint32_t)((p.w_bytes + 1023) & ~1023);
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
 __global__ void __launch_bounds__(256) conv_row_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int mode, int O, int I,
                                                             int total) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
-        out[idx] = row_pack_elem(w, mode, O, I, idx);
+        out[idx] = row_pack_elem(w, mode, O, I, 9, idx);
 }
 
 struct RGeo {

@@ -16,7 +16,8 @@ __host__ __device__ __forceinline__ long long row_pack_total(int mode, int O, in
     return (mode & 4) ? 6ll * O * I * 4 : 9ll * O * I;
 }
 
-__device__ __forceinline__ float row_pack_elem(const float* __restrict__ w, int mode, int O, int I, int idx) {
+// T: taps of the filter (9, or 27 for the 3D halo-block kernel; the pair mode is 2D only)
+__device__ __forceinline__ float row_pack_elem(const float* __restrict__ w, int mode, int O, int I, int T, int idx) {
     const int dgrad = mode & 1;
     const int rows = dgrad ? O : I, cols = dgrad ? I : O;
     float v;
@@ -27,7 +28,7 @@ __device__ __forceinline__ float row_pack_elem(const float* __restrict__ w, int 
         const int col = r % cols; r /= cols;
         const int pl = r % np, tap = r / np;
         const int row = pl * cpp + k;
-        v = dgrad ? w[((size_t)row * I + col) * 9 + (8 - tap)] : w[((size_t)col * I + row) * 9 + tap];
+        v = dgrad ? w[((size_t)row * I + col) * T + (T - 1 - tap)] : w[((size_t)col * I + row) * T + tap];
     } else {
         const int np = rows / 16;
         const int k = idx & 31;

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
     __shared__ __align__(8) uint64_t full_x[MAX_RX], empty_x[MAX_RX], full_d[MAX_RD], empty_d[MAX_RD], acc_full, acc_empty;
     __shared__ uint32_t tmem_base_smem;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t d_base = smem0 + 1024;                                       // [guard][dy ring + 2 mirrors][guard][x ring][guard]
     const uint32_t x_base = d_base + (uint32_t)(p.RD + 2) * p.ds_bytes + 1024;

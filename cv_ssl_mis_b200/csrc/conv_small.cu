@@ -34,7 +34,7 @@ __device__ __forceinline__ float pack_elem(const float* __restrict__ w, int kind
     }
     const int dgrad = mode & 1;
     const int rows = dgrad ? O : I, cols = dgrad ? I : O;
-    if (kind == 3) return row_pack_elem(w, mode, O, I, idx);      // row-ring kernels (conv_row_pack.cuh)
+    if (kind == 3) return row_pack_elem(w, mode, O, I, T, idx);      // row-ring kernels (conv_row_pack.cuh)
     const int colsP = (cols + 15) / 16 * 16;
     int row, col, tap;
     if (kind == 1) {            // [chunk][tap][colsP][16]

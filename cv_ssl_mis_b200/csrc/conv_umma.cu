@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) conv_umma_kernel(const UmmaP p) {
     constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;               // two 128-row blocks, BN fp32 columns each
     using SM = USmem<BN>;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
     const int tile_w = blockIdx.x % p.tiles_w, tile_r = blockIdx.x / p.tiles_w;
     const int w0 = tile_w * p.TW, R0 = tile_r * p.TH;
     const int n0 = blockIdx.y * BN;
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(U2_THREADS) conv_umma2_kernel(const Umma2P p) 
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
     const int n0 = blockIdx.y * BN;
     const int plane_a = p.NPIXA * 16;
     const int halo_bytes = 4 * plane_a;

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(G_THREADS) gemm_umma_kernel(const __grid_const
     __shared__ __align__(8) uint64_t full_bar[G_MAX_STAGES], empty_bar[G_MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
     const int S = p.nstages, BN = p.BN;
     const int stage_bytes = A_BYTES + BN * BK * 4;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;      // the 128-byte swizzle wants 1024-byte alignment

@@ -167,7 +167,7 @@ class ConvLayer:
         if (self.row_fwd or self.blk_fwd) and self.has_act:
             self.stats_blocks = ops.conv_row_stats_blocks(self.desc) if self.row_fwd else ops.conv_blk_stats_blocks(self.desc)
             rt.need_scratch(self.stats_blocks * 2 * self.cout * 8)
-        nfwd = (ops.conv_row_packed_floats(self.desc, False) if self.row_fwd else 9 * O * I if self.blk_fwd else
+        nfwd = (ops.conv_row_packed_floats(self.desc, False) if self.row_fwd else self.T * O * I if self.blk_fwd else
                 ops.conv_umma_packed_floats(False, O, I, self.T) if self.umma_fwd else
                 ops.conv_tile_packed_floats(False, O, I, self.T) if self.tile_fwd else ops.conv_packed_floats(fwd_mode, O, I, self.T))
         self.wp_fwd = torch.empty(nfwd, dtype=torch.float32, device=dev)
@@ -184,7 +184,7 @@ class ConvLayer:
                 self.bwd_mode = PACK_DECONV_DGRAD
                 rt.need_scratch(max(ops.deconv_k2s2_wgrad_workspace_bytes(self.desc),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
-            nbwd = (ops.conv_row_packed_floats(self.desc, True) if self.row_dgrad else 9 * O * I if self.blk_dgrad else
+            nbwd = (ops.conv_row_packed_floats(self.desc, True) if self.row_dgrad else self.T * O * I if self.blk_dgrad else
                     ops.conv_umma_packed_floats(True, O, I, self.T) if self.umma_dgrad else
                     ops.conv_tile_packed_floats(True, O, I, self.T) if self.tile_dgrad else ops.conv_packed_floats(self.bwd_mode, O, I, self.T))
             self.wp_bwd = torch.empty(nbwd, dtype=torch.float32, device=dev)
@@ -229,7 +229,7 @@ class ConvLayer:
         elif self.row_fwd:
             ops.conv_row_pack_weights(self.desc, False, self.conv.weight, self.wp_fwd)
         elif self.blk_fwd:
-            ops.conv_blk_pack_weights(self.conv.weight, self.wp_fwd, False, O, I)
+            ops.conv_blk_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
@@ -240,7 +240,7 @@ class ConvLayer:
             if self.row_dgrad:
                 ops.conv_row_pack_weights(self.desc, True, self.conv.weight, self.wp_bwd)
             elif self.blk_dgrad:
-                ops.conv_blk_pack_weights(self.conv.weight, self.wp_bwd, True, O, I)
+                ops.conv_blk_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.umma_dgrad:
                 ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.tile_dgrad:

@@ -169,8 +169,8 @@ def conv_blk_stats_blocks(d) -> int:
     return int(_lib.query("b200_conv_blk_stats_blocks", C.byref(d)))
 
 
-def conv_blk_pack_weights(w, out, dgrad, O, I):
-    _lib.call("b200_conv_blk_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, _st())
+def conv_blk_pack_weights(w, out, dgrad, O, I, taps=9):
+    _lib.call("b200_conv_blk_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, taps, _st())
 
 
 def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):

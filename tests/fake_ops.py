@@ -287,19 +287,19 @@ def conv_row_packed_floats(d, dgrad=False):
     return d.cout * (d.c0 + d.c1) * (24 if m & 4 else 9)
 
 
-def _row_pack_index(mode, O, I):
-    """csrc/conv_row_pack.cuh:row_pack_elem as index arithmetic: (flat source index into w[O][I][9], validity) per output element."""
+def _row_pack_index(mode, O, I, T=9):
+    """csrc/conv_row_pack.cuh:row_pack_elem as index arithmetic: (flat source index into w[O][I][T], validity) per output element."""
     dgrad = mode & 1
     rows, cols = (O, I) if dgrad else (I, O)
     if not mode & 4:
         cpp = 16 if mode & 2 else 32
         npl = rows // cpp
-        idx = torch.arange(9 * O * I)
+        idx = torch.arange(T * O * I)
         k, r = idx % cpp, idx // cpp
         col, r = r % cols, r // cols
         pl, tap = r % npl, r // npl
         row = pl * cpp + k
-        src = (row * I + col) * 9 + (8 - tap) if dgrad else (col * I + row) * 9 + tap
+        src = (row * I + col) * T + (T - 1 - tap) if dgrad else (col * I + row) * T + tap
         return src, torch.ones_like(src, dtype=torch.bool)
     npl = rows // 16
     idx = torch.arange(6 * O * I * 4)
@@ -366,7 +366,8 @@ def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
 
 # ------------------------------------------------------------------ halo-block tcgen05 forward / data gradient
 def conv_blk_supported(d, dgrad=False):
-    if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
+    flat = d.kd == 1 and d.id == 1 and d.pd == 0
+    if not ((flat or (d.kd == 3 and d.pd == 1)) and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1):
         return False
     if d.iw < 4 or d.iw > 96:
         return False
@@ -379,23 +380,23 @@ def conv_blk_supported(d, dgrad=False):
 
 
 def conv_blk_stats_blocks(d):
-    return d.n * d.ih          # (any upper bound of the real block count works for the stand-in: unused rows stay zero)
+    return d.n * d.id * d.ih   # (any upper bound of the real block count works for the stand-in: unused rows stay zero)
 
 
-def conv_blk_pack_weights(w, out, dgrad, O, I):
-    src, ok = _row_pack_index(1 if dgrad else 0, O, I)
+def conv_blk_pack_weights(w, out, dgrad, O, I, taps=9):
+    src, ok = _row_pack_index(1 if dgrad else 0, O, I, taps)
     out.copy_(_tf32_rna(w.detach().reshape(-1))[src])
 
 
-def _blk_unpack(wpk, dgrad, O, I):
-    src, _ = _row_pack_index(1 if dgrad else 0, O, I)
-    W = torch.zeros(O * I * 9)
+def _blk_unpack(wpk, dgrad, O, I, kd=1):
+    src, _ = _row_pack_index(1 if dgrad else 0, O, I, 9 * kd)
+    W = torch.zeros(O * I * 9 * kd)
     W[src] = wpk.reshape(-1)
-    return W.reshape(O, I, 1, 3, 3)
+    return W.reshape(O, I, kd, 3, 3)
 
 
 def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
-    W = _blk_unpack(wpk, False, d.cout, d.c0 + d.c1)
+    W = _blk_unpack(wpk, False, d.cout, d.c0 + d.c1, d.kd)
     y = _ncdhw_to_cl(F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))).reshape(dst.shape)
     dst.copy_(y)
     if stats_part is not None:
@@ -406,7 +407,7 @@ def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
 
 
 def conv_blk_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
-    W = _blk_unpack(wpk_dgrad, True, d.cout, d.c0 + d.c1)
+    W = _blk_unpack(wpk_dgrad, True, d.cout, d.c0 + d.c1, d.kd)
     g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
     dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
     _split_store(dx, d, dx0, dx1, accumulate)
@@ -474,7 +475,7 @@ def conv_pack_batch(jobs_dev, njobs, blocks_per_job=16, jobs_py=None):
         elif kind == 1:
             conv_tile_pack_weights(w, out, bool(mode), O, I, T)
         elif kind == 3:
-            src, ok = _row_pack_index(mode, O, I)
+            src, ok = _row_pack_index(mode, O, I, T)
             out.copy_(torch.where(ok, _tf32_rna(w.detach().reshape(-1))[src], torch.zeros(())))
         else:
             conv_umma_pack_weights(w, out, bool(mode), O, I, T)

@@ -188,3 +188,69 @@ def test_blk_dgrad(case):
     ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx0, dx1, accumulate=True)
     got2 = dx0.cpu() if dx1 is None else torch.cat([dx0.cpu(), dx1.cpu()], 1)
     torch.testing.assert_close(got2, 2 * got, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ halo-block kernel, 3D
+BLK3_CASES = [
+    # n, d, h, w, cin, cout  (code/networks/vnet.py:28 at the 32 / 64 / 128 / 256-channel levels, plus ragged shapes)
+    (2, 8, 12, 40, 32, 32),
+    (1, 28, 28, 20, 64, 64),
+    (2, 14, 14, 10, 128, 128),
+    (2, 7, 7, 5, 256, 256),
+    (1, 5, 9, 7, 32, 64),
+    (3, 3, 4, 6, 64, 32),
+    (1, 1, 6, 13, 32, 96),
+]
+
+
+def _mk3(case, seed=0):
+    n, dd, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(seed + sum(case))
+    M = n * dd * h * w
+    return (torch.randn(M, cin, generator=g), torch.randn(cout, cin, 3, 3, 3, generator=g) * (cin * 27) ** -0.5,
+            torch.randn(cout, generator=g), torch.randn(M, cout, generator=g))
+
+
+def _ncdhw(t, n, dd, h, w, c):
+    return t.view(n, dd, h, w, c).permute(0, 4, 1, 2, 3).double()
+
+
+@pytest.mark.parametrize("case", BLK3_CASES)
+def test_blk3d_fwd_and_stats(case):
+    n, dd, h, w, cin, cout = case
+    d = ops.conv_desc(n, dd, h, w, cin, 0, cout, 3, 1, 1, 3)
+    assert ops.conv_blk_supported(d, False)
+    x, wgt, bias, _ = _mk3(case)
+    M = n * dd * h * w
+    wpk = torch.empty(27 * cout * cin, device=DEV)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, False, cout, cin, 27)
+    y = torch.full((M, cout), float("nan"), device=DEV)
+    nb = ops.conv_blk_stats_blocks(d)
+    part = torch.full((nb * 2 * cout,), float("nan"), dtype=torch.float64, device=DEV)
+    ops.conv_blk_fwd(d, x.to(DEV), None, wpk, bias.to(DEV), y, part)
+    torch.cuda.synchronize()
+    ref = F.conv3d(_ncdhw(x, n, dd, h, w, cin), wgt.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(M, cout)
+    torch.testing.assert_close(y.cpu().double(), ref, rtol=2e-2, atol=5e-3)
+    s = part.view(nb, 2, cout).sum(0).cpu()
+    yd = y.cpu().double()
+    torch.testing.assert_close(s[0], yd.sum(0), rtol=1e-5, atol=1e-5 * M)
+    torch.testing.assert_close(s[1], (yd * yd).sum(0), rtol=1e-5, atol=1e-5 * M)
+
+
+@pytest.mark.parametrize("case", BLK3_CASES)
+def test_blk3d_dgrad(case):
+    n, dd, h, w, cin, cout = case
+    d = ops.conv_desc(n, dd, h, w, cin, 0, cout, 3, 1, 1, 3)
+    assert ops.conv_blk_supported(d, True)
+    _, wgt, _, dy = _mk3(case, 1)
+    M = n * dd * h * w
+    wpk = torch.empty(27 * cout * cin, device=DEV)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, True, cout, cin, 27)
+    dx = torch.full((M, cin), float("nan"), device=DEV)
+    ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx, None)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(_ncdhw(dy, n, dd, h, w, cout), wgt.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(M, cin)
+    torch.testing.assert_close(dx.cpu().double(), ref, rtol=2e-2, atol=5e-3)
+    got = dx.clone()
+    ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx, None, accumulate=True)
+    torch.testing.assert_close(dx, 2 * got, rtol=1e-6, atol=1e-6)
