@@ -14,7 +14,7 @@
 //   warp 1     MMA issuer (elected lane): per (plane, filter row) 3 blocks x 3 taps x 4 k-steps of tcgen05.mma kind::tf32
 //   warps 2-5  epilogue: tcgen05.ld -> + bias -> per-warp swizzled staging tile -> coalesced 16-byte stores of the valid
 //              pixels (two destinations for the data gradient of a virtual concat); BatchNorm (sum, sum^2) of the tile from
-//              the staged values, written per item as fp64 partials for b200_bn_finalize (code/networks/unet.py:38,42)
+//              the staged values, accumulated per CTA in fp64 and written as one partial per CTA for b200_bn_finalize (code/networks/unet.py:38,42)
 // Packed weights: the row-kernel layout [tap][plane][column][32] (conv_row_pack.cuh, mode = data-gradient flag).
 //
 // 3D (code/networks/vnet.py:28, 3x3x3 stride 1 pad 1, >= 32 channels): the same kernel with a depth axis on the halo --
@@ -49,7 +49,7 @@ struct BlkP {
     float* dst1;
     int D0, D1;                  // channels of the destinations (columns [0, D0) -> dst0, the rest -> dst1)
     int accumulate;
-    double* stats;               // [N * tiles_d * tiles_r][2][Ntot] or null
+    double* stats;               // [gridDim.x][2][Ntot] or null (forward only: Ntot = cout <= 256)
     int debug;                   // profiling only: 1 no MMAs, 2 epilogue only releases the accumulator, 4 no TMA loads / waits,
                                  // 8 every tap reads the unshifted halo (wrong results: cost of atom-misaligned A operands)
     FastDiv fdP, fdR2;
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
         const uint32_t rowb = (uint32_t)(Nh * 4);
         const uint32_t stw = stg + (uint32_t)ew * 32u * rowb;        // this warp's staging tile: 32 rows x Nh floats
         const int et = ew * 32 + lane;
+        double acc1 = 0.0, acc2 = 0.0;                               // BatchNorm sums of GEMM column et over this CTA's items
         int il = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++il) {
             const int nt = item % p.ntiles_n, t = item / p.ntiles_n, tr = t % p.tiles_r, t2 = t / p.tiles_r;
@@ -283,12 +284,18 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                     }
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (et < 2 * Nt) {
-                    const int which = et / Nt, c = et % Nt;
-                    const double s = (double)sred[0][which][c] + (double)sred[1][which][c] + (double)sred[2][which][c] + (double)sred[3][which][c];
-                    p.stats[((size_t)t * 2 + which) * p.Ntot + col0 + c] = s;
+                // epilogue thread et owns GEMM column et for the whole launch (cout <= 256): items are visited in a fixed
+                // order, so the per-CTA fp64 sums are deterministic
+                if (et >= col0 && et < col0 + Nt) {
+                    const int c = et - col0;
+                    acc1 += (double)sred[0][0][c] + (double)sred[1][0][c] + (double)sred[2][0][c] + (double)sred[3][0][c];
+                    acc2 += (double)sred[0][1][c] + (double)sred[1][1][c] + (double)sred[2][1][c] + (double)sred[3][1][c];
                 }
             }
+        }
+        if (p.stats && et < p.Ntot) {
+            p.stats[((size_t)blockIdx.x * 2 + 0) * p.Ntot + et] = acc1;
+            p.stats[((size_t)blockIdx.x * 2 + 1) * p.Ntot + et] = acc2;
         }
     }
     tc_fence_before();
@@ -356,16 +363,20 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
             if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = c; }
         }
     } else {
-        // cost model per item: tensor-pipe cycles of its accumulator blocks (27 taps x 4 k-steps per plane; ~45 / 48 cycles
-        // per N = 32 / 64 instruction) against the TMA bytes of halo and weight chunks (~14 B / cycle / SM, the measured
-        // 28 GB/s streaming cap), plus a fixed hand-off; items run in waves over the SMs
-        const double cyc = g.Nt == 64 ? 48.0 : 45.0, sms = (double)b200_num_sms();
+        // cost model per item, calibrated on tools/bench_conv3d.py sweeps: tensor-pipe cycles of its accumulator blocks
+        // (27 taps x 4 k-steps per plane; ~55 / 58 cycles per N = 32 / 64 instruction as issued here) against the TMA
+        // bytes of halo and weight chunks (~26 B / cycle / SM when they hit L2), plus a fixed hand-off per item; items
+        // run in waves over the SMs
+        const double cyc = g.Nt == 64 ? 58.0 : 55.0, sms = (double)b200_num_sms();
+        const char* etd = getenv("B200_BLK_TD");                     // tuning override: fixed (TD, TR)
+        const char* etr = getenv("B200_BLK_TR");
         for (int td = 1; td <= d->id && td <= 16; ++td)
             for (int tr = 1; tr <= d->ih; ++tr) {
                 BGeo c = g;
                 if (!bfit(c, 3, d->iw, td, tr)) break;
+                if (etd && etr && (td != atoi(etd) || tr != atoi(etr))) continue;
                 const double mma = (double)c.nb * 27 * 4 * c.NP * cyc;
-                const double tma = (double)c.NP * (c.a_box + 9.0 * c.w_bytes) / 14.0;
+                const double tma = (double)c.NP * (c.a_box + 9.0 * c.w_bytes) / 26.0;
                 const double items = (double)d->n * ((d->id + td - 1) / td) * ((d->ih + tr - 1) / tr) * c.ntiles_n;
                 const double waves = items <= sms ? 1.0 : items / sms;
                 const double cost = waves * ((mma > tma ? mma : tma) + 3000.0);
@@ -389,7 +400,8 @@ B200_API int b200_conv_blk_supported(const b200_conv_desc* d, int dgrad) {
 B200_API long long b200_conv_blk_stats_blocks(const b200_conv_desc* d) {
     BGeo g;
     if (!d || !bgeometry(d, 0, g)) return 0;
-    return (long long)d->n * g.tiles_d * g.tiles_r;
+    const long long items = (long long)d->n * g.tiles_d * g.tiles_r * g.ntiles_n;
+    return items < b200_num_sms() ? items : b200_num_sms();         // one partial per CTA
 }
 
 B200_API int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, int taps, cudaStream_t st) {
@@ -407,6 +419,7 @@ static int run_blk(const b200_conv_desc* d, int dgrad, const float* a0, const fl
     const int N = d->n, D = d->id, H = d->ih, W = d->iw;
     const int ca0 = dgrad ? d->cout : d->c0, ca1 = dgrad ? 0 : d->c1;
     B200_REQUIRE(a0 && wpk && dst0 && (ca1 == 0 || a1) && (g.D1 == 0 || dst1), "%s: null pointer", who);
+    B200_REQUIRE(!stats || g.Ntot <= 256, "%s: fused statistics need cout <= 256", who);
     CUtensorMap tx0, tx1, tw;
     auto make_in = [&](CUtensorMap* m, const float* base, int C) -> int {
         const cuuint64_t rowb = (cuuint64_t)W * C * 4;

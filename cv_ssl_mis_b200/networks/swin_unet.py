@@ -606,9 +606,10 @@ class SwinPlan:
     def logits(self):            # [B, C, H*W] (NCHW)
         return self.logits_val.v
 
-    def forward(self, x, train=True):
+    def forward(self, x, train=True, repack=True):
         """x: [B, 1, img, img] fp32 contiguous."""
-        self.packer.run()
+        if repack:                       # False: the weights have not changed since this plan's previous forward
+            self.packer.run()
         self.x_in = x
         for op in self.tape:
             op.fwd(self.rt, train)

@@ -118,10 +118,11 @@ class UNetPlan:
     def g_logits(self):          # channels-last d(loss)/d(logits), [B*H*W, C]
         return self.head.g
 
-    def forward(self, x, train=True):
+    def forward(self, x, train=True, repack=True):
         """x: [B,1,H,W] (== channels-last for one channel) or [B*H*W, in_chns] channels-last."""
         rt, B = self.rt, self.B
-        self.packer.run()
+        if repack:                       # False: the weights have not changed since this plan's previous forward
+            self.packer.run()
         self.x_in = x
         src = x
         h, w = self.H, self.W

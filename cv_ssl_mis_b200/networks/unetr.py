@@ -442,10 +442,11 @@ class UNETRPlan:
     def g_logits(self):          # channels-last d(loss)/d(logits), [B*D*H*W, C]
         return self.g_logits_all
 
-    def forward(self, x, train=True):
+    def forward(self, x, train=True, repack=True):
         """x: [B, C, D, H, W] fp32 contiguous (C = 1: identical to channels-last)."""
         rt = self.rt
-        self.packer.run()
+        if repack:                       # False: the weights have not changed since this plan's previous forward
+            self.packer.run()
         self.x_in = x
         B, (D, H, W) = self.B, self.dims3
         if self.net.in_channels == 1:

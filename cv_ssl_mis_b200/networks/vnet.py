@@ -96,9 +96,10 @@ class VNetPlan:
     def g_logits(self):          # channels-last d(loss)/d(logits), [B*D*H*W, C]
         return self.head.g
 
-    def forward(self, x, train=True):
+    def forward(self, x, train=True, repack=True):
         rt = self.rt
-        self.packer.run()
+        if repack:                       # False: the weights have not changed since this plan's previous forward
+            self.packer.run()
         self.x_in = x
         cur = x
         for s in range(5):

@@ -233,7 +233,7 @@ class MeanTeacherTrainer(_Pipelined):
             for i in range(self.T // 2):
                 self.t_off += 1
                 ops.noise_add(self.x_rep, self.ema_in2, 0.1, 0.2, self.noise_seed, self.t_off, NOISE_STREAM)
-                self.t_plan2.forward(self.ema_in2, train=True)
+                self.t_plan2.forward(self.ema_in2, train=True, repack=(i == 0))    # same EMA weights in all T//2 passes
                 ops.mc_softmax_accumulate(self.t_plan2.logits, self.psum, 2, self.U, self.C, self.S, False, i == 0)
 
     def step(self, images, labels, read_loss=False):
