@@ -24,6 +24,11 @@
 //   warp 1     MMA issuer (one lane) + TMEM allocation; tcgen05.commit releases the slots
 //   warps 2-5  epilogue: tcgen05.ld -> partial dW of this (row range, ci group, co block) into the workspace
 // A second kernel reduces the row-range partials in fixed order (deterministic) into the framework layout [co][ci][3][3].
+//
+// 3D (3x3x3, backward of code/networks/vnet.py:28 and of the UNETR residual blocks): for a fixed depth tap kd the sum
+// over (n, d) of the 2D problem between x plane d + kd - 1 and dy plane d, so kd joins the work-item index (ci group,
+// co block, kd, row range); the "images" of the row walk are the N * D planes of x, the dy rows come from the plane one
+// depth tap away (planes -1 and D are out of bounds of the tensor map = zero).
 #include "umma_common.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -37,7 +42,8 @@ constexpr int WG_THREADS = 192;
 constexpr int MAX_RX = 8, MAX_RD = 8;
 
 struct WgP {
-    int N, H, P;             // images, rows per image, k-rows per staged image row (multiple of 8)
+    int N, H, P;             // images (2D) or planes N * D (3D), rows per image, k-rows per staged image row (multiple of 8)
+    int D, KD;               // planes per volume (1 in 2D), depth taps (1 or 3)
     int ppr;                 // pixels per k-row: 1 (channel counts multiple of 32) or 2 (16-channel tensors)
     int G, G0;               // x channel groups in total / served by the first source
     int MB, MG;              // co blocks (128 channels), 128-byte planes per dy slot
@@ -64,7 +70,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
     const uint32_t x_base = d_base + (uint32_t)(p.RD + 2) * p.ds_bytes + 1024;
     const uint32_t total = x_base + (uint32_t)p.RX * p.xs_bytes + 1024 - smem0;
     const int R = p.N * p.H;
-    const int nitems = p.G * p.MB * p.S;
+    const int nitems = p.G * p.MB * p.S * p.KD;
 
     // every byte an MMA may touch (guards, the row groups beyond the real channels) must hold finite data
     for (uint32_t o = (uint32_t)tid * 16; o < total; o += WG_THREADS * 16)
@@ -92,11 +98,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
             int xs = 0, xph = 0, xcnt = 0;            // x ring slot / parity of the fill being overwritten / fills so far
             int ds = 0, dph = 0, dcnt = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int g = item % p.G, t = item / p.G, mb = t % p.MB, s = t / p.MB;
+                const int g = item % p.G, t = item / p.G, mb = t % p.MB, t2 = t / p.MB, kd = t2 % p.KD, s = t2 / p.KD;
                 const int r0 = (int)((long long)s * R / p.S), r1 = (int)((long long)(s + 1) * R / p.S);
                 const bool second = g >= p.G0;
                 const int gl = second ? g - p.G0 : g;
-                int n = r0 / p.H, X = r0 - n * p.H;
+                const int img = r0 / p.H;
+                int n = img / p.D, xd = img - n * p.D, X = r0 - img * p.H;
+                const int dshift = p.KD == 3 ? 1 - kd : 0;          // dy plane = x plane + 1 - kd
+                const uint32_t plane_b = (uint32_t)p.P * 128;
                 for (int r = r0; r < r1; ++r) {
                     const bool new_seg = (r == r0) || (X == 0);
                     const int first = new_seg ? X - 1 : X + 1, cnt = new_seg ? 3 : 1;
@@ -105,8 +114,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
                         const uint32_t fb = smem_u32(&full_d[ds]);
                         if (leader) {
                             mbar_expect_tx(fb, (uint32_t)p.ds_bytes * (ds < 2 ? 2u : 1u));
-                            tma_load_5d(d_base + (uint32_t)ds * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
-                            if (ds < 2) tma_load_5d(d_base + (uint32_t)(p.RD + ds) * p.ds_bytes, &tdy, 0, -1, mb * p.MG, first + k, n, fb);
+                            for (int j = 0; j < p.MG; ++j) {
+                                const int c0 = 32 * (mb * p.MG + j);
+                                tma_load_5d(d_base + (uint32_t)ds * p.ds_bytes + (uint32_t)j * plane_b, &tdy, c0, -1, first + k, xd + dshift, n, fb);
+                                if (ds < 2)
+                                    tma_load_5d(d_base + (uint32_t)(p.RD + ds) * p.ds_bytes + (uint32_t)j * plane_b, &tdy, c0, -1, first + k,
+                                                xd + dshift, n, fb);
+                            }
                         }
                         __syncwarp();
                         if (++ds == p.RD) { ds = 0; dph ^= 1; }
@@ -115,13 +129,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
                     const uint32_t fb = smem_u32(&full_x[xs]);
                     if (leader) {
                         mbar_expect_tx(fb, (uint32_t)p.xs_bytes);
-                        if (second) tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx1, 0, -1, gl, X, n, fb);
-                        else tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx0, 0, -1, gl, X, n, fb);
+                        if (second) tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx1, 32 * gl, -1, X, xd, n, fb);
+                        else tma_load_5d(x_base + (uint32_t)xs * p.xs_bytes, &tx0, 32 * gl, -1, X, xd, n, fb);
                     }
                     __syncwarp();
                     ++xcnt;
                     if (++xs == p.RX) { xs = 0; xph ^= 1; }
-                    if (++X == p.H) { X = 0; ++n; }
+                    if (++X == p.H) { X = 0; if (++xd == p.D) { xd = 0; ++n; } }
                 }
             }
         }
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
             int fslot = 0, fph = 0, ahead = 0;      // dy ring: next slot to wait for / its parity / rows already waited beyond wslot
             int il = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++il) {
-                const int s = item / (p.G * p.MB);
+                const int s = item / (p.G * p.MB * p.KD);
                 const int r0 = (int)((long long)s * R / p.S), r1 = (int)((long long)(s + 1) * R / p.S);
                 if (il >= 1) mbar_wait(smem_u32(&acc_empty), (il - 1) & 1);
                 tc_fence_after();
@@ -210,7 +224,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
         const int q = warp & 3;
         int il = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++il) {
-            const int g = item % p.G, t = item / p.G, mb = t % p.MB, s = t / p.MB;
+            const int g = item % p.G, t = item / p.G, mb = t % p.MB, t2 = t / p.MB, kd = t2 % p.KD, s = t2 / p.KD;
+            const int T = 9 * p.KD, tap0 = kd * 9;
             mbar_wait(smem_u32(&acc_full), il & 1);
             tc_fence_after();
             for (int a = 0; a < p.NMMA; ++a) {
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
                     if (p.ppr == 1) {
                         const int co = mb * 128 + pl * 32 + lane;
                         if (co < p.Cout) {
-                            float* dst = p.ws + ((size_t)((s * 9 + kh * 3 + c) * p.Cin + g * 32)) * p.Cout + co;
+                            float* dst = p.ws + ((size_t)((s * T + tap0 + kh * 3 + c) * p.Cin + g * 32)) * p.Cout + co;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) dst[(size_t)i * p.Cout] = __uint_as_float(rg[i]);
                         }
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
                         for (int i = 0; i < 32; ++i) {
                             const int kw = 2 * c + (i >> 4) - 1 - pa;            // pixel offset of this column block minus pa
                             if (kw >= 0 && kw <= 2)
-                                p.ws[((size_t)(((s * 2 + pa) * 9 + kh * 3 + kw) * p.Cin + g * 16 + (i & 15))) * p.Cout + co] =
+                                p.ws[((size_t)(((s * 2 + pa) * T + tap0 + kh * 3 + kw) * p.Cin + g * 16 + (i & 15))) * p.Cout + co] =
                                     __uint_as_float(rg[i]);
                         }
                     }
@@ -256,11 +271,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_row_wgrad_kernel(const __g
 // dw[co][ci][tap] (+)= sum over partials of ws[s][tap][ci][co]: a block covers 64 float4 columns (co fastest) with 4
 // interleaved partial sums each, combined in a fixed order (deterministic).  db_zero: bias gradient of a convolution that
 // feeds a train-mode BatchNorm -- identically zero (the BatchNorm backward removes the per-channel mean of its gradient).
-__global__ void __launch_bounds__(256) conv_row_wgrad_reduce_kernel(const float* __restrict__ ws, int nparts, int Cin, int Cout,
+__global__ void __launch_bounds__(256) conv_row_wgrad_reduce_kernel(const float* __restrict__ ws, int nparts, int Cin, int Cout, int T,
                                                                     float* __restrict__ dw, int accumulate, float* __restrict__ db_zero) {
     __shared__ float4 part[4][64];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-    const int E = 9 * Cin * Cout;
+    const int E = T * Cin * Cout;
     const int e = (blockIdx.x * 64 + tx) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e < E) {
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(256) conv_row_wgrad_reduce_kernel(const float*
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float* o = dw + ((size_t)(co + k) * Cin + ci) * 9 + tap;
+            float* o = dw + ((size_t)(co + k) * Cin + ci) * T + tap;
             *o = accumulate ? *o + vv[k] : vv[k];
         }
     }
@@ -289,11 +304,13 @@ __global__ void __launch_bounds__(256) conv_row_wgrad_reduce_kernel(const float*
 }
 
 struct Geo {
-    int ppr, Wk, P, G, G0, MB, MG, KHM, NMMA, S, RX, RD, xs, ds, smem;
+    int ppr, Wk, P, G, G0, MB, MG, KHM, NMMA, S, RX, RD, xs, ds, smem, KD;
 };
 
 bool geometry(const b200_conv_desc* d, Geo& g) {
-    if (d->id != 1 || d->kd != 1 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->ph != 1 || d->pw != 1 || d->pd != 0) return false;
+    const bool is3 = d->kd == 3 && d->pd == 1 && d->id >= 1, is2 = d->kd == 1 && d->pd == 0 && d->id == 1;
+    if ((!is2 && !is3) || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->ph != 1 || d->pw != 1) return false;
+    g.KD = is3 ? 3 : 1;
     const int c0 = d->c0, c1 = d->c1, co = d->cout;
     if (d->n < 1 || d->ih < 1 || d->iw < 1) return false;
     if (c0 % 32 == 0 && c1 % 32 == 0 && c0 > 0 && co % 32 == 0 && (co <= 128 || co % 128 == 0)) {
@@ -327,8 +344,8 @@ bool geometry(const b200_conv_desc* d, Geo& g) {
     if (!g.RD) return false;
     // the row groups beyond the stacked window read up to 4 planes past the last mirror slot: they must stay inside the x ring
     if ((long long)g.RX * g.xs + 1024 < 4ll * g.P * 128) return false;
-    const long long R = (long long)d->n * d->ih;
-    long long S = b200_num_sms() / ((long long)g.G * g.MB);
+    const long long R = (long long)d->n * d->id * d->ih;
+    long long S = b200_num_sms() / ((long long)g.G * g.MB * g.KD);
     if (S > R) S = R;
     if (S < 1) S = 1;
     g.S = (int)S;
@@ -345,7 +362,7 @@ B200_API int b200_conv_row_wgrad_supported(const b200_conv_desc* d) {
 B200_API long long b200_conv_row_wgrad_workspace_bytes(const b200_conv_desc* d) {
     Geo g;
     if (!d || !geometry(d, g)) return 0;
-    return (long long)g.S * g.ppr * 9 * (d->c0 + d->c1) * d->cout * (long long)sizeof(float);
+    return (long long)g.S * g.ppr * 9 * g.KD * (d->c0 + d->c1) * d->cout * (long long)sizeof(float);
 }
 
 B200_API int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, const float* src1, const float* dy, float* workspace,
@@ -357,25 +374,25 @@ B200_API int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, con
         b200_set_error("conv_row_wgrad: workspace too small (%lld < %lld bytes)", workspace_bytes, b200_conv_row_wgrad_workspace_bytes(d));
         return B200_ERR_WORKSPACE;
     }
-    const int N = d->n, H = d->ih, W = d->iw, Cin = d->c0 + d->c1, Cout = d->cout;
+    const int N = d->n, D = d->id, H = d->ih, W = d->iw, Cin = d->c0 + d->c1, Cout = d->cout;
     CUtensorMap tx0, tx1, tdy;
-    auto make = [&](CUtensorMap* m, const float* base, int C, int planes) -> int {
-        // channels-last [N][H][W][C] viewed as {32 floats, k-rows of an image row, 128-byte channel groups, H, N}
-        const int cg = g.ppr == 1 ? C / 32 : 1;
+    auto make = [&](CUtensorMap* m, const float* base, int C) -> int {
+        // channels-last [N][D][H][W][C] viewed as {channels (a box takes one 128-byte group), k-rows of an image row, H, D, N};
+        // 16-channel tensors: the 128-byte k-row is a pixel pair
         const cuuint64_t rowb = (cuuint64_t)W * C * 4;
-        const cuuint64_t dims[5] = {32u, (cuuint64_t)g.Wk, (cuuint64_t)cg, (cuuint64_t)H, (cuuint64_t)N};
-        const cuuint64_t strides[4] = {g.ppr == 1 ? (cuuint64_t)C * 4 : 128u, g.ppr == 1 ? 128u : rowb, rowb, rowb * H};
-        const cuuint32_t box[5] = {32u, (cuuint32_t)g.P, (cuuint32_t)planes, 1u, 1u};
+        const cuuint64_t dims[5] = {g.ppr == 1 ? (cuuint64_t)C : 32u, (cuuint64_t)g.Wk, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t strides[4] = {g.ppr == 1 ? (cuuint64_t)C * 4 : 128u, rowb, rowb * H, rowb * H * D};
+        const cuuint32_t box[5] = {32u, (cuuint32_t)g.P, 1u, 1u, 1u};
         return make_tmap(m, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "conv_row_wgrad");
     };
-    if (int rc = make(&tx0, src0, d->c0, 1)) return rc;
+    if (int rc = make(&tx0, src0, d->c0)) return rc;
     tx1 = tx0;
-    if (d->c1) if (int rc = make(&tx1, src1, d->c1, 1)) return rc;
-    if (int rc = make(&tdy, dy, Cout, g.MG)) return rc;
+    if (d->c1) if (int rc = make(&tx1, src1, d->c1)) return rc;
+    if (int rc = make(&tdy, dy, Cout)) return rc;
 
     WgP p;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.H = H; p.P = g.P; p.ppr = g.ppr; p.G = g.G; p.G0 = g.G0; p.MB = g.MB; p.MG = g.MG; p.KHM = g.KHM; p.NMMA = g.NMMA;
+    p.N = N * D; p.D = D; p.KD = g.KD; p.H = H; p.P = g.P; p.ppr = g.ppr; p.G = g.G; p.G0 = g.G0; p.MB = g.MB; p.MG = g.MG; p.KHM = g.KHM; p.NMMA = g.NMMA;
     p.S = g.S; p.RX = g.RX; p.RD = g.RD; p.xs_bytes = g.xs; p.ds_bytes = g.ds; p.Cin = Cin; p.Cout = Cout; p.ws = workspace;
     const char* e = getenv("B200_WGRAD_DEBUG");
     p.debug = e ? atoi(e) : 0;
@@ -384,12 +401,12 @@ B200_API int b200_conv_row_wgrad(const b200_conv_desc* d, const float* src0, con
         cudaFuncSetAttribute(conv_row_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem);
         attr_bytes = g.smem;
     }
-    const int nitems = g.G * g.MB * g.S;
+    const int nitems = g.G * g.MB * g.S * g.KD;
     const int grid = nitems < b200_num_sms() ? nitems : b200_num_sms();
     conv_row_wgrad_kernel<<<grid, WG_THREADS, g.smem, st>>>(tx0, tx1, tdy, p);
     B200_CHECK_LAUNCH("conv_row_wgrad");
-    const int total = 9 * Cin * Cout;
-    conv_row_wgrad_reduce_kernel<<<(total / 4 + 63) / 64, 256, 0, st>>>(workspace, g.S * g.ppr, Cin, Cout, dw, accumulate, db_zero);
+    const int total = 9 * g.KD * Cin * Cout;
+    conv_row_wgrad_reduce_kernel<<<(total / 4 + 63) / 64, 256, 0, st>>>(workspace, g.S * g.ppr, Cin, Cout, 9 * g.KD, dw, accumulate, db_zero);
     B200_CHECK_LAUNCH("conv_row_wgrad_reduce");
     return B200_OK;
 }

@@ -415,7 +415,8 @@ def conv_blk_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
 
 # ------------------------------------------------------------------ row-ring tcgen05 weight gradient
 def conv_row_wgrad_supported(d):
-    if not (d.kd == 1 and d.id == 1 and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1 and d.pd == 0):
+    flat = d.kd == 1 and d.id == 1 and d.pd == 0
+    if not ((flat or (d.kd == 3 and d.pd == 1)) and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1):
         return False
     c0, c1, co = d.c0, d.c1, d.cout
     if c0 > 0 and c0 % 32 == 0 and c1 % 32 == 0 and co % 32 == 0 and (co <= 128 or co % 128 == 0):

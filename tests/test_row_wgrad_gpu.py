@@ -89,3 +89,44 @@ def test_row_wgrad_accumulate():
     once = dw.clone()
     ops.conv_row_wgrad(d, x0, None, dy, ws, dw, accumulate=True)
     torch.testing.assert_close(dw, 2 * once, rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ 3D (3x3x3)
+CASES3 = [
+    # n, d, h, w, c0, c1, cout   (backward of code/networks/vnet.py:28 and of the UNETR residual blocks)
+    (2, 6, 8, 16, 32, 0, 32),
+    (1, 5, 6, 12, 64, 0, 64),
+    (2, 3, 5, 6, 128, 0, 128),
+    (1, 4, 4, 4, 256, 0, 256),
+    (2, 4, 6, 16, 16, 0, 16),
+    (1, 3, 5, 8, 32, 32, 32),
+    (1, 1, 7, 10, 64, 0, 32),
+    (1, 2, 4, 8, 16, 16, 16),
+]
+
+
+@pytest.mark.parametrize("case", CASES3)
+def test_row_wgrad_3d_matches_torch(case):
+    n, dd, h, w, c0, c1, cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    M, cin = n * dd * h * w, c0 + c1
+    x0 = torch.randn(M, c0, generator=g)
+    x1 = torch.randn(M, c1, generator=g) if c1 else None
+    dy = torch.randn(M, cout, generator=g)
+    d = ops.conv_desc(n, dd, h, w, c0, c1, cout, 3, 1, 1, 3)
+    assert ops.conv_row_wgrad_supported(d)
+    ws = torch.full((ops.conv_row_wgrad_workspace_bytes(d) // 4 + 4,), float("nan"), device=DEV)
+    dw = torch.full((cout, cin, 3, 3, 3), float("nan"), device=DEV)
+    db = torch.full((cout,), float("nan"), device=DEV)
+    ops.conv_row_wgrad(d, x0.to(DEV), None if x1 is None else x1.to(DEV), dy.to(DEV), ws, dw, False, db)
+    torch.cuda.synchronize()
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    xn = x.view(n, dd, h, w, cin).permute(0, 4, 1, 2, 3).double()
+    dyn = dy.view(n, dd, h, w, cout).permute(0, 4, 1, 2, 3).double()
+    ref = torch.nn.grad.conv3d_weight(xn, (cout, cin, 3, 3, 3), dyn, stride=1, padding=1).float()
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(dw.cpu(), ref, rtol=2e-2, atol=4e-3 * scale)
+    assert float(db.abs().max()) == 0.0
+    once = dw.clone()
+    ops.conv_row_wgrad(d, x0.to(DEV), None if x1 is None else x1.to(DEV), dy.to(DEV), ws, dw, True)
+    torch.testing.assert_close(dw, 2 * once, rtol=1e-6, atol=0)
