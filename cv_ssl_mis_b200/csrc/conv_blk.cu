@@ -55,9 +55,15 @@ struct BlkP {
     FastDiv fdP, fdR2;
 };
 
+// CPP: channels per halo row -- 32 (128-byte rows, 128-byte swizzle) or 16 (16-channel tensors: 64-byte rows, 64-byte swizzle)
+template <int CPP>
 __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_constant__ CUtensorMap tx0,
                                                                  const __grid_constant__ CUtensorMap tx1,
                                                                  const __grid_constant__ CUtensorMap tw, const BlkP p) {
+    constexpr int RB = CPP * 4;                       // bytes of one halo position of a plane
+    constexpr int KS = CPP / 8;                       // k-steps per plane
+    constexpr uint32_t LAYOUT = CPP == 32 ? 2u : 4u;  // K-major, 128-byte / 64-byte swizzle
+    constexpr uint32_t SBO = 8 * RB;                  // 8-row core-matrix group
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[MAX_NW], w_empty[MAX_NW], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -108,8 +114,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                 if (leader && !(p.debug & 4)) {
                     const uint32_t fb = smem_u32(&a_full[as]);
                     mbar_expect_tx(fb, (uint32_t)p.a_box_bytes);
-                    if (pl < p.NP0) tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx0, 32 * pl, -1, h0 - 1, z0, n, fb);
-                    else tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx1, 32 * (pl - p.NP0), -1, h0 - 1, z0, n, fb);
+                    if (pl < p.NP0) tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx0, CPP * pl, -1, h0 - 1, z0, n, fb);
+                    else tma_load_5d(a_ring + (uint32_t)as * p.a_bytes, &tx1, CPP * (pl - p.NP0), -1, h0 - 1, z0, n, fb);
                 }
                 __syncwarp();
                 ++acnt;
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                         const uint32_t fb = smem_u32(&w_full[ws]);
                         mbar_expect_tx(fb, (uint32_t)p.w_bytes);
                         for (int kw = 0; kw < 3; ++kw)
-                            tma_load_2d(w_ring + (uint32_t)ws * p.w_bytes + (uint32_t)(kw * p.Nt * 128), &tw, 0,
+                            tma_load_2d(w_ring + (uint32_t)ws * p.w_bytes + (uint32_t)(kw * p.Nt * RB), &tw, 0,
                                         ((kh * 3 + kw) * p.NP + pl) * p.Ntot + nt * p.Nt, fb);
                     }
                     __syncwarp();
@@ -133,8 +139,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
         // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
         const bool leader = elect_one();
         const uint32_t idesc = idesc_tf32(128, p.Nt, 0, 0);
-        const uint64_t wtap16 = (uint64_t)((p.Nt * 128) >> 4);
-        const uint64_t row16 = (uint64_t)(p.P * 8);                   // one halo row in 16-byte units
+        const uint64_t wtap16 = (uint64_t)((p.Nt * RB) >> 4);
+        const uint64_t row16 = (uint64_t)(p.P * (RB >> 4));           // one halo row in 16-byte units
         int as = 0, aph = 0, ws = 0, wph = 0, il = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++il) {
             const int buf = il & 1;
@@ -143,24 +149,24 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
             const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
             for (int pl = 0; pl < p.NP; ++pl) {
                 if (!(p.debug & 4)) mbar_wait(smem_u32(&a_full[as]), aph);
-                const uint64_t ad0 = smem_desc(a_ring + (uint32_t)as * p.a_bytes, 16, 1024, 2);
+                const uint64_t ad0 = smem_desc(a_ring + (uint32_t)as * p.a_bytes, 16, SBO, LAYOUT);
                 for (int kk = 0, kd = 0, kh = 0; kk < 3 * p.KD; ++kk) {
                     if (!(p.debug & 4)) mbar_wait(smem_u32(&w_full[ws]), wph);
                     tc_fence_after();
-                    const uint64_t wd0 = smem_desc(w_ring + (uint32_t)ws * p.w_bytes, 16, 1024, 2);
+                    const uint64_t wd0 = smem_desc(w_ring + (uint32_t)ws * p.w_bytes, 16, SBO, LAYOUT);
                     const uint32_t first = (pl | kk) == 0 ? 0u : 1u;
                     const uint64_t tap16 = (p.debug & 8) ? 0ull : (uint64_t)(kd * p.R2 + kh) * row16;
                     if (++kh == 3) { kh = 0; ++kd; }
 #pragma unroll 1
                     for (int b = 0; b < p.nb; ++b) {
-                        const uint64_t ab = ad0 + (uint64_t)(b * 1024) + tap16;                     // 128 positions = 1024 units
+                        const uint64_t ab = ad0 + (uint64_t)(b * 8 * RB) + tap16;                   // 128 positions
                         const uint32_t d = d0 + (uint32_t)(b * p.Nt);
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
+                            for (int ks = 0; ks < KS; ++ks) {
                                 if (leader && !(p.debug & 1))
-                                    mma_tf32(d, ab + (uint64_t)(((p.debug & 8) ? 0 : kw * 8) + 2 * ks), wd0 + (uint64_t)kw * wtap16 + (uint64_t)(2 * ks), idesc,
+                                    mma_tf32(d, ab + (uint64_t)(((p.debug & 8) ? 0 : kw * (RB >> 4)) + 2 * ks), wd0 + (uint64_t)kw * wtap16 + (uint64_t)(2 * ks), idesc,
                                              (kw | ks) == 0 ? first : 1u);
                             }
                         }
@@ -182,7 +188,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
         // a warp owns 32 accumulator rows x Nt/2 columns of every block, stages them in its own swizzled tile and writes
         // the valid pixels with coalesced 16-byte stores (TPP lanes cover the Nt/2 * 4 contiguous bytes of one pixel).
         const int ew = warp - 2, q = warp & 3, half = ew >> 2;
-        const int Nt = p.Nt, Nh = Nt >> 1;                           // columns per item / per warp
+        const int Nt = p.Nt, Nh = Nt == 16 ? 16 : Nt >> 1;           // columns per item / per warp
+        const bool idle = Nt == 16 && half == 1;                     // 16-column items: one warp per lane quarter does the work
         const int TPP = Nh >> 2, RPI = 32 / TPP;                     // lanes per pixel, pixels per store instruction
         const int chunk = lane % TPP, rsub = lane / TPP;
         const uint32_t rowb = (uint32_t)(Nh * 4);
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
                 continue;
             }
-            for (int b = 0; b < p.nb; ++b) {
+            for (int b = 0; b < (idle ? 0 : p.nb); ++b) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + b * Nt + half * Nh);
 #pragma unroll 1
                 for (int c0 = 0; c0 < Nh; c0 += 16) {
@@ -267,6 +274,11 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                 }
                 __syncwarp();
             }
+            if (idle) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+            }
             if (p.stats) {
                 // lanes with the same chunk (same four channels) across the RPI pixel groups, then the four quarter-warps
 #pragma unroll
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_blk_kernel(const __grid_co
                         s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
                     }
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // sred of the previous item has been consumed
-                if (rsub == 0) {
+                if (rsub == 0 && !idle) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         sred[q][0][half * Nh + chunk * 4 + k] = s1[k];
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(256) conv_blk_pack_kernel(const float* __restr
 }
 
 struct BGeo {
-    int KD, P, TD, tiles_d, R2, TR, tiles_r, nb, NP, NP0, Nt, ntiles_n, Ntot, a_bytes, a_box, w_bytes, NW, smem, D0, D1;
+    int KD, P, TD, tiles_d, R2, TR, tiles_r, nb, NP, NP0, Nt, ntiles_n, Ntot, a_bytes, a_box, w_bytes, NW, smem, D0, D1, cpp;
 };
 
 // shared-memory plan of one (TD, TR) candidate; false when it does not fit
@@ -321,9 +333,9 @@ bool bfit(BGeo& g, int KD, int W, int TD, int TR) {
     if (g.nb * g.Nt > 256) return false;                             // TMEM: two item buffers of 256 columns
     const int box_pos = (KD == 3 ? TD + 2 : 1) * g.R2 * g.P;
     if (g.R2 > 256 || TD + 2 > 256) return false;
-    g.a_box = box_pos * 128;
+    g.a_box = box_pos * g.cpp * 4;
     const int need = g.nb * 128 + ((KD == 3 ? 2 * g.R2 : 0) + 2) * g.P + 2;      // positions an accumulator block may touch
-    g.a_bytes = ((need > box_pos ? need : box_pos) * 128 + 1023) & ~1023;
+    g.a_bytes = ((need > box_pos ? need : box_pos) * g.cpp * 4 + 1023) & ~1023;
     const int stage = 128 * g.Nt * 4;
     g.NW = 0;
     for (int nw = 3; nw >= 2; --nw) {
@@ -341,16 +353,18 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
     if (d->n < 1 || d->ih < 1 || d->iw < 4 || d->iw > 96) return false;
     const int a0 = dgrad ? d->cout : d->c0, a1 = dgrad ? 0 : d->c1;
     const int n0 = dgrad ? d->c0 : d->cout, n1 = dgrad ? d->c1 : 0;
-    if (a0 <= 0 || a0 % 32 != 0 || a1 % 32 != 0) return false;
+    if (a0 <= 0 || a0 % 16 != 0 || a1 % 16 != 0) return false;
+    g.cpp = (a0 % 32 == 0 && a1 % 32 == 0) ? 32 : 16;               // 16-channel tensors: 64-byte halo rows
+    if (g.cpp == 16 && !is3) return false;                           // (2D 16-channel layers: conv_row's pixel-pair mode)
     g.KD = is3 ? 3 : 1;
-    g.NP0 = a0 / 32; g.NP = (a0 + a1) / 32;
+    g.NP0 = a0 / g.cpp; g.NP = (a0 + a1) / g.cpp;
     g.Ntot = n0 + n1; g.D0 = n0; g.D1 = n1;
-    if (g.Ntot % 32 != 0) return false;
-    g.Nt = g.Ntot % 64 == 0 && (n1 == 0 || n0 % 64 == 0) ? 64 : 32;
+    if (g.Ntot % 16 != 0 || (g.Ntot % 32 != 0 && !is3)) return false;
+    g.Nt = g.Ntot % 64 == 0 && (n1 == 0 || n0 % 64 == 0) ? 64 : (g.Ntot % 32 == 0 && (n1 == 0 || n0 % 32 == 0) ? 32 : 16);
     if (n1 != 0 && n0 % g.Nt != 0) return false;
     g.ntiles_n = g.Ntot / g.Nt;
     g.P = d->iw + 2;
-    g.w_bytes = 3 * g.Nt * 128;
+    g.w_bytes = 3 * g.Nt * g.cpp * 4;
     BGeo best = g;
     double best_cost = -1;
     if (!is3) {
@@ -367,7 +381,7 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
         // (27 taps x 4 k-steps per plane; ~55 / 58 cycles per N = 32 / 64 instruction as issued here) against the TMA
         // bytes of halo and weight chunks (~26 B / cycle / SM when they hit L2), plus a fixed hand-off per item; items
         // run in waves over the SMs
-        const double cyc = g.Nt == 64 ? 58.0 : 55.0, sms = (double)b200_num_sms();
+        const double cyc = g.Nt == 64 ? 58.0 : (g.Nt == 32 ? 55.0 : 50.0), sms = (double)b200_num_sms();
         const char* etd = getenv("B200_BLK_TD");                     // tuning override: fixed (TD, TR)
         const char* etr = getenv("B200_BLK_TR");
         for (int td = 1; td <= d->id && td <= 16; ++td)
@@ -375,7 +389,7 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
                 BGeo c = g;
                 if (!bfit(c, 3, d->iw, td, tr)) break;
                 if (etd && etr && (td != atoi(etd) || tr != atoi(etr))) continue;
-                const double mma = (double)c.nb * 27 * 4 * c.NP * cyc;
+                const double mma = (double)c.nb * 27 * (c.cpp / 8) * c.NP * cyc;
                 const double tma = (double)c.NP * (c.a_box + 9.0 * c.w_bytes) / 26.0;
                 const double items = (double)d->n * ((d->id + td - 1) / td) * ((d->ih + tr - 1) / tr) * c.ntiles_n;
                 const double waves = items <= sms ? 1.0 : items / sms;
@@ -394,7 +408,8 @@ bool bgeometry(const b200_conv_desc* d, int dgrad, BGeo& g) {
 
 B200_API int b200_conv_blk_supported(const b200_conv_desc* d, int dgrad) {
     BGeo g;
-    return (d && bgeometry(d, dgrad, g)) ? 1 : 0;
+    if (!d || !bgeometry(d, dgrad, g)) return 0;
+    return 8 + (dgrad ? 1 : 0) + (g.cpp == 16 ? 2 : 0);              // 8 + weight-pack mode (conv_row_pack.cuh)
 }
 
 B200_API long long b200_conv_blk_stats_blocks(const b200_conv_desc* d) {
@@ -404,10 +419,11 @@ B200_API long long b200_conv_blk_stats_blocks(const b200_conv_desc* d) {
     return items < b200_num_sms() ? items : b200_num_sms();         // one partial per CTA
 }
 
-B200_API int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, int taps, cudaStream_t st) {
-    B200_REQUIRE(w && out && O > 0 && I > 0 && (dgrad ? O : I) % 32 == 0 && (taps == 9 || taps == 27), "conv_blk_pack_weights: bad arguments");
+B200_API int b200_conv_blk_pack_weights(const float* w, float* out, int mode, int O, int I, int taps, cudaStream_t st) {
+    B200_REQUIRE(w && out && O > 0 && I > 0 && mode >= 0 && mode < 4 && ((mode & 1) ? O : I) % ((mode & 2) ? 16 : 32) == 0 &&
+                 (taps == 9 || taps == 27), "conv_blk_pack_weights: bad arguments");
     const int total = taps * O * I;
-    conv_blk_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, dgrad ? 1 : 0, O, I, taps, total);
+    conv_blk_pack_kernel<<<(total + 255) / 256 < 64 ? (total + 255) / 256 : 64, 256, 0, st>>>(w, out, mode, O, I, taps, total);
     B200_CHECK_LAUNCH("conv_blk_pack_weights");
     return B200_OK;
 }
@@ -421,21 +437,22 @@ static int run_blk(const b200_conv_desc* d, int dgrad, const float* a0, const fl
     B200_REQUIRE(a0 && wpk && dst0 && (ca1 == 0 || a1) && (g.D1 == 0 || dst1), "%s: null pointer", who);
     B200_REQUIRE(!stats || g.Ntot <= 256, "%s: fused statistics need cout <= 256", who);
     CUtensorMap tx0, tx1, tw;
+    const CUtensorMapSwizzle swz = g.cpp == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     auto make_in = [&](CUtensorMap* m, const float* base, int C) -> int {
         const cuuint64_t rowb = (cuuint64_t)W * C * 4;
         const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t strides[4] = {(cuuint64_t)C * 4, rowb, rowb * H, rowb * H * D};
-        const cuuint32_t box[5] = {32u, (cuuint32_t)g.P, (cuuint32_t)g.R2, (cuuint32_t)(g.KD == 3 ? g.TD + 2 : 1), 1u};
-        return make_tmap(m, base, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, who);
+        const cuuint32_t box[5] = {(cuuint32_t)g.cpp, (cuuint32_t)g.P, (cuuint32_t)g.R2, (cuuint32_t)(g.KD == 3 ? g.TD + 2 : 1), 1u};
+        return make_tmap(m, base, 5, dims, strides, box, swz, who);
     };
     if (int rc = make_in(&tx0, a0, ca0)) return rc;
     tx1 = tx0;
     if (ca1) if (int rc = make_in(&tx1, a1, ca1)) return rc;
     {
-        const cuuint64_t dims[2] = {32u, (cuuint64_t)(9 * g.KD * g.NP * g.Ntot)};
-        const cuuint64_t strides[1] = {128u};
-        const cuuint32_t box[2] = {32u, (cuuint32_t)g.Nt};
-        if (int rc = make_tmap(&tw, wpk, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
+        const cuuint64_t dims[2] = {(cuuint64_t)g.cpp, (cuuint64_t)(9 * g.KD * g.NP * g.Ntot)};
+        const cuuint64_t strides[1] = {(cuuint64_t)g.cpp * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)g.cpp, (cuuint32_t)g.Nt};
+        if (int rc = make_tmap(&tw, wpk, 2, dims, strides, box, swz, who)) return rc;
     }
     BlkP p;
     memset(&p, 0, sizeof(p));
@@ -446,11 +463,17 @@ static int run_blk(const b200_conv_desc* d, int dgrad, const float* a0, const fl
     p.fdP.init(g.P);
     p.fdR2.init(g.R2);
     { const char* e = getenv("B200_BLK_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    static int attr = 0;
-    if (g.smem > attr) { cudaFuncSetAttribute(conv_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
     const long long items = (long long)N * g.tiles_d * g.tiles_r * g.ntiles_n;
     const int grid = (int)(items < b200_num_sms() ? items : b200_num_sms());
-    conv_blk_kernel<<<grid, CB_THREADS, g.smem, st>>>(tx0, tx1, tw, p);
+    if (g.cpp == 32) {
+        static int attr = 0;
+        if (g.smem > attr) { cudaFuncSetAttribute(conv_blk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
+        conv_blk_kernel<32><<<grid, CB_THREADS, g.smem, st>>>(tx0, tx1, tw, p);
+    } else {
+        static int attr = 0;
+        if (g.smem > attr) { cudaFuncSetAttribute(conv_blk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem); attr = g.smem; }
+        conv_blk_kernel<16><<<grid, CB_THREADS, g.smem, st>>>(tx0, tx1, tw, p);
+    }
     B200_CHECK_LAUNCH(who);
     return B200_OK;
 }

@@ -150,8 +150,8 @@ class ConvLayer:
         # narrow images (the 64^2 / 32^2 / 16^2 levels): halo-block tcgen05 kernel (TMA halo planes, all accumulator
         # blocks of an item in TMEM, statistics in the epilogue).  B200_CONV_BLK=0 keeps conv_umma2 for A/B runs.
         want_blk = want_row and os.environ.get("B200_CONV_BLK", "1") != "0"
-        self.blk_fwd = want_blk and not self.row_fwd and not self.out_nchw and ops.conv_blk_supported(self.desc, False)
-        self.blk_dgrad = want_blk and need_grad and not self.row_dgrad and ops.conv_blk_supported(self.desc, True)
+        self.blk_fwd = ops.conv_blk_supported(self.desc, False) if (want_blk and not self.row_fwd and not self.out_nchw) else 0    # 8 + pack mode
+        self.blk_dgrad = ops.conv_blk_supported(self.desc, True) if (want_blk and need_grad and not self.row_dgrad) else 0
         self.umma_fwd = (want_umma and wide and ops.conv_umma_supported(self.desc, False) and not self.row_fwd
                          and not self.blk_fwd and (self.out_nchw or self.cout % 4 == 0))
         self.umma_dgrad = (want_umma and wide and ops.conv_umma_supported(self.desc, True) and not self.row_dgrad
@@ -200,7 +200,7 @@ class ConvLayer:
             if self.row_fwd:
                 jobs.append((w, self.wp_fwd, 3, self.row_fwd - 8, O, I, T))
             elif self.blk_fwd:
-                jobs.append((w, self.wp_fwd, 3, 0, O, I, T))
+                jobs.append((w, self.wp_fwd, 3, self.blk_fwd - 8, O, I, T))
             elif self.umma_fwd:
                 jobs.append((w, self.wp_fwd, 2, 0, O, I, T))
             elif self.tile_fwd:
@@ -211,7 +211,7 @@ class ConvLayer:
             if self.row_dgrad:
                 jobs.append((w, self.wp_bwd, 3, self.row_dgrad - 8, O, I, T))
             elif self.blk_dgrad:
-                jobs.append((w, self.wp_bwd, 3, 1, O, I, T))
+                jobs.append((w, self.wp_bwd, 3, self.blk_dgrad - 8, O, I, T))
             elif self.umma_dgrad:
                 jobs.append((w, self.wp_bwd, 2, 1, O, I, T))
             elif self.tile_dgrad:
@@ -229,7 +229,7 @@ class ConvLayer:
         elif self.row_fwd:
             ops.conv_row_pack_weights(self.desc, False, self.conv.weight, self.wp_fwd)
         elif self.blk_fwd:
-            ops.conv_blk_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
+            ops.conv_blk_pack_weights(self.conv.weight, self.wp_fwd, self.blk_fwd - 8, O, I, self.T)
         elif self.umma_fwd:
             ops.conv_umma_pack_weights(self.conv.weight, self.wp_fwd, False, O, I, self.T)
         elif self.tile_fwd:
@@ -240,7 +240,7 @@ class ConvLayer:
             if self.row_dgrad:
                 ops.conv_row_pack_weights(self.desc, True, self.conv.weight, self.wp_bwd)
             elif self.blk_dgrad:
-                ops.conv_blk_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
+                ops.conv_blk_pack_weights(self.conv.weight, self.wp_bwd, self.blk_dgrad - 8, O, I, self.T)
             elif self.umma_dgrad:
                 ops.conv_umma_pack_weights(self.conv.weight, self.wp_bwd, True, O, I, self.T)
             elif self.tile_dgrad:

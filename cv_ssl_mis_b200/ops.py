@@ -161,16 +161,17 @@ def bn_finalize(part, nblocks, M, C_, gamma, beta, eps, momentum, running_mean, 
 
 
 # halo-block tcgen05 forward / data gradient (narrow-image 2D 3x3 stride-1 pad-1: the 64^2 / 32^2 / 16^2 levels)
-def conv_blk_supported(d, dgrad=False) -> bool:
-    return bool(_lib.query("b200_conv_blk_supported", C.byref(d), int(dgrad)))
+def conv_blk_supported(d, dgrad=False) -> int:
+    """0, or 8 + the weight-pack mode (bit 0 data gradient, bit 1 16-channel planes)"""
+    return int(_lib.query("b200_conv_blk_supported", C.byref(d), int(dgrad)))
 
 
 def conv_blk_stats_blocks(d) -> int:
     return int(_lib.query("b200_conv_blk_stats_blocks", C.byref(d)))
 
 
-def conv_blk_pack_weights(w, out, dgrad, O, I, taps=9):
-    _lib.call("b200_conv_blk_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, taps, _st())
+def conv_blk_pack_weights(w, out, mode, O, I, taps=9):
+    _lib.call("b200_conv_blk_pack_weights", _pf(w), _pf(out), int(mode), O, I, taps, _st())
 
 
 def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):

@@ -144,10 +144,11 @@ int b200_conv_row_dgrad(const b200_conv_desc* d, const float* dy, const float* w
  * with mode = data-gradient flag, or b200_conv_blk_pack_weights).  b200_conv_blk_fwd can emit the BatchNorm (sum, sum of
  * squares) of its output as b200_conv_blk_stats_blocks(d) fp64 partials [block][2][cout] for b200_bn_finalize.
  * The same entry points serve the 3D 3x3x3 stride-1 pad-1 convolutions of the VNet (code/networks/vnet.py:28; taps = 27,
- * framework weights [O][I][3][3][3]) with >= 32 channels on both sides: the halo block gains a depth axis. */
+ * framework weights [O][I][3][3][3]): the halo block gains a depth axis; 16-channel tensors are staged as 64-byte rows.
+ * b200_conv_blk_supported returns 0 or 8 + the weight-pack mode (bit 0 data gradient, bit 1 16-channel planes). */
 int b200_conv_blk_supported(const b200_conv_desc* d, int dgrad);
 long long b200_conv_blk_stats_blocks(const b200_conv_desc* d);
-int b200_conv_blk_pack_weights(const float* w, float* out, int dgrad, int O, int I, int taps, cudaStream_t stream);
+int b200_conv_blk_pack_weights(const float* w, float* out, int mode, int O, int I, int taps, cudaStream_t stream);
 int b200_conv_blk_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wpk, const float* bias,
                       float* dst, double* stats_partials, cudaStream_t stream);
 int b200_conv_blk_dgrad(const b200_conv_desc* d, const float* dy, const float* wpk_dgrad, float* dx0, float* dx1,

@@ -366,37 +366,47 @@ def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
 
 # ------------------------------------------------------------------ halo-block tcgen05 forward / data gradient
 def conv_blk_supported(d, dgrad=False):
+    """0 or 8 + weight-pack mode, as csrc/conv_blk.cu:bgeometry (minus the shared-memory fit)"""
     flat = d.kd == 1 and d.id == 1 and d.pd == 0
-    if not ((flat or (d.kd == 3 and d.pd == 1)) and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1):
-        return False
+    is3 = d.kd == 3 and d.pd == 1
+    if not ((flat or is3) and d.kh == 3 and d.kw == 3 and d.stride == 1 and d.ph == 1 and d.pw == 1):
+        return 0
     if d.iw < 4 or d.iw > 96:
-        return False
+        return 0
     a0, a1 = (d.cout, 0) if dgrad else (d.c0, d.c1)
     n0, n1 = (d.c0, d.c1) if dgrad else (d.cout, 0)
-    if a0 <= 0 or a0 % 32 or a1 % 32 or (n0 + n1) % 32:
-        return False
-    nt = 64 if (n0 + n1) % 64 == 0 and (n1 == 0 or n0 % 64 == 0) else 32
-    return not (n1 != 0 and n0 % nt)
+    if a0 <= 0 or a0 % 16 or a1 % 16:
+        return 0
+    cpp = 32 if (a0 % 32 == 0 and a1 % 32 == 0) else 16
+    if cpp == 16 and not is3:
+        return 0
+    ntot = n0 + n1
+    if ntot % 16 or (ntot % 32 and not is3):
+        return 0
+    nt = 64 if ntot % 64 == 0 and (n1 == 0 or n0 % 64 == 0) else (32 if ntot % 32 == 0 and (n1 == 0 or n0 % 32 == 0) else 16)
+    if n1 != 0 and n0 % nt:
+        return 0
+    return 8 + (1 if dgrad else 0) + (2 if cpp == 16 else 0)
 
 
 def conv_blk_stats_blocks(d):
     return d.n * d.id * d.ih   # (any upper bound of the real block count works for the stand-in: unused rows stay zero)
 
 
-def conv_blk_pack_weights(w, out, dgrad, O, I, taps=9):
-    src, ok = _row_pack_index(1 if dgrad else 0, O, I, taps)
+def conv_blk_pack_weights(w, out, mode, O, I, taps=9):
+    src, ok = _row_pack_index(int(mode), O, I, taps)
     out.copy_(_tf32_rna(w.detach().reshape(-1))[src])
 
 
-def _blk_unpack(wpk, dgrad, O, I, kd=1):
-    src, _ = _row_pack_index(1 if dgrad else 0, O, I, 9 * kd)
+def _blk_unpack(wpk, mode, O, I, kd=1):
+    src, _ = _row_pack_index(mode, O, I, 9 * kd)
     W = torch.zeros(O * I * 9 * kd)
     W[src] = wpk.reshape(-1)
     return W.reshape(O, I, kd, 3, 3)
 
 
 def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
-    W = _blk_unpack(wpk, False, d.cout, d.c0 + d.c1, d.kd)
+    W = _blk_unpack(wpk, conv_blk_supported(d, False) - 8, d.cout, d.c0 + d.c1, d.kd)
     y = _ncdhw_to_cl(F.conv3d(_input(d, src0, src1), W, bias, **_kw(d))).reshape(dst.shape)
     dst.copy_(y)
     if stats_part is not None:
@@ -407,7 +417,7 @@ def conv_blk_fwd(d, src0, src1, wpk, bias, dst, stats_part=None):
 
 
 def conv_blk_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
-    W = _blk_unpack(wpk_dgrad, True, d.cout, d.c0 + d.c1, d.kd)
+    W = _blk_unpack(wpk_dgrad, conv_blk_supported(d, True) - 8, d.cout, d.c0 + d.c1, d.kd)
     g = _cl_to_ncdhw(dy, d.n, d.id, d.ih, d.iw, d.cout)
     dx = F.conv_transpose3d(g, W, None, stride=1, padding=(d.pd, d.ph, d.pw))
     _split_store(dx, d, dx0, dx1, accumulate)

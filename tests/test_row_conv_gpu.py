@@ -200,6 +200,10 @@ BLK3_CASES = [
     (1, 5, 9, 7, 32, 64),
     (3, 3, 4, 6, 64, 32),
     (1, 1, 6, 13, 32, 96),
+    (2, 6, 10, 96, 16, 16),      # 16-channel level (64-byte halo rows)
+    (1, 5, 7, 24, 16, 32),
+    (1, 4, 6, 12, 32, 16),
+    (2, 3, 3, 8, 16, 48),
 ]
 
 
@@ -219,11 +223,12 @@ def _ncdhw(t, n, dd, h, w, c):
 def test_blk3d_fwd_and_stats(case):
     n, dd, h, w, cin, cout = case
     d = ops.conv_desc(n, dd, h, w, cin, 0, cout, 3, 1, 1, 3)
-    assert ops.conv_blk_supported(d, False)
+    mode = ops.conv_blk_supported(d, False) - 8
+    assert mode >= 0
     x, wgt, bias, _ = _mk3(case)
     M = n * dd * h * w
     wpk = torch.empty(27 * cout * cin, device=DEV)
-    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, False, cout, cin, 27)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, mode, cout, cin, 27)
     y = torch.full((M, cout), float("nan"), device=DEV)
     nb = ops.conv_blk_stats_blocks(d)
     part = torch.full((nb * 2 * cout,), float("nan"), dtype=torch.float64, device=DEV)
@@ -241,11 +246,12 @@ def test_blk3d_fwd_and_stats(case):
 def test_blk3d_dgrad(case):
     n, dd, h, w, cin, cout = case
     d = ops.conv_desc(n, dd, h, w, cin, 0, cout, 3, 1, 1, 3)
-    assert ops.conv_blk_supported(d, True)
+    mode = ops.conv_blk_supported(d, True) - 8
+    assert mode >= 1
     _, wgt, _, dy = _mk3(case, 1)
     M = n * dd * h * w
     wpk = torch.empty(27 * cout * cin, device=DEV)
-    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, True, cout, cin, 27)
+    ops.conv_blk_pack_weights(wgt.to(DEV), wpk, mode, cout, cin, 27)
     dx = torch.full((M, cin), float("nan"), device=DEV)
     ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx, None)
     torch.cuda.synchronize()

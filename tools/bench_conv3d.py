@@ -8,7 +8,7 @@ from cv_ssl_mis_b200 import ops
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["blk", "tile"]
 dgrad = len(sys.argv) > 3 and sys.argv[3] == "dgrad"
-SHAPES = [(4, 56, 56, 40, 32), (4, 28, 28, 20, 64), (4, 14, 14, 10, 128), (4, 7, 7, 5, 256), (2, 56, 56, 40, 32), (2, 28, 28, 20, 64)]
+SHAPES = [(4, 96, 96, 96, 16), (4, 48, 48, 48, 32), (4, 56, 56, 40, 32), (4, 28, 28, 20, 64), (4, 14, 14, 10, 128), (4, 7, 7, 5, 256), (2, 56, 56, 40, 32), (2, 28, 28, 20, 64)]
 for (n, dd, h, w, c) in SHAPES:
     d = ops.conv_desc(n, dd, h, w, c, 0, c, 3, 1, 1, 3)
     M = n * dd * h * w
@@ -23,7 +23,7 @@ for (n, dd, h, w, c) in SHAPES:
             if not ops.conv_blk_supported(d, dgrad):
                 continue
             wt = torch.empty(27 * c * c, device="cuda")
-            ops.conv_blk_pack_weights(wgt, wt, dgrad, c, c, 27)
+            ops.conv_blk_pack_weights(wgt, wt, ops.conv_blk_supported(d, dgrad) - 8, c, c, 27)
             part = torch.empty(ops.conv_blk_stats_blocks(d) * 2 * c, dtype=torch.float64, device="cuda")
             fn = (lambda: ops.conv_blk_dgrad(d, x0, wt, y, None, False)) if dgrad else (lambda: ops.conv_blk_fwd(d, x0, None, wt, bias, y, part))
         else:
