@@ -19,31 +19,42 @@ def no_dropout(monkeypatch):
     monkeypatch.setattr(unet_mod, "DROPOUT", [0.0] * 5)
 
 
-def test_unet_matches_reference_fixture(golden, no_dropout):
-    """Forward logits, loss and gradients of the reference UNet itself (tests/golden/unet_small.pt)."""
+@pytest.mark.parametrize("exact", [True, False])
+def test_unet_matches_reference_fixture(golden, no_dropout, exact):
+    """Forward logits, loss and gradients of the reference UNet itself (tests/golden/unet_small.pt); exact=False is the
+    production TF32 path (tcgen05 / tile kernels) with TF32 tolerances: logits 5e-2 of the largest logit, loss 1e-2, gradient
+    norms 0.15 per tensor (the backward chain amplifies TF32 round-off up to ~9 % at the first layer, see the full-size test)."""
     g = golden("unet_small.pt")
     torch.manual_seed(g["seed"])
-    net = unet_mod.UNet(1, 4, exact=True)
+    net = unet_mod.UNet(1, 4, exact=exact)
     if abs(checksum(net.state_dict()) - g["checksum"]) > 1e-6 * g["checksum"]:
         pytest.skip("torch RNG stream differs from the fixture's")
     net = net.cuda()
     net.train()
     logits = net(g["x"].cuda())
-    torch.testing.assert_close(logits.cpu(), g["logits"], rtol=1e-3, atol=1e-4)
+    big = float(g["logits"].abs().max())
+    if exact:
+        torch.testing.assert_close(logits.cpu(), g["logits"], rtol=1e-3, atol=1e-4)
+    else:
+        assert float((logits.cpu() - g["logits"]).abs().max()) <= 5e-2 * big
     loss, ce, dice = O.supervised_loss(logits, g["y"].cuda(), 4)            # torch autograd over our module
-    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4 if exact else 1e-2, atol=1e-5)
     loss.backward()
     for n, p in net.named_parameters():
         gn = float(p.grad.norm())
-        assert abs(gn - g["grad_norm"][n]) <= 5e-3 * g["grad_norm"][n] + 1e-6, (n, gn, g["grad_norm"][n])
-        torch.testing.assert_close(p.grad.flatten()[:8].cpu(), g["grad_head"][n], rtol=1e-2, atol=1e-5, msg=lambda m, n=n: f"{n}: {m}")
+        assert abs(gn - g["grad_norm"][n]) <= (5e-3 if exact else 0.15) * g["grad_norm"][n] + (1e-6 if exact else 1e-4), (n, gn, g["grad_norm"][n])
+        if exact:
+            torch.testing.assert_close(p.grad.flatten()[:8].cpu(), g["grad_head"][n], rtol=1e-2, atol=1e-5, msg=lambda m, n=n: f"{n}: {m}")
     sd = net.state_dict()
     for k, v in g["running"].items():
-        torch.testing.assert_close(sd[k].cpu(), v, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(sd[k].cpu(), v, rtol=1e-4 if exact else 2e-2, atol=1e-5 if exact else 1e-3)
     net.eval()
     with torch.no_grad():
         ev = net(g["x"].cuda())
-    torch.testing.assert_close(ev.cpu(), g["logits_eval"], rtol=1e-3, atol=1e-4)
+    if exact:
+        torch.testing.assert_close(ev.cpu(), g["logits_eval"], rtol=1e-3, atol=1e-4)
+    else:
+        assert float((ev.cpu() - g["logits_eval"]).abs().max()) <= 5e-2 * float(g["logits_eval"].abs().max())
 
 
 @pytest.mark.parametrize("exact", [True, False])

@@ -16,22 +16,28 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def test_vnet_matches_reference_fixture(golden):
-    """Student logits of the reference's own VNet (tests/golden/vnet_uamt.pt) -- exact (3xTF32) mode."""
+@pytest.mark.parametrize("exact", [True, False])
+def test_vnet_matches_reference_fixture(golden, exact):
+    """Student logits of the reference's own VNet (tests/golden/vnet_uamt.pt): exact (3xTF32) mode, and the production TF32
+    path (3-D halo-block tcgen05 forward / data gradient, row-ring weight gradient) with TF32 tolerances."""
     g = golden("vnet_uamt.pt")
     torch.manual_seed(g["seed"])
-    net = vnet_mod.VNet(1, 2, has_dropout=False, exact=True)          # the fixture ran with Dropout3d p = 0
+    net = vnet_mod.VNet(1, 2, has_dropout=False, exact=exact)         # the fixture ran with Dropout3d p = 0
     if abs(checksum(net.state_dict()) - g["init_ck"][0]) > 1e-6 * g["init_ck"][0]:
         pytest.skip("torch RNG stream differs from the fixture's")
     x, y, _ = O.vnet_fixture_inputs(g["gen_seed"], g["B"], g["labeled_bs"], g["P"])
     net = net.cuda().train()
     logits = net(x.cuda())
-    torch.testing.assert_close(logits[:, :, ::4, ::4, ::4].cpu(), g["logits_sub"], rtol=2e-3, atol=3e-4)
-    assert abs(float(logits.abs().mean()) - g["logits_stat"][1]) < 1e-3 * g["logits_stat"][1]
+    if exact:
+        torch.testing.assert_close(logits[:, :, ::4, ::4, ::4].cpu(), g["logits_sub"], rtol=2e-3, atol=3e-4)
+    else:
+        err = float((logits[:, :, ::4, ::4, ::4].cpu() - g["logits_sub"]).abs().max())
+        assert err <= 5e-2 * float(g["logits_sub"].abs().max()), err
+    assert abs(float(logits.detach().abs().mean()) - g["logits_stat"][1]) < (1e-3 if exact else 1e-2) * g["logits_stat"][1]
     Lb = g["labeled_bs"]
     loss, ce, dice = O.supervised_loss(logits[:Lb], y[:Lb].cuda(), 2)
-    torch.testing.assert_close(ce.cpu(), g["ce"], rtol=1e-3, atol=1e-5)
-    torch.testing.assert_close(dice.cpu(), g["dice"], rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(ce.cpu(), g["ce"], rtol=1e-3 if exact else 1e-2, atol=1e-5)
+    torch.testing.assert_close(dice.cpu(), g["dice"], rtol=1e-3 if exact else 1e-2, atol=1e-5)
     loss.backward()                                                    # backward runs (values are checked in the step test)
     assert all(torch.isfinite(p.grad).all() for p in net.parameters())
 
