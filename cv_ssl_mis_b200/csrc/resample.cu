@@ -377,6 +377,71 @@ B200_API int b200_colsum(const float* g, long long M, int C, float* out, int acc
     return B200_OK;
 }
 
+// ---------------------------------------------------------------- 2x2x2 stride-2 (transposed) convolutions as GEMMs
+// A kernel-2 stride-2 convolution touches every input voxel exactly once, so it is the GEMM
+//     y[(n,do,ho,wo)][co] = sum over (kd,kh,kw,ci) of  xs[(n,do,ho,wo)][(kd,kh,kw,ci)] * W2[co][(kd,kh,kw,ci)]
+// over the space-to-depth view xs of x (code/networks/vnet.py:73), and its transpose (vnet.py:100, the UNETR up-blocks)
+// is ys[(n,d,h,w)][(kd,kh,kw,co)] = x W2d^T scattered depth-to-space.  These two kernels are the views (pure 16-byte
+// copies; the (kw, c) pairs are contiguous on both sides); the products run on gemm_umma_kernel (b200_linear_fwd).
+struct S2dP {
+    int D, H, W, C4;             // INPUT dims of the strided conv / of the transposed conv, channels / 4 of the moved tensor
+    FastDiv fdC4, fdW2, fdH2, fdD2;
+};
+
+// gather: DIR = 0: xs[m][(tap, c)] = x[fine voxel]     scatter: DIR = 1: y[fine voxel] = ys[m][(tap, c)] + bias[c]
+template <int DIR>
+__global__ void __launch_bounds__(256) s2d_kernel(const float4* __restrict__ src, float4* __restrict__ dst, const float* __restrict__ bias,
+                                                  long long total4, const S2dP p) {
+    const int Wc = DIR == 0 ? p.W / 2 : p.W, Hc = DIR == 0 ? p.H / 2 : p.H, Dc = DIR == 0 ? p.D / 2 : p.D;   // coarse grid
+    const int Wf = 2 * Wc, Hf = 2 * Hc, Df = 2 * Dc;                                                          // fine grid
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        // coarse-major index: i = ((m * 8 + tap) * C4 + c4)
+        uint32_t r, c4, tap, wo, ho, dz, n;
+        p.fdC4.divmod((uint32_t)i, r, c4);
+        tap = r & 7; r >>= 3;
+        p.fdW2.divmod(r, r, wo);
+        p.fdH2.divmod(r, r, ho);
+        p.fdD2.divmod(r, n, dz);
+        const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
+        const long long fine = ((((long long)n * Df + 2 * dz + kd) * Hf + 2 * ho + kh) * Wf + 2 * wo + kw) * p.C4 + c4;
+        if (DIR == 0) {
+            dst[i] = __ldg(src + fine);
+        } else {
+            float4 v = __ldg(src + i);
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            dst[fine] = v;
+        }
+    }
+    (void)Wc; (void)Hc; (void)Dc;
+}
+
+static int s2d_launch(int dir, const float* src, float* dst, const float* bias, int N, int D, int H, int W, int C, cudaStream_t st,
+                      const char* who) {
+    B200_REQUIRE(src && dst && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "%s: bad arguments (C %% 4 == 0)", who);
+    B200_REQUIRE(dir == 1 || ((D | H | W) & 1) == 0, "%s: D, H, W must be even", who);
+    S2dP p;
+    p.D = D; p.H = H; p.W = W; p.C4 = C / 4;
+    const int Wc = dir == 0 ? W / 2 : W, Hc = dir == 0 ? H / 2 : H, Dc = dir == 0 ? D / 2 : D;
+    p.fdC4.init(p.C4); p.fdW2.init(Wc); p.fdH2.init(Hc); p.fdD2.init(Dc);
+    const long long total4 = (long long)N * Dc * Hc * Wc * 8 * p.C4;
+    B200_REQUIRE(total4 < (1ll << 32), "%s: tensor too large", who);
+    if (dir == 0) s2d_kernel<0><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), nullptr, total4, p);
+    else s2d_kernel<1><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), bias, total4, p);
+    B200_CHECK_LAUNCH(who);
+    return B200_OK;
+}
+
+B200_API int b200_s2d_gather3d(const float* x, float* xs, int N, int D, int H, int W, int C, cudaStream_t st) {
+    return s2d_launch(0, x, xs, nullptr, N, D, H, W, C, st, "s2d_gather3d");
+}
+
+B200_API int b200_d2s_scatter3d(const float* ys, const float* bias, float* y, int N, int D, int H, int W, int C, cudaStream_t st) {
+    return s2d_launch(1, ys, y, bias, N, D, H, W, C, st, "d2s_scatter3d");
+}
+
 B200_API int b200_add(const float* a, const float* b, float* c, long long n, cudaStream_t st) {
     B200_REQUIRE(a && b && c && n > 0 && (n & 3) == 0, "add: bad arguments (n multiple of 4)");
     add_kernel<<<ew_grid(n / 4), 256, 0, st>>>(a, b, c, n / 4);

@@ -137,6 +137,23 @@ class ConvLayer:
                 rt.need_scratch(max(ops.linear_wgrad_workspace_bytes(self.M, self.cout, self.cin),
                                     ops.colsum_workspace_bytes(self.M, self.cout)))
             return self
+        # 3D 2x2x2 stride-2 convs / transposed convs (vnet.py:73,100, the UNETR up-blocks): every input voxel is used once,
+        # so the forward is a pure GEMM over the space-to-depth view (tcgen05 GEMM + one 16-byte copy kernel).
+        # B200_K2S2=generic keeps the implicit-GEMM kernels for A/B runs; the backward still uses them.
+        self.k2s2_gemm = False
+        self.wp_gemm = None
+        if (self.dims == 3 and self.k == 2 and self.stride == 2 and self.pad == 0 and c1 == 0 and not rt.exact and not self.out_nchw
+                and os.environ.get("B200_K2S2", "gemm") == "gemm" and c0 % 4 == 0 and self.cout % 4 == 0):
+            if is_conv and id_ % 2 == 0 and ih % 2 == 0 and iw % 2 == 0:
+                self.k2s2_gemm = bool(ops.linear_supported(self.M, self.cout, 8 * c0, 0))
+                shape = (self.M, 8 * c0)
+            elif not is_conv:
+                self.k2s2_gemm = bool(ops.linear_supported(n * id_ * ih * iw, 8 * self.cout, c0, 0))
+                shape = (n * id_ * ih * iw, 8 * self.cout)
+            if self.k2s2_gemm:
+                self.gview = torch.empty(shape, dtype=torch.float32, device=dev)       # xs (conv) / ys (transposed conv)
+                self.gemm_mode = PACK_CONV_DGRAD_D2S if is_conv else PACK_DECONV_DGRAD  # [cout][8 cin] / [8 cout][cin]
+                self.wp_gemm = torch.empty(ops.conv_packed_floats(self.gemm_mode, O, I, self.T), dtype=torch.float32, device=dev)
         # 2D 3x3: tcgen05/TMEM kernel (B200_CONV=tile falls back to the mma.sync tile kernel for A/B comparisons)
         want_umma = is_conv and not rt.exact and os.environ.get("B200_CONV", "umma") == "umma"
         # measured (tools/bench_conv.py): with fp32 operands the UMMA is bound by its shared-memory operand reads,
@@ -196,6 +213,8 @@ class ConvLayer:
         jobs = []
         if self.gemm:
             return jobs
+        if self.wp_gemm is not None:
+            jobs.append((w, self.wp_gemm, 0, self.gemm_mode, O, I, T))
         if not self.use_c1_kernel:
             if self.row_fwd:
                 jobs.append((w, self.wp_fwd, 3, self.row_fwd - 8, O, I, T))
@@ -224,6 +243,8 @@ class ConvLayer:
         O, I = self.cout, self.cin
         if self.gemm:
             return
+        if self.wp_gemm is not None:
+            ops.conv_pack_weights(self.conv.weight, self.wp_gemm, self.gemm_mode, O, I, self.T)
         if self.use_c1_kernel:
             pass
         elif self.row_fwd:
@@ -254,6 +275,14 @@ class ConvLayer:
         self.bn_train = train
         if self.gemm:
             ops.linear_fwd(src0, src1, self.conv.weight.view(self.cout, self.cin), self.conv.bias, self.y, self.M, self.cout)
+        elif self.k2s2_gemm and self.kind == "conv":
+            d = self.desc
+            ops.s2d_gather3d(src0, self.gview, d.n, d.id, d.ih, d.iw, self.cin)
+            ops.linear_fwd(self.gview, None, self.wp_gemm.view(self.cout, 8 * self.cin), self.conv.bias, self.y, self.M, self.cout)
+        elif self.k2s2_gemm:
+            d = self.desc
+            ops.linear_fwd(src0, None, self.wp_gemm.view(8 * self.cout, self.cin), None, self.gview, self.gview.shape[0], 8 * self.cout)
+            ops.d2s_scatter3d(self.gview, self.conv.bias, self.y, d.n, d.id, d.ih, d.iw, self.cout)
         elif self.use_c1_kernel:
             ops.conv_c1_fwd(self.desc, src0, self.conv.weight, self.conv.bias, self.y)
         elif self.row_fwd:

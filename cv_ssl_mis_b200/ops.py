@@ -161,6 +161,16 @@ def bn_finalize(part, nblocks, M, C_, gamma, beta, eps, momentum, running_mean, 
 
 
 # halo-block tcgen05 forward / data gradient (narrow-image 2D 3x3 stride-1 pad-1: the 64^2 / 32^2 / 16^2 levels)
+def s2d_gather3d(x, xs, N, D, H, W, C):
+    """xs[(n,do,ho,wo)][(kd,kh,kw,c)] = x[n][2do+kd][2ho+kh][2wo+kw][c]  (space-to-depth view for the 2x2x2 stride-2 convs)"""
+    _lib.call("b200_s2d_gather3d", _pf(x), _pf(xs), N, D, H, W, C, _st())
+
+
+def d2s_scatter3d(ys, bias, y, N, D, H, W, C):
+    """y[n][2d+kd][2h+kh][2w+kw][c] = ys[(n,d,h,w)][(kd,kh,kw,c)] + bias[c]  (depth-to-space of the transposed 2x2x2 convs)"""
+    _lib.call("b200_d2s_scatter3d", _pf(ys), _pf(bias), _pf(y), N, D, H, W, C, _st())
+
+
 def conv_blk_supported(d, dgrad=False) -> int:
     """0, or 8 + the weight-pack mode (bit 0 data gradient, bit 1 16-channel planes)"""
     return int(_lib.query("b200_conv_blk_supported", C.byref(d), int(dgrad)))

@@ -364,6 +364,19 @@ def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
     _split_store(dx, d, dx0, dx1, accumulate)
 
 
+# ------------------------------------------------------------------ 2x2x2 stride-2 views
+def s2d_gather3d(x, xs, N, D, H, W, C):
+    v = x.reshape(N, D // 2, 2, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 5, 2, 4, 6, 7)     # n do ho wo kd kh kw c
+    xs.copy_(v.reshape(xs.shape))
+
+
+def d2s_scatter3d(ys, bias, y, N, D, H, W, C):
+    v = ys.reshape(N, D, H, W, 2, 2, 2, C)
+    if bias is not None:
+        v = v + bias
+    y.copy_(v.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(y.shape))                               # n d kd h kh w kw c
+
+
 # ------------------------------------------------------------------ halo-block tcgen05 forward / data gradient
 def conv_blk_supported(d, dgrad=False):
     """0 or 8 + weight-pack mode, as csrc/conv_blk.cu:bgeometry (minus the shared-memory fit)"""

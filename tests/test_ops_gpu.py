@@ -453,3 +453,44 @@ def test_first_layer_kernels(case):
     ref.conv_c1_wgrad(desc, x, dy, None, dw_ref, db_ref)
     torch.testing.assert_close(dw.cpu(), dw_ref, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db.cpu(), db_ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", [(2, 4, 6, 8, 16), (1, 2, 2, 4, 32), (3, 6, 4, 2, 8)])
+def test_k2s2_views_and_gemm_match_torch(case):
+    """2x2x2 stride-2 conv = GEMM over the space-to-depth view, transposed conv = GEMM + depth-to-space scatter
+    (code/networks/vnet.py:73,100): the two copy kernels bit-exact against the fake-ops restatement, the composed
+    products against torch's conv3d / conv_transpose3d (TF32 tolerance)."""
+    import torch.nn.functional as F
+    from tests import fake_ops as ref
+    from cv_ssl_mis_b200._lib import PACK_CONV_DGRAD_D2S, PACK_DECONV_DGRAD
+    n, dd, h, w, c = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n * dd * h * w, c, generator=g)
+    xs, xs_r = torch.empty(n * dd * h * w // 8, 8 * c, device="cuda"), torch.empty(n * dd * h * w // 8, 8 * c)
+    ops.s2d_gather3d(x.cuda(), xs, n, dd, h, w, c)
+    ref.s2d_gather3d(x, xs_r, n, dd, h, w, c)
+    assert torch.equal(xs.cpu(), xs_r)
+    cout = 2 * c
+    wgt, bias = torch.randn(cout, c, 2, 2, 2, generator=g) * (8 * c) ** -0.5, torch.randn(cout, generator=g)
+    wp = torch.empty(ops.conv_packed_floats(PACK_CONV_DGRAD_D2S, cout, c, 8), device="cuda")
+    ops.conv_pack_weights(wgt.cuda(), wp, PACK_CONV_DGRAD_D2S, cout, c, 8)
+    y = torch.empty(xs.shape[0], cout, device="cuda")
+    ops.linear_fwd(xs, None, wp.view(cout, 8 * c), bias.cuda(), y, xs.shape[0], cout)
+    xn = x.view(n, dd, h, w, c).permute(0, 4, 1, 2, 3).double()
+    want = F.conv3d(xn, wgt.double(), bias.double(), stride=2).permute(0, 2, 3, 4, 1).reshape(-1, cout)
+    torch.testing.assert_close(y.cpu().double(), want, rtol=2e-2, atol=5e-3)
+    # transposed: c -> c // 2 channels, output twice the size
+    co = c // 2
+    wt, bt = torch.randn(c, co, 2, 2, 2, generator=g) * c ** -0.5, torch.randn(co, generator=g)
+    wpt = torch.empty(ops.conv_packed_floats(PACK_DECONV_DGRAD, co, c, 8), device="cuda")
+    ops.conv_pack_weights(wt.cuda(), wpt, PACK_DECONV_DGRAD, co, c, 8)
+    M = n * dd * h * w
+    ys = torch.empty(M, 8 * co, device="cuda")
+    if ops.linear_supported(M, 8 * co, c, 0):
+        ops.linear_fwd(x.cuda(), None, wpt.view(8 * co, c), None, ys, M, 8 * co)
+        out, out_r = torch.empty(8 * M, co, device="cuda"), torch.empty(8 * M, co)
+        ops.d2s_scatter3d(ys, bt.cuda(), out, n, dd, h, w, co)
+        ref.d2s_scatter3d(ys.cpu(), bt, out_r, n, dd, h, w, co)
+        assert torch.equal(out.cpu(), out_r)
+        want = F.conv_transpose3d(xn, wt.double(), bt.double(), stride=2).permute(0, 2, 3, 4, 1).reshape(-1, co)
+        torch.testing.assert_close(out.cpu().double(), want, rtol=2e-2, atol=5e-3)
