@@ -6,12 +6,14 @@ from ._common import (add_swin_flags, base_parser, build_swin_config, process_gr
                       snapshot_dir, synthetic_batches)
 
 
-def main(argv=None, loader=None):
+def main(argv=None, loader=None, defaults=None):
     p = base_parser("ACDC/Cross_Teaching_Between_CNN_Transformer", "unet", 16, (224, 224), 8, 7, "../data/ACDC", num_classes=4)
     add_swin_flags(p)
     p.add_argument('--model2', type=str, default="ViT_Seg", help='second network (reference: the Swin-UNet ViT_seg)')
     p.add_argument('--pseudo_loss', type=str, default="dice", choices=["dice", "ce"],
                    help='dice: cross teaching (:242-245); ce: cross pseudo supervision')
+    if defaults:                                                  # same loop under another reference script name
+        p.set_defaults(**defaults)
     args = p.parse_args(argv)
     seed_everything(args)
     from ..networks.net_factory import net_factory

@@ -2,20 +2,27 @@
 --uncertainty_T 8, and code/train_fully_supervised_2D.py with --labeled_bs equal to --batch_size)."""
 import sys
 
-from ._common import base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
+from ._common import add_swin_flags, base_parser, build_swin_config, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None):
+def main(argv=None, loader=None, defaults=None):
     p = base_parser("ACDC/Mean_Teacher", "unet", 24, (224, 224), 12, 7, "../data/ACDC", num_classes=4)
     p.add_argument('--uncertainty_T', type=int, default=0, help='8: the uncertainty-aware variant (MC-dropout mask)')
+    p.add_argument('--supervised', type=int, default=0, help='1: no unlabeled half (train_fully_supervised_2D.py)')
+    add_swin_flags(p)                                             # only used by --model ViT_Seg (train_mean_teacher_ViT.py)
+    if defaults:                                                  # same loop under another reference script name
+        p.set_defaults(**defaults)
     args = p.parse_args(argv)
+    if args.supervised:
+        args.labeled_bs = args.batch_size
     seed_everything(args)
     from ..networks.net_factory import net_factory
     from ..trainers import MeanTeacherTrainer
     pg, rank = process_group()
 
     def create_model(ema=False):                                  # code/train_mean_teacher_2D.py:136-144
-        model = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)
+        kw = dict(config=build_swin_config(args), img_size=args.patch_size) if args.model == "ViT_Seg" else {}
+        model = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes, **kw)
         if model is None:
             raise SystemExit(f"--model {args.model}: not built (available: unet, ViT_Seg)")
         if ema:

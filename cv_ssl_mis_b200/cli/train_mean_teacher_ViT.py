@@ -1,0 +1,14 @@
+"""Command line of code/train_mean_teacher_ViT.py (Mean Teacher over two Swin-UNets): the loop of cli/train_mean_teacher_2D.py with the defaults of this script."""
+import sys
+
+from . import train_mean_teacher_2D as _impl
+
+DEFAULTS = dict(exp='ACDC/Mean_Teacher_ViT', patch_size=[224, 224], labeled_num=7, model='ViT_Seg')
+
+
+def main(argv=None, loader=None):
+    return _impl.main(argv, loader, defaults=DEFAULTS)
+
+
+if __name__ == "__main__":
+    print(main(sys.argv[1:]))

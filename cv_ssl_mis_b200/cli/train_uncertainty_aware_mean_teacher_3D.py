@@ -5,9 +5,11 @@ import sys
 from ._common import base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None):
+def main(argv=None, loader=None, defaults=None):
     p = base_parser("BraTs2019_Uncertainty_Aware_Mean_Teacher", "vnet", 4, (96, 96, 96), 2, 25, "../data/BraTS2019")
     p.add_argument('--uncertainty_T', type=int, default=8, help='stochastic teacher passes (reference: T = 8)')
+    if defaults:                                                  # same loop under another reference script name
+        p.set_defaults(**defaults)
     args = p.parse_args(argv)
     args.num_classes = 2                                          # :100
     seed_everything(args)

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) colpart_finalize_kernel(const float* __re
 
 static inline int ln_grid(long long M) {
     long long want = (M + 7) / 8;
-    const long long cap = (long long)b200_num_sms() * 2;
+    const long long cap = (long long)b200_num_sms() * 8;      // one row in flight per warp: the sweep needs many resident warps to cover the load latency
     return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -104,3 +104,22 @@ def test_swin_config_from_cfg_and_opts(tmp_path):
         build_swin_config(argparse.Namespace(cfg=str(y), opts=["MODEL.NOPE", "1"], batch_size=8))
     with pytest.raises(SystemExit):
         build_swin_config(argparse.Namespace(cfg=str(tmp_path / "missing.yaml"), opts=None, batch_size=8))
+
+
+def test_reference_script_names(cpu_env):
+    """The reference's other script names on the path run the same loops with their own defaults
+    (code/train_uncertainty_aware_mean_teacher_2D.py, train_fully_supervised_2D.py, train_mean_teacher_3D.py,
+    train_cross_pseudo_supervision_2D.py; train_mean_teacher_ViT.py is only parsed here -- a 224^2 Swin-UNet is a GPU job)."""
+    from cv_ssl_mis_b200.cli import (train_uncertainty_aware_mean_teacher_2D as uamt2d, train_fully_supervised_2D as fs2d,
+                                     train_mean_teacher_3D as mt3d, train_cross_pseudo_supervision_2D as cps,
+                                     train_mean_teacher_ViT as mtvit)
+    small = ["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32"]
+    assert uamt2d.main(small + COMMON) == "Training Finished!"
+    assert (cpu_env / "model" / "ACDC" / "Uncertainty_Aware_Mean_Teacher_136_labeled" / "unet" / "ema_iter_2.pth").exists()
+    assert fs2d.main(["--batch_size", "2", "--patch_size", "32", "32"] + COMMON) == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Fully_Supervised_50_labeled" / "unet"
+    assert (snap / "iter_2.pth").exists() and not (snap / "ema_iter_2.pth").exists()
+    assert cps.main(small + COMMON) == "Training Finished!"
+    assert (cpu_env / "model" / "ACDC" / "Cross_Pseudo_Supervision_1_labeled" / "unet" / "model2_iter_2.pth").exists()
+    assert mt3d.main(["--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
+    assert mtvit.DEFAULTS["model"] == "ViT_Seg" and mtvit.DEFAULTS["exp"] == "ACDC/Mean_Teacher_ViT"
