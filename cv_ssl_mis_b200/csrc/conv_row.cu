@@ -37,7 +37,7 @@ namespace {
 
 using namespace umma;
 
-constexpr int CR_THREADS = 192;
+constexpr int CR_THREADS = 320;      // TMA warp, MMA warp, 4 epilogue warps, 4 statistics warps
 constexpr int MAX_R = 8;
 constexpr int NACC = 4;
 
@@ -198,14 +198,65 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
             else { wslot = w1; ahead = 2; }
             h = (h == p.H - 1) ? 0 : h + 1;
         }
+    } else if (warp >= 6) {
+        // ------------------------------------------------------------------ statistics warps (BatchNorm sum / sum of squares)
+        // The epilogue warps are the throughput limit of this kernel (profiles/r2_ncu_full_conv_row.csv: ~3400 warp
+        // instructions per 128-pixel block, 60 % of them the statistics pass), so the statistics of a staged tile are taken
+        // by four more warps while the epilogue warps already convert the next accumulator.  Hand-off through named
+        // barriers per staging buffer: 6 + sb "tile staged" (epilogue arrives, statistics warps wait), 4 + sb "tile read"
+        // (statistics warps arrive, the epilogue waits before overwriting the buffer two blocks later).
+        const int st_ = (warp - 6) * 32 + lane;
+        const int Nc = p.Cout, G = p.G;
+        const int nsub = 128 / Nc;                                // threads sharing a channel
+        const int sc = st_ % Nc, ssub = st_ / Nc;
+        const bool use_s = p.stats && !(p.debug & 5);
+        if (use_s) {
+            double d1 = 0.0, d2 = 0.0;
+            const int total = (r1 - r0) * p.nblk;
+            const int gi = sc / G, cg = sc % G;
+            for (int k = 0; k < total; ++k) {
+                const int sb = k & 1;
+                const uint32_t sbase = stg + (uint32_t)sb * stg_bytes;
+                if (sb == 0) asm volatile("bar.sync 6, 256;" ::: "memory"); else asm volatile("bar.sync 7, 256;" ::: "memory");
+                // channel sc over rows [ssub * Nc, ssub * Nc + Nc) of the staged tile (nsub * Nc == 128)
+                const uint32_t gb = sbase + (uint32_t)gi * (128u * G * 4u) + (uint32_t)((cg & 3) * 4);
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < Nc; ++i) {
+                    const int row = ssub * Nc + i;
+                    const int srow = G == 32 ? row : (row >> 1), chunk = (G == 32 ? 0 : (row & 1) * 4) + (cg >> 2);
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(gb + (uint32_t)srow * 128u + (uint32_t)((chunk ^ (srow & 7)) * 16)));
+                    s1 += v;
+                    s2 += v * v;
+                }
+                d1 += (double)s1;
+                d2 += (double)s2;
+                if (k + 2 < total) {                              // somebody will wait for this buffer again
+                    if (sb == 0) asm volatile("bar.arrive 4, 256;" ::: "memory"); else asm volatile("bar.arrive 5, 256;" ::: "memory");
+                }
+            }
+            // cross-thread reduction in the (now idle) first staging buffer: [sub][2][64] doubles = 8 KB
+            asm volatile("bar.sync 3, 256;" ::: "memory");        // the epilogue's last TMA store has read the staging buffers
+            double* sred = reinterpret_cast<double*>(smem_raw + (stg - smem_u32(smem_raw)));
+            sred[(ssub * 2 + 0) * 64 + sc] = d1;
+            sred[(ssub * 2 + 1) * 64 + sc] = d2;
+            asm volatile("bar.sync 8, 128;" ::: "memory");
+            const int Cr = Nc / p.fold;                          // real channels (pair mode: columns (pa, c) fold onto c)
+            if (st_ < 2 * Cr) {
+                const int which = st_ / Cr, c = st_ % Cr;
+                double s = 0.0;
+                for (int k = 0; k < nsub; ++k)
+                    for (int fo = 0; fo < p.fold; ++fo) s += sred[(k * 2 + which) * 64 + fo * Cr + c];
+                p.stats[(size_t)blockIdx.x * 2 * Cr + which * Cr + c] = s;
+            }
+        }
     } else {
         // ------------------------------------------------------------------ epilogue (4 warps = 128 accumulator rows)
         const int q = warp & 3, et = q * 32 + lane;              // TMEM lane quarter; thread index within the epilogue
         const int Nc = p.Cout, G = p.G;
-        const int nsub = 128 / Nc;                                // threads sharing a channel in the statistics pass
-        const int sc = et % Nc, ssub = et / Nc;
-        double d1 = 0.0, d2 = 0.0;
-        int buf = 0, fph = 0, sb = 0, nstore = 0;
+        const bool use_s = p.stats && !(p.debug & 5);            // statistics warps active
+        int buf = 0, fph = 0, sb = 0, nstore = 0, kblk = 0;
         int n = r0 / p.H, h = r0 - n * p.H;
         for (int r = r0; r < r1; ++r) {
             for (int b = 0; b < p.nblk; ++b) {
@@ -222,6 +273,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                 }
                 // staging buffer sb was handed to the TMA unit two blocks ago: its reads must be done
                 if (et == 0 && nstore >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (use_s && kblk >= 2) {                         // ... and the statistics warps must have read it
+                    if (sb == 0) asm volatile("bar.sync 4, 256;" ::: "memory"); else asm volatile("bar.sync 5, 256;" ::: "memory");
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
                 for (int c0 = 0; c0 < Nc; c0 += 16) {
@@ -256,6 +310,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (use_s) {
+                    if (sb == 0) asm volatile("bar.arrive 6, 256;" ::: "memory"); else asm volatile("bar.arrive 7, 256;" ::: "memory");
+                }
                 if (et == 0 && !(p.debug & 2)) {
                     // G = 32: box {32 channels, 128 k-pixels}; G = 16: box {one 128-byte pixel pair, 64 pairs}
                     const int pix0 = G == 32 ? (n * p.H + h) * p.W + 128 * b : ((n * p.H + h) * p.W + 128 * b) >> 1;
@@ -274,44 +331,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_row_kernel(const __grid_co
                     tma_commit_group();
                     ++nstore;
                 }
-                if (p.stats && !(p.debug & 1)) {
-                    // channel sc over rows [ssub * Nc, ssub * Nc + Nc) of the staged tile (nsub * Nc == 128)
-                    const int gi = sc / G, cg = sc % G;
-                    const uint32_t gb = sbase + (uint32_t)gi * (128u * G * 4u) + (uint32_t)((cg & 3) * 4);
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-                    for (int i = 0; i < Nc; ++i) {
-                        const int row = ssub * Nc + i;
-                        const int srow = G == 32 ? row : (row >> 1), chunk = (G == 32 ? 0 : (row & 1) * 4) + (cg >> 2);
-                        float v;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(gb + (uint32_t)srow * 128u + (uint32_t)((chunk ^ (srow & 7)) * 16)));
-                        s1 += v;
-                        s2 += v * v;
-                    }
-                    d1 += (double)s1;
-                    d2 += (double)s2;
-                }
+                ++kblk;
                 sb ^= 1;
                 if (++buf == NACC) { buf = 0; fph ^= 1; }
             }
             if (++h == p.H) { h = 0; ++n; }
         }
-        if (p.stats) {
-            // cross-thread reduction in the (now idle) first staging buffer: [sub][2][64] doubles = 8 KB
+        if (use_s) {
             if (et == 0) tma_wait_group_read0();
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            double* sred = reinterpret_cast<double*>(smem_raw + (stg - smem_u32(smem_raw)));
-            sred[(ssub * 2 + 0) * 64 + sc] = d1;
-            sred[(ssub * 2 + 1) * 64 + sc] = d2;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int Cr = Nc / p.fold;                          // real channels (pair mode: columns (pa, c) fold onto c)
-            if (et < 2 * Cr) {
-                const int which = et / Cr, c = et % Cr;
-                double s = 0.0;
-                for (int k = 0; k < nsub; ++k)
-                    for (int fo = 0; fo < p.fold; ++fo) s += sred[(k * 2 + which) * 64 + fo * Cr + c];
-                p.stats[(size_t)blockIdx.x * 2 * Cr + which * Cr + c] = s;
-            }
+            asm volatile("bar.sync 3, 256;" ::: "memory");        // hands the staging buffers to the statistics warps' reduction
         }
         if (et == 0) tma_wait_group0();
     }
