@@ -62,8 +62,6 @@ SIGNATURES = {
     "b200_conv_umma_supported": (_I, [_D, _I]),
     "b200_conv_umma_packed_floats": (_L, [_I, _I, _I, _I]),
     "b200_conv_umma_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),
-    "b200_conv_umma_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
-    "b200_conv_umma_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_fwd": (_I, [_D, _P, _P, _P, _P, _P, _I, _S]),
     "b200_conv_umma2_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
     "b200_conv_row_wgrad_supported": (_I, [_D]),

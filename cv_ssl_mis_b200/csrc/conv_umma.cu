@@ -22,26 +22,6 @@ namespace {
 
 constexpr int UKC = 16;          // channels per chunk (two K = 8 TF32 MMAs per tap)
 
-struct UmmaP {
-    const float* src0;
-    const float* src1;
-    int C0, C1, Cin;
-    int N, H, W;
-    int TH, TW, HW;              // tile rows / cols, halo width (TW + 2)
-    int NPIXA;                   // halo pixel slots allocated per k-chunk plane (multiple of 8)
-    int tiles_w, tiles_r;
-    FastDiv fd_hw, fd_hp2;       // / HW, / (H + 2)
-    const float* wt;             // [chunk][tap][kq][CoutP][4], TF32-rounded
-    int Cout, CoutP;
-    const float* bias;
-    float* dst0;
-    float* dst1;
-    int D0, D1;
-    int out_nchw;
-    int accumulate;
-    int nstages;                 // 1 if the reduction is a single chunk, else 2
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
@@ -95,178 +75,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 
-template <int BN>
-struct USmem {
-    static constexpr int W_BYTES = 9 * 4 * BN * 16;                     // [tap][kq][BN][16 B]
-    __host__ __device__ static int halo_bytes(int npixa) { return 4 * npixa * 16; }
-    __host__ __device__ static int stage_bytes(int npixa) { return halo_bytes(npixa) + W_BYTES; }
-};
-
-template <int BN>
-__global__ void __launch_bounds__(256) conv_umma_kernel(const UmmaP p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bars[2];
-    __shared__ uint32_t tmem_base_smem;
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;               // two 128-row blocks, BN fp32 columns each
-    using SM = USmem<BN>;
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (role branches on the uniform datapath)
-    const int tile_w = blockIdx.x % p.tiles_w, tile_r = blockIdx.x / p.tiles_w;
-    const int w0 = tile_w * p.TW, R0 = tile_r * p.TH;
-    const int n0 = blockIdx.y * BN;
-    const int rows_total = p.N * (p.H + 2);
-    const int stage_bytes = SM::stage_bytes(p.NPIXA);
-    const int plane_a = p.NPIXA * 16;                                   // bytes between k-chunk planes of the halo
-
-    if (tid == 0) {
-        mbar_init(smem_u32(&bars[0]), 1);
-        mbar_init(smem_u32(&bars[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    // pixel slots past the real halo only feed junk accumulator rows; zero them once so no NaN patterns circulate
-    {
-        const int real = (p.TH + 2) * p.HW;
-        for (int s = tid; s < (p.NPIXA - real) * 4 * p.nstages; s += 256) {
-            const int st = s / ((p.NPIXA - real) * 4), r = s % ((p.NPIXA - real) * 4);
-            const int kq = r / (p.NPIXA - real), q = real + r % (p.NPIXA - real);
-            *reinterpret_cast<float4*>(smem + st * stage_bytes + kq * plane_a + q * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_smem;
-
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-    const int nchunks = (p.Cin + UKC - 1) / UKC;
-    const int npix_real = (p.TH + 2) * p.HW;
-
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int stage = p.nstages == 2 ? (chunk & 1) : 0;
-        unsigned char* st = smem + stage * stage_bytes;
-        // the MMAs that read this stage two chunks ago must have retired before it is overwritten
-        if (chunk >= 2) mbar_wait(smem_u32(&bars[stage]), ((chunk >> 1) - 1) & 1);
-        // ---- halo of channels [16 chunk, 16 chunk + 16)
-        const uint32_t sh = smem_u32(st);
-        for (int s = tid; s < npix_real * 4; s += 256) {
-            const int kq = s & 3, q = s >> 2;
-            uint32_t rr, cc;
-            p.fd_hw.divmod((uint32_t)q, rr, cc);
-            const int P = R0 + (int)rr;
-            uint32_t n, hh;
-            p.fd_hp2.divmod((uint32_t)P, n, hh);
-            const int ih = (int)hh - 1, iw = w0 + (int)cc - 1, ch = chunk * UKC + kq * 4;
-            const bool ok = P < rows_total && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W && ch < p.Cin;
-            const float* src = p.src0;
-            if (ok) {
-                const size_t pix = ((size_t)n * p.H + ih) * p.W + iw;
-                src = ch < p.C0 ? p.src0 + pix * p.C0 + ch : p.src1 + pix * p.C1 + (ch - p.C0);
-            }
-            cp16(sh + kq * plane_a + q * 16, src, ok);
-        }
-        // ---- weights of this chunk: [tap][kq][BN][4]
-        const uint32_t sw = sh + SM::halo_bytes(p.NPIXA);
-        const float* wsrc = p.wt + (size_t)chunk * 9 * 4 * p.CoutP * 4;
-        for (int s = tid; s < 9 * 4 * BN; s += 256) {
-            const int nn = s % BN, tk = s / BN;                         // tk = tap * 4 + kq
-            const bool ok = n0 + nn < p.CoutP;
-            cp16(sw + (tk * BN + nn) * 16, wsrc + ((size_t)tk * p.CoutP + (ok ? n0 + nn : 0)) * 4, ok);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-#pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int kh = tap / 3, kw = tap % 3;
-                    const uint32_t a0 = sh + (uint32_t)(b * 128 + kh * p.HW + kw) * 16;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t ad = umma_desc(a0 + 2 * ks * plane_a, plane_a, 128);
-                        const uint64_t bd = umma_desc(sw + (uint32_t)((tap * 4 + 2 * ks) * BN) * 16, BN * 16, 128);
-                        umma_tf32(tmem_base + b * BN, ad, bd, idesc, (chunk | tap | ks) != 0);
-                    }
-                }
-            }
-            umma_commit(smem_u32(&bars[stage]));
-        }
-    }
-
-    // ---- epilogue: wait for the last commit (MMAs retire in order), then TMEM -> registers -> global
-    {
-        const int last = nchunks - 1;
-        const int stage = p.nstages == 2 ? (last & 1) : 0;
-        mbar_wait(smem_u32(&bars[stage]), p.nstages == 2 ? ((last >> 1) & 1) : (last & 1));
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        const int b = warp >> 2, lslice = (warp & 3) * 32;
-        const int q = b * 128 + lslice + lane;
-        uint32_t rr, cc;
-        p.fd_hw.divmod((uint32_t)q, rr, cc);
-        const int P = R0 + (int)rr;
-        uint32_t n, hh;
-        p.fd_hp2.divmod((uint32_t)P, n, hh);
-        const int ow = w0 + (int)cc;
-        const bool valid = (int)rr < p.TH && (int)cc < p.TW && P < rows_total && (int)hh < p.H && ow < p.W;
-        const size_t S_img = (size_t)p.H * p.W;
-        const size_t sp = (size_t)hh * p.W + ow;
-        const size_t pix = (size_t)n * S_img + sp;
-#pragma unroll 1
-        for (int j = 0; j < BN / 16; ++j) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)lslice << 16) + (uint32_t)(b * BN + j * 16), r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int c0 = n0 + j * 16;
-            if (!valid || c0 >= p.Cout) continue;
-            float v[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                v[e] = __uint_as_float(r[e]);
-                if (p.bias && c0 + e < p.Cout) v[e] += __ldg(p.bias + c0 + e);
-            }
-            if (p.out_nchw) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (c0 + e < p.Cout) {
-                        float* o = p.dst0 + ((size_t)n * p.Cout + c0 + e) * S_img + sp;
-                        *o = p.accumulate ? *o + v[e] : v[e];
-                    }
-            } else {
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                    const int c = c0 + e4 * 4;
-                    if (c >= p.Cout) break;
-                    // D0, D1, Cout are multiples of 4 on this path, so a quad never straddles the split
-                    float* o = c < p.D0 ? p.dst0 + pix * p.D0 + c : p.dst1 + pix * p.D1 + (c - p.D0);
-                    float4 val = make_float4(v[e4 * 4], v[e4 * 4 + 1], v[e4 * 4 + 2], v[e4 * 4 + 3]);
-                    if (p.accumulate) {
-                        const float4 old = *reinterpret_cast<const float4*>(o);
-                        val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-                    }
-                    *reinterpret_cast<float4*>(o) = val;
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-    }
-}
-
-// weights for the UMMA kernel: [chunk][tap][kq][CoutP][4], TF32-rounded, zero padded
 __global__ void pack_umma_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int dgrad, int O, int I,
                                          int T, int rows, int cols, int colsP, int chunks) {
     const long long total = (long long)chunks * T * 4 * colsP * 4;
@@ -289,51 +97,6 @@ __global__ void pack_umma_weights_kernel(const float* __restrict__ w, float* __r
 
 inline int round16(int v) { return (v + 15) / 16 * 16; }
 
-// choose the tile width that wastes the fewest of the 256 accumulator rows
-void choose_tile(int W, int& TW, int& TH) {
-    const int cand[6] = {W <= 62 ? W : 30, 14, 30, 32, 62, 64};
-    double best = -1;
-    for (int i = 0; i < 6; ++i) {
-        const int tw = cand[i] > W ? W : cand[i];
-        const int hw = tw + 2, th = 256 / hw;
-        if (th < 1) continue;
-        const int ntw = (W + tw - 1) / tw;
-        const double eff = (double)(th * tw) / 256.0 * (double)W / (double)(ntw * tw);
-        if (eff > best) { best = eff; TW = tw; TH = th; }
-    }
-}
-
-template <int BN>
-int launch_umma(const UmmaP& p, cudaStream_t st) {
-    using SM = USmem<BN>;
-    auto kern = conv_umma_kernel<BN>;
-    const int bytes = p.nstages * SM::stage_bytes(p.NPIXA);
-    static int attr_bytes = 0;
-    if (bytes > attr_bytes) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        attr_bytes = bytes;
-    }
-    dim3 grid(p.tiles_w * p.tiles_r, (p.Cout + BN - 1) / BN);
-    kern<<<grid, 256, bytes, st>>>(p);
-    B200_CHECK_LAUNCH("conv_umma");
-    return B200_OK;
-}
-
-int run_umma(UmmaP& p, cudaStream_t st) {
-    choose_tile(p.W, p.TW, p.TH);
-    p.HW = p.TW + 2;
-    p.NPIXA = (256 + 2 * p.HW + 2 + 7) / 8 * 8;
-    if (p.NPIXA < (p.TH + 2) * p.HW) p.NPIXA = ((p.TH + 2) * p.HW + 7) / 8 * 8;
-    p.tiles_w = (p.W + p.TW - 1) / p.TW;
-    p.tiles_r = (p.N * (p.H + 2) + p.TH - 1) / p.TH;
-    p.fd_hw.init(p.HW);
-    p.fd_hp2.init(p.H + 2);
-    p.nstages = p.Cin > UKC ? 2 : 1;
-    if (p.Cout <= 16) return launch_umma<16>(p, st);
-    if (p.Cout <= 32) return launch_umma<32>(p, st);
-    if (p.Cout <= 64) return launch_umma<64>(p, st);
-    return launch_umma<128>(p, st);
-}
 
 int umma_supported(const b200_conv_desc* d) {
     return d && d->stride == 1 && d->kd == 1 && d->kh == 3 && d->kw == 3 && d->pd == 0 && d->ph == 1 && d->pw == 1 &&
@@ -364,35 +127,8 @@ B200_API int b200_conv_umma_pack_weights(const float* w, float* out, int dgrad, 
     return B200_OK;
 }
 
-B200_API int b200_conv_umma_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt,
-                                const float* bias, float* dst, int out_nchw, cudaStream_t st) {
-    B200_REQUIRE(b200_conv_umma_supported(d, 0), "conv_umma_fwd: unsupported convolution (needs 2D 3x3 stride 1 pad 1, channels % 4 == 0)");
-    B200_REQUIRE(src0 && wt && dst && (d->c1 == 0 || src1), "conv_umma_fwd: null pointer");
-    B200_REQUIRE(out_nchw || (d->cout & 3) == 0, "conv_umma_fwd: channels-last output needs cout % 4 == 0");
-    UmmaP p;
-    memset(&p, 0, sizeof(p));
-    p.src0 = src0; p.src1 = src1; p.C0 = d->c0; p.C1 = d->c1; p.Cin = d->c0 + d->c1;
-    p.N = d->n; p.H = d->ih; p.W = d->iw;
-    p.wt = wt; p.Cout = d->cout; p.CoutP = round16(d->cout); p.bias = bias;
-    p.dst0 = dst; p.D0 = d->cout; p.D1 = 0; p.out_nchw = out_nchw;
-    return run_umma(p, st);
-}
-
-B200_API int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
-                                  int accumulate, cudaStream_t st) {
-    B200_REQUIRE(b200_conv_umma_supported(d, 1), "conv_umma_dgrad: unsupported convolution");
-    B200_REQUIRE(dy && wt_dgrad && dx0 && (d->c1 == 0 || dx1), "conv_umma_dgrad: null pointer");
-    UmmaP p;
-    memset(&p, 0, sizeof(p));
-    p.src0 = dy; p.C0 = d->cout; p.C1 = 0; p.Cin = d->cout;
-    p.N = d->n; p.H = d->ih; p.W = d->iw;
-    p.wt = wt_dgrad; p.Cout = d->c0 + d->c1; p.CoutP = round16(p.Cout);
-    p.dst0 = dx0; p.dst1 = dx1; p.D0 = d->c0; p.D1 = d->c1; p.accumulate = accumulate;
-    return run_umma(p, st);
-}
-
 // =====================================================================================================
-// v2: the same convolution, persistent and warp-specialised.
+// The convolution kernel: persistent and warp-specialised (the simpler one-tile-per-CTA first version is in the git history).
 //   warps 0-3  producers: per 16-channel chunk the halo arrives with coalesced 16-byte cp.async (four lanes cover the
 //              64 bytes of one pixel and scatter them into the four 4-channel planes the UMMA descriptor wants;
 //              zero-fill = conv padding); cp.async.mbarrier.arrive.noinc signals the stage's "full" barrier when a

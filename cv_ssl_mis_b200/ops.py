@@ -220,21 +220,12 @@ def conv_umma_pack_weights(w, out, dgrad, O, I, T):
     _lib.call("b200_conv_umma_pack_weights", _pf(w), _pf(out), int(dgrad), O, I, T, _st())
 
 
-UMMA_V2 = True        # TMA-fed warp-specialised kernel (False: the simpler cp.async variant)
-
-
 def conv_umma_fwd(d, src0, src1, wt, bias, dst, out_nchw=False):
-    if UMMA_V2:
-        _lib.call("b200_conv_umma2_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())
-        return
-    _lib.call("b200_conv_umma_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())
+    _lib.call("b200_conv_umma2_fwd", C.byref(d), _pf(src0), _pf(src1), _pf(wt), _pf(bias), _pf(dst), int(out_nchw), _st())
 
 
 def conv_umma_dgrad(d, dy, wt_dgrad, dx0, dx1=None, accumulate=False):
-    if UMMA_V2:
-        _lib.call("b200_conv_umma2_dgrad", C.byref(d), _pf(dy), _pf(wt_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
-        return
-    _lib.call("b200_conv_umma_dgrad", C.byref(d), _pf(dy), _pf(wt_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
+    _lib.call("b200_conv_umma2_dgrad", C.byref(d), _pf(dy), _pf(wt_dgrad), _pf(dx0), _pf(dx1), int(accumulate), _st())
 
 
 # batched packing / first-layer kernels

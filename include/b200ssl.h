@@ -98,12 +98,8 @@ int b200_conv_tile_wgrad(const b200_conv_desc* d, const float* src0, const float
 int b200_conv_umma_supported(const b200_conv_desc* d, int for_dgrad);
 long long b200_conv_umma_packed_floats(int dgrad, int O, int I, int T);
 int b200_conv_umma_pack_weights(const float* w, float* out, int dgrad, int O, int I, int T, cudaStream_t stream);
-int b200_conv_umma_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt, const float* bias,
-                       float* dst, int out_nchw, cudaStream_t stream);
-int b200_conv_umma_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,
-                         int accumulate, cudaStream_t stream);
-/* same operation and weight packing, persistent and warp-specialised: cp.async producer warps + cp.async.bulk weights ->
- * multi-stage mbarrier ring -> one MMA-issuing lane -> double-buffered TMEM accumulators -> epilogue warps */
+/* persistent and warp-specialised: cp.async producer warps + cp.async.bulk weights -> multi-stage mbarrier ring -> one
+ * MMA-issuing lane -> double-buffered TMEM accumulators -> epilogue warps */
 int b200_conv_umma2_fwd(const b200_conv_desc* d, const float* src0, const float* src1, const float* wt, const float* bias,
                         float* dst, int out_nchw, cudaStream_t stream);
 int b200_conv_umma2_dgrad(const b200_conv_desc* d, const float* dy, const float* wt_dgrad, float* dx0, float* dx1,

@@ -388,11 +388,9 @@ UMMA_CASES = [
 ]
 
 
-@pytest.mark.parametrize("v2", [True, False])
 @pytest.mark.parametrize("case", UMMA_CASES)
-def test_conv_umma_kernels(case, v2, monkeypatch):
-    """tcgen05.mma / TMEM convolution (TMA warp-specialised v2 and cp.async v1) against the fp32 reference op."""
-    monkeypatch.setattr(ops, "UMMA_V2", v2)
+def test_conv_umma_kernels(case):
+    """tcgen05.mma / TMEM convolution (persistent warp-specialised conv_umma2 kernel) against the fp32 reference op."""
     n, h, w, c0, c1, cout = case
     g = torch.Generator().manual_seed(sum(case) * 3)
     desc = ops.conv_desc(n, 1, h, w, c0, c1, cout, 3, 1, 1, 2)

@@ -38,7 +38,6 @@ for (n, h, w, c0, c1, cout) in SHAPES:
             part = torch.empty(ops.conv_blk_stats_blocks(d) * 2 * cout, dtype=torch.float64, device="cuda")
             fn = lambda: ops.conv_blk_fwd(d, x0, x1, wt, bias, y, part)
         elif name.startswith("umma"):
-            ops.UMMA_V2 = name == "umma2"
             wt = torch.empty(ops.conv_umma_packed_floats(False, cout, cin, 9), device="cuda")
             ops.conv_umma_pack_weights(wgt, wt, False, cout, cin, 9)
             fn = lambda: ops.conv_umma_fwd(d, x0, x1, wt, bias, y)
