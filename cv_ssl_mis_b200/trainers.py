@@ -191,10 +191,13 @@ class MeanTeacherTrainer(_Pipelined):
                          self.lossbuf, self.loss_ws, psum, float(self.T), thr)
         ops.ssl_loss_bwd(self.s_plan.logits, teacher_logits, self.y, False, self.B, self.Lb, self.C, self.S, w,
                          self.lossbuf, 1.0, self.s_plan.g_logits, True, psum, float(self.T), thr)
-        if self.world > 1 and hasattr(self.s_plan, "decoder_grad_offset") and os.environ.get("B200_DP_BUCKETS", "1") == "1":
-            # two gradient buckets -- the decoder's (produced first) is all-reduced on a communication stream while the
-            # encoder's backward is still running; the encoder's follows on the main stream (B200_DP_BUCKETS=0: one
-            # all-reduce after the whole backward).
+        if self.world > 1 and hasattr(self.s_plan, "decoder_grad_offset") and os.environ.get("B200_DP_BUCKETS", "0") == "1":
+            # opt-in: two gradient buckets -- the decoder's (produced first) is all-reduced on a communication stream while
+            # the encoder's backward is still running; the encoder's follows on the main stream.  Measured with the 4.3 ms
+            # step (profiles/r2_bench_config2_{2,8}gpu.json vs r2_dp_config2_{2,8}gpu_bucketed.json): 4.375 vs 4.395 ms at 2 GPUs,
+            # 4.428 vs 4.444 ms at 8 -- the 7.3 MB exchange costs a fixed NCCL latency that is already hidden behind the
+            # weight-gradient side stream, and the extra stream joins cost more than the overlap gains; the single
+            # all-reduce below stays the default.
             off = self.s_plan.decoder_grad_offset()
             cuda = self.dev.type == "cuda"
             if cuda and self.comm is None:
