@@ -45,6 +45,7 @@ CONV_CASES = [
     (2, 8, 8, 8, 16, 0, 32, 2, 2, 3),
     (1, 4, 4, 4, 16, 0, 2, 1, 1, 3),
     (2, 1, 16, 16, 16, 0, 32, 2, 2, 2),
+    (2, 1, 14, 14, 96, 0, 4, 1, 1, 2),       # Swin-UNet head (1x1, 96 -> 4): FFMA data gradient
 ]
 
 
