@@ -611,16 +611,16 @@ B200_API int b200_add_droppath(const float* x, const float* branch, float* out, 
 // ================================================================================================ rearrangements
 // PatchMerging gather (:336-341): y[b][h2][w2][q*C + c] = x[b][2*h2 + (q & 1)][2*w2 + (q >> 1)][c]
 __global__ void __launch_bounds__(256) patch_merge_gather_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H,
-                                                                 int W, int C, int inverse, int accumulate) {
-    const int CQ = C >> 2, H2 = H >> 1, W2 = W >> 1;
-    const long long total = (long long)B * H2 * W2 * 4 * CQ;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(i % CQ);
-        long long r = i / CQ;
-        const int q = (int)(r & 3); r >>= 2;
-        const int w2 = (int)(r % W2); r /= W2;
-        const int h2 = (int)(r % H2);
-        const int b = (int)(r / H2);
+                                                                 int W, int C, int inverse, int accumulate, const FastDiv fdCQ,
+                                                                 const FastDiv fdW2, const FastDiv fdH2) {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const uint32_t total = (uint32_t)B * H2 * W2 * 4 * (C >> 2);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r, cq, w2, h2, b;
+        fdCQ.divmod(i, r, cq);
+        const uint32_t q = r & 3; r >>= 2;
+        fdW2.divmod(r, r, w2);
+        fdH2.divmod(r, b, h2);
         const long long big = (((long long)b * H + 2 * h2 + (q & 1)) * W + 2 * w2 + (q >> 1)) * C + cq * 4;
         const long long small = (((long long)b * H2 + h2) * W2 + w2) * 4 * C + q * C + cq * 4;
         if (!inverse) {
@@ -639,24 +639,32 @@ __global__ void __launch_bounds__(256) patch_merge_gather_kernel(const float* __
 B200_API int b200_patch_merge_gather(const float* x, float* y, int B, int H, int W, int C, int inverse, int accumulate,
                                      cudaStream_t st) {
     B200_REQUIRE(x && y && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && (C & 3) == 0, "patch_merge_gather: bad arguments");
-    patch_merge_gather_kernel<<<ew_grid((long long)B * H * W * (C / 4)), 256, 0, st>>>(x, y, B, H, W, C, inverse, accumulate);
+    const long long total = (long long)B * H * W * (C / 4);
+    B200_REQUIRE(total < (1ll << 32) - (1 << 24), "patch_merge_gather: tensor too large");
+    FastDiv fdCQ, fdW2, fdH2;
+    fdCQ.init(C / 4); fdW2.init(W / 2); fdH2.init(H / 2);
+    patch_merge_gather_kernel<<<ew_grid(total), 256, 0, st>>>(x, y, B, H, W, C, inverse, accumulate, fdCQ, fdW2, fdH2);
     B200_CHECK_LAUNCH("patch_merge_gather");
     return B200_OK;
 }
 
 // PatchExpand rearrange (:378-379, :405-407): y[b][h*p + p1][w*p + p2][c] = x[b][h][w][(p1*p + p2)*C + c]
+struct ShufP {
+    FastDiv fdCQ, fdWP, fdHP, fdP;
+};
+// index math in 32 bits with precomputed reciprocals: the 64-bit divisions of the first version made this copy
+// compute-bound (0.05 of the HBM peak on the final x4 expand)
 __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
-                                                            int C, int P, int inverse) {
-    const int CQ = C >> 2, HP = H * P, WP = W * P;
-    const long long total = (long long)B * HP * WP * CQ;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(i % CQ);
-        long long r = i / CQ;
-        const int wo = (int)(r % WP); r /= WP;
-        const int ho = (int)(r % HP);
-        const int b = (int)(r / HP);
-        const int h = ho / P, p1 = ho - h * P, w = wo / P, p2 = wo - w * P;
-        const long long fine = i * 4;
+                                                            int C, int P, int inverse, const ShufP q) {
+    const uint32_t total = (uint32_t)B * H * P * W * P * (C >> 2);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r, cq, wo, ho, b, h, p1, w, p2;
+        q.fdCQ.divmod(i, r, cq);
+        q.fdWP.divmod(r, r, wo);
+        q.fdHP.divmod(r, b, ho);
+        q.fdP.divmod(ho, h, p1);
+        q.fdP.divmod(wo, w, p2);
+        const long long fine = (long long)i * 4;
         const long long coarse = ((((long long)b * H + h) * W + w) * P * P + p1 * P + p2) * C + cq * 4;
         if (!inverse) stg4(y + fine, ldg4(x + coarse));
         else stg4(y + coarse, ldg4(x + fine));
@@ -665,7 +673,11 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
 
 B200_API int b200_pixel_shuffle(const float* x, float* y, int B, int H, int W, int C, int p, int inverse, cudaStream_t st) {
     B200_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0 && p > 0, "pixel_shuffle: bad arguments");
-    pixel_shuffle_kernel<<<ew_grid((long long)B * H * W * p * p * (C / 4)), 256, 0, st>>>(x, y, B, H, W, C, p, inverse);
+    const long long total = (long long)B * H * W * p * p * (C / 4);
+    B200_REQUIRE(total < (1ll << 32) - (1 << 24), "pixel_shuffle: tensor too large");
+    ShufP q;
+    q.fdCQ.init(C / 4); q.fdWP.init(W * p); q.fdHP.init(H * p); q.fdP.init(p);
+    pixel_shuffle_kernel<<<ew_grid(total), 256, 0, st>>>(x, y, B, H, W, C, p, inverse, q);
     B200_CHECK_LAUNCH("pixel_shuffle");
     return B200_OK;
 }
