@@ -98,8 +98,10 @@ def cost_of(name, a):
             return 8.0 * a[2], 0.0
         if name in ("b200_nchw_to_nhwc", "b200_nhwc_to_nchw"):
             return 8.0 * a[2] * a[3] * a[4], 0.0
-        if name in ("b200_patch_merge_gather", "b200_pixel_shuffle"):
+        if name == "b200_patch_merge_gather":
             return 8.0 * a[2] * a[3] * a[4] * a[5], 0.0
+        if name == "b200_pixel_shuffle":                  # C is the channel count AFTER the expand: B H W p^2 C elements
+            return 8.0 * a[2] * a[3] * a[4] * a[5] * a[6] * a[6], 0.0
     except (AttributeError, IndexError, TypeError):
         return None
     return None
