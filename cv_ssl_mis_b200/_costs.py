@@ -66,6 +66,14 @@ def cost_of(name, a):
             return 12.0 * a[3] * a[4], 0.0
         if name in ("b200_add_lrelu_fwd", "b200_lrelu_bwd", "b200_add"):
             return 12.0 * a[3], 0.0
+        if name == "b200_maxpool3d_fwd":
+            return 4.0 * a[2] * a[3] * a[4] * a[5] * a[6] * 1.125, 0.0
+        if name == "b200_maxpool3d_bwd":
+            return 4.0 * a[3] * a[4] * a[5] * a[6] * a[7] * (2.125 + (1.0 if a[8] else 0.0)), 0.0
+        if name == "b200_upsample3d2x_fwd":
+            return 4.0 * a[2] * a[3] * a[4] * a[5] * a[6] * 9.0, 0.0
+        if name == "b200_upsample3d2x_bwd":
+            return 4.0 * a[2] * a[3] * a[4] * a[5] * a[6] * 9.0, 0.0
         if name == "b200_s2d_gather3d":
             return 8.0 * a[2] * a[3] * a[4] * a[5] * a[6], 0.0
         if name == "b200_d2s_scatter3d":

@@ -73,6 +73,10 @@ SIGNATURES = {
     "b200_conv_row_stats_blocks": (_L, [_D]),
     "b200_conv_row_fwd": (_I, [_D, _P, _P, _P, _P, _P, _P, _S]),
     "b200_conv_row_dgrad": (_I, [_D, _P, _P, _P, _P, _I, _S]),
+    "b200_maxpool3d_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
+    "b200_maxpool3d_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
+    "b200_upsample3d2x_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
+    "b200_upsample3d2x_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "b200_s2d_gather3d": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
     "b200_d2s_scatter3d": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _S]),
     "b200_conv_blk_supported": (_I, [_D, _I]),

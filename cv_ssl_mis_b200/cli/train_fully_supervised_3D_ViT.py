@@ -15,7 +15,7 @@ def main(argv=None, loader=None):
     pg, rank = process_group()
     model = net_factory_3d(net_type=args.model, in_chns=1, class_num=args.num_classes)            # :98
     if model is None:
-        raise SystemExit(f"--model {args.model}: not built (available: vnet, unetr)")
+        raise SystemExit(f"--model {args.model}: not built (available: unet_3D, vnet, unetr)")
     if pg is not None:
         import torch.distributed as dist
         dist.broadcast(model.materialize().data, 0)

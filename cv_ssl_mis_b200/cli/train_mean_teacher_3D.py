@@ -1,9 +1,9 @@
-"""Command line of code/train_mean_teacher_3D.py (the reference default --model unet_3D is not built: vnet): the loop of cli/train_uncertainty_aware_mean_teacher_3D.py with the defaults of this script."""
+"""Command line of code/train_mean_teacher_3D.py (default --model unet_3D, like the reference): the loop of cli/train_uncertainty_aware_mean_teacher_3D.py with the defaults of this script."""
 import sys
 
 from . import train_uncertainty_aware_mean_teacher_3D as _impl
 
-DEFAULTS = dict(exp='BraTs2019_Mean_Teacher', uncertainty_T=0)
+DEFAULTS = dict(exp='BraTs2019_Mean_Teacher', model='unet_3D', uncertainty_T=0)
 
 
 def main(argv=None, loader=None):

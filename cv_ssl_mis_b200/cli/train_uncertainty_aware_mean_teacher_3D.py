@@ -20,7 +20,7 @@ def main(argv=None, loader=None, defaults=None):
     def create_model(ema=False):                                  # :103-110
         net = net_factory_3d(net_type=args.model, in_chns=1, class_num=args.num_classes)
         if net is None:
-            raise SystemExit(f"--model {args.model}: not built (available: vnet, unetr)")
+            raise SystemExit(f"--model {args.model}: not built (available: unet_3D, vnet, unetr)")
         if ema:
             for param in net.parameters():
                 param.detach_()

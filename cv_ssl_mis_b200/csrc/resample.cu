@@ -377,6 +377,187 @@ B200_API int b200_colsum(const float* g, long long M, int C, float* out, int acc
     return B200_OK;
 }
 
+// ---------------------------------------------------------------- 3D pooling / trilinear x2 (code/networks/unet_3D.py)
+struct Vol3P {
+    int D, H, W, C4;             // INPUT dims of the pooling / of the up-sampling, channels / 4
+    FastDiv fdC4, fdW, fdH, fdD; // divisors of the COARSE grid (pool output / up-sample input)
+};
+
+// nn.MaxPool3d(2): out[n][d][h][w][c] = max over the 2x2x2 window; BWD routes dp to the FIRST maximum of the window in
+// scan order (kd, kh, kw) with a strict > comparison (torch's tie rule -- windows of equal zeros are common after ReLU)
+template <int BWD>
+__global__ void __launch_bounds__(256) maxpool3d_kernel(const float4* __restrict__ a, const float4* __restrict__ dp,
+                                                        float4* __restrict__ out, long long total4, int accumulate, const Vol3P p) {
+    const long long sW = p.C4, sH = (long long)p.W * p.C4, sD = (long long)p.H * p.W * p.C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t r, c4, w, h, d, n;
+        p.fdC4.divmod((uint32_t)i, r, c4);
+        p.fdW.divmod(r, r, w);
+        p.fdH.divmod(r, r, h);
+        p.fdD.divmod(r, n, d);
+        const long long base = (((long long)n * p.D + 2 * d) * p.H + 2 * h) * sH + (long long)(2 * w) * sW + c4;
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(a + base + (k >> 2) * sD + ((k >> 1) & 1) * sH + (k & 1) * sW);
+        if (!BWD) {
+            float4 m = v[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) m = max4(m, v[k]);
+            out[i] = m;
+        } else {
+            const float4 g = __ldg(dp + i);
+            int ax = 0, ay = 0, az = 0, aw = 0;
+            float bx = v[0].x, by = v[0].y, bz = v[0].z, bw = v[0].w;
+#pragma unroll
+            for (int k = 1; k < 8; ++k) {
+                if (v[k].x > bx) { bx = v[k].x; ax = k; }
+                if (v[k].y > by) { by = v[k].y; ay = k; }
+                if (v[k].z > bz) { bz = v[k].z; az = k; }
+                if (v[k].w > bw) { bw = v[k].w; aw = k; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float4 o = make_float4(k == ax ? g.x : 0.f, k == ay ? g.y : 0.f, k == az ? g.z : 0.f, k == aw ? g.w : 0.f);
+                float4* dst = out + base + (k >> 2) * sD + ((k >> 1) & 1) * sH + (k & 1) * sW;
+                if (accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *dst = o;
+            }
+        }
+    }
+}
+
+static int pool3d_launch(int bwd, const float* a, const float* dp, float* out, int N, int D, int H, int W, int C, int accumulate,
+                         cudaStream_t st, const char* who) {
+    B200_REQUIRE(a && out && (!bwd || dp) && N > 0 && C > 0 && (C & 3) == 0 && D > 0 && H > 0 && W > 0 && ((D | H | W) & 1) == 0,
+                 "%s: bad arguments (C %% 4 == 0, even D, H, W)", who);
+    Vol3P p;
+    p.D = D; p.H = H; p.W = W; p.C4 = C / 4;
+    p.fdC4.init(p.C4); p.fdW.init(W / 2); p.fdH.init(H / 2); p.fdD.init(D / 2);
+    const long long total4 = (long long)N * (D / 2) * (H / 2) * (W / 2) * p.C4;
+    B200_REQUIRE(total4 < (1ll << 32), "%s: tensor too large", who);
+    if (!bwd) maxpool3d_kernel<0><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(a), nullptr, reinterpret_cast<float4*>(out), total4, 0, p);
+    else maxpool3d_kernel<1><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(dp),
+                                                              reinterpret_cast<float4*>(out), total4, accumulate, p);
+    B200_CHECK_LAUNCH(who);
+    return B200_OK;
+}
+
+B200_API int b200_maxpool3d_fwd(const float* a, float* out, int N, int D, int H, int W, int C, cudaStream_t st) {
+    return pool3d_launch(0, a, nullptr, out, N, D, H, W, C, 0, st, "maxpool3d_fwd");
+}
+
+B200_API int b200_maxpool3d_bwd(const float* a, const float* dp, float* da, int N, int D, int H, int W, int C, int accumulate,
+                                cudaStream_t st) {
+    return pool3d_launch(1, a, dp, da, N, D, H, W, C, accumulate, st, "maxpool3d_bwd");
+}
+
+// nn.Upsample(scale_factor=2, mode='trilinear') (align_corners=False): per axis the source coordinate of output o is
+// max(0, (o + 0.5) / 2 - 0.5), i.e. output 2i reads (i-1, i) with weights (0.25, 0.75) (output 0: input 0 alone) and output
+// 2i+1 reads (i, min(i+1, n-1)) with weights (0.75, 0.25).  The backward is the transposed gather: input i collects from
+// outputs 2i-1 (0.25), 2i (0.75, or 1 at i = 0), 2i+1 (0.75, or 1 at i = n-1), 2i+2 (0.25) -- deterministic, no atomics.
+__device__ __forceinline__ void tri_src(int o, int n, int& i0, int& i1, float& w1) {
+    const int i = o >> 1;
+    if (o & 1) { i0 = i; i1 = i + 1 < n ? i + 1 : n - 1; w1 = 0.25f; }
+    else if (i == 0) { i0 = 0; i1 = 0; w1 = 0.f; }
+    else { i0 = i - 1; i1 = i; w1 = 0.75f; }
+}
+// weights of the (up to) four outputs 2i-1 .. 2i+2 that read input i
+__device__ __forceinline__ void tri_dst(int i, int n, float (&w)[4]) {
+    w[0] = i >= 1 ? 0.25f : 0.f;
+    w[1] = i == 0 ? 1.f : 0.75f;
+    w[2] = i == n - 1 ? 1.f : 0.75f;
+    w[3] = i + 1 < n ? 0.25f : 0.f;
+}
+
+__global__ void __launch_bounds__(256) upsample3d2x_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long total4,
+                                                               const Vol3P p) {
+    const long long sW = p.C4, sH = (long long)p.W * p.C4, sD = (long long)p.H * p.W * p.C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t r, c4, w, h, d, n;                       // OUTPUT coordinates (fd* hold the output extents here)
+        p.fdC4.divmod((uint32_t)i, r, c4);
+        p.fdW.divmod(r, r, w);
+        p.fdH.divmod(r, r, h);
+        p.fdD.divmod(r, n, d);
+        int d0, d1, h0, h1, w0, w1;
+        float ad, ah, aw;
+        tri_src((int)d, p.D, d0, d1, ad);
+        tri_src((int)h, p.H, h0, h1, ah);
+        tri_src((int)w, p.W, w0, w1, aw);
+        const float4* b = x + (long long)n * p.D * sD + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wt = ((k & 4) ? ad : 1.f - ad) * ((k & 2) ? ah : 1.f - ah) * ((k & 1) ? aw : 1.f - aw);
+            const float4 v = __ldg(b + ((k & 4) ? d1 : d0) * sD + ((k & 2) ? h1 : h0) * sH + ((k & 1) ? w1 : w0) * sW);
+            acc.x += wt * v.x; acc.y += wt * v.y; acc.z += wt * v.z; acc.w += wt * v.w;
+        }
+        y[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample3d2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, long long total4,
+                                                               int accumulate, const Vol3P p) {
+    const int OD = 2 * p.D, OH = 2 * p.H, OW = 2 * p.W;
+    const long long sW = p.C4, sH = (long long)OW * p.C4, sD = (long long)OH * OW * p.C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t r, c4, w, h, d, n;                       // INPUT coordinates
+        p.fdC4.divmod((uint32_t)i, r, c4);
+        p.fdW.divmod(r, r, w);
+        p.fdH.divmod(r, r, h);
+        p.fdD.divmod(r, n, d);
+        float wd[4], wh[4], ww[4];
+        tri_dst((int)d, p.D, wd);
+        tri_dst((int)h, p.H, wh);
+        tri_dst((int)w, p.W, ww);
+        const float4* b = dy + (long long)n * OD * sD + c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < 4; ++a) {
+            const int od = 2 * (int)d - 1 + a;
+            if (wd[a] == 0.f) continue;
+            for (int e = 0; e < 4; ++e) {
+                const int oh = 2 * (int)h - 1 + e;
+                if (wh[e] == 0.f) continue;
+                const float wde = wd[a] * wh[e];
+                const float4* row = b + od * sD + oh * sH;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    if (ww[f] == 0.f) continue;
+                    const float wt = wde * ww[f];
+                    const float4 v = __ldg(row + (2 * (int)w - 1 + f) * sW);
+                    acc.x += wt * v.x; acc.y += wt * v.y; acc.z += wt * v.z; acc.w += wt * v.w;
+                }
+            }
+        }
+        if (accumulate) { const float4 old = dx[i]; acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w; }
+        dx[i] = acc;
+    }
+}
+
+B200_API int b200_upsample3d2x_fwd(const float* x, float* y, int N, int D, int H, int W, int C, cudaStream_t st) {
+    B200_REQUIRE(x && y && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample3d2x_fwd: bad arguments");
+    Vol3P p;
+    p.D = D; p.H = H; p.W = W; p.C4 = C / 4;
+    p.fdC4.init(p.C4); p.fdW.init(2 * W); p.fdH.init(2 * H); p.fdD.init(2 * D);
+    const long long total4 = (long long)N * 8 * D * H * W * p.C4;
+    B200_REQUIRE(total4 < (1ll << 32), "upsample3d2x_fwd: tensor too large");
+    upsample3d2x_fwd_kernel<<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), total4, p);
+    B200_CHECK_LAUNCH("upsample3d2x_fwd");
+    return B200_OK;
+}
+
+B200_API int b200_upsample3d2x_bwd(const float* dy, float* dx, int N, int D, int H, int W, int C, int accumulate, cudaStream_t st) {
+    B200_REQUIRE(dy && dx && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "upsample3d2x_bwd: bad arguments");
+    Vol3P p;
+    p.D = D; p.H = H; p.W = W; p.C4 = C / 4;
+    p.fdC4.init(p.C4); p.fdW.init(W); p.fdH.init(H); p.fdD.init(D);
+    const long long total4 = (long long)N * D * H * W * p.C4;
+    B200_REQUIRE(total4 < (1ll << 32), "upsample3d2x_bwd: tensor too large");
+    upsample3d2x_bwd_kernel<<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), total4,
+                                                             accumulate, p);
+    B200_CHECK_LAUNCH("upsample3d2x_bwd");
+    return B200_OK;
+}
+
 // ---------------------------------------------------------------- 2x2x2 stride-2 (transposed) convolutions as GEMMs
 // A kernel-2 stride-2 convolution touches every input voxel exactly once, so it is the GEMM
 //     y[(n,do,ho,wo)][co] = sum over (kd,kh,kw,ci) of  xs[(n,do,ho,wo)][(kd,kh,kw,ci)] * W2[co][(kd,kh,kw,ci)]

@@ -161,6 +161,23 @@ def bn_finalize(part, nblocks, M, C_, gamma, beta, eps, momentum, running_mean, 
 
 
 # halo-block tcgen05 forward / data gradient (narrow-image 2D 3x3 stride-1 pad-1: the 64^2 / 32^2 / 16^2 levels)
+def maxpool3d_fwd(a, out, N, D, H, W, C):
+    _lib.call("b200_maxpool3d_fwd", _pf(a), _pf(out), N, D, H, W, C, _st())
+
+
+def maxpool3d_bwd(a, dp, da, N, D, H, W, C, accumulate=False):
+    _lib.call("b200_maxpool3d_bwd", _pf(a), _pf(dp), _pf(da), N, D, H, W, C, int(accumulate), _st())
+
+
+def upsample3d2x_fwd(x, y, N, D, H, W, C):
+    """trilinear x2, align_corners=False; D, H, W: input extents"""
+    _lib.call("b200_upsample3d2x_fwd", _pf(x), _pf(y), N, D, H, W, C, _st())
+
+
+def upsample3d2x_bwd(dy, dx, N, D, H, W, C, accumulate=False):
+    _lib.call("b200_upsample3d2x_bwd", _pf(dy), _pf(dx), N, D, H, W, C, int(accumulate), _st())
+
+
 def s2d_gather3d(x, xs, N, D, H, W, C):
     """xs[(n,do,ho,wo)][(kd,kh,kw,c)] = x[n][2do+kd][2ho+kh][2wo+kw][c]  (space-to-depth view for the 2x2x2 stride-2 convs)"""
     _lib.call("b200_s2d_gather3d", _pf(x), _pf(xs), N, D, H, W, C, _st())

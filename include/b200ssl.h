@@ -134,6 +134,15 @@ int b200_conv_row_fwd(const b200_conv_desc* d, const float* src0, const float* s
 int b200_conv_row_dgrad(const b200_conv_desc* d, const float* dy, const float* wpk_dgrad, float* dx0, float* dx1,
                         int accumulate, cudaStream_t stream);
 
+/* nn.MaxPool3d(2) and nn.Upsample(scale_factor=2, mode='trilinear') (align_corners=False) on channels-last volumes
+ * [N][D][H][W][C] (code/networks/unet_3D.py:35-48, code/networks/utils.py:264); D, H, W are the INPUT extents of the op.  The
+ * pooling backward recomputes the arg-max (first maximum in (kd, kh, kw) scan order, torch's tie rule). */
+int b200_maxpool3d_fwd(const float* a, float* out, int N, int D, int H, int W, int C, cudaStream_t stream);
+int b200_maxpool3d_bwd(const float* a, const float* dp, float* da, int N, int D, int H, int W, int C, int accumulate,
+                       cudaStream_t stream);
+int b200_upsample3d2x_fwd(const float* x, float* y, int N, int D, int H, int W, int C, cudaStream_t stream);
+int b200_upsample3d2x_bwd(const float* dy, float* dx, int N, int D, int H, int W, int C, int accumulate, cudaStream_t stream);
+
 /* 2x2x2 stride-2 convolutions and transposed convolutions as GEMMs (code/networks/vnet.py:73,100; the UNETR up-blocks):
  * b200_s2d_gather3d writes the space-to-depth view xs[(n,do,ho,wo)][(kd,kh,kw,c)] of x[N][D][H][W][C] (D, H, W even), so that
  * the strided convolution is b200_linear_fwd(xs, W2[cout][8 cin]) (weights packed with B200_PACK_CONV_DGRAD_D2S);

@@ -364,6 +364,39 @@ def conv_row_dgrad(d, dy, wpk_dgrad, dx0, dx1=None, accumulate=False):
     _split_store(dx, d, dx0, dx1, accumulate)
 
 
+# ------------------------------------------------------------------ 3D pooling / trilinear up-sampling
+def _vol(t, N, D, H, W, C):
+    return t.reshape(N, D, H, W, C).permute(0, 4, 1, 2, 3)
+
+
+def _unvol(t):
+    return t.permute(0, 2, 3, 4, 1).reshape(-1, t.shape[1])
+
+
+def maxpool3d_fwd(a, out, N, D, H, W, C):
+    out.copy_(_unvol(F.max_pool3d(_vol(a, N, D, H, W, C), 2)).reshape(out.shape))
+
+
+def maxpool3d_bwd(a, dp, da, N, D, H, W, C, accumulate=False):
+    with torch.enable_grad():
+        x = _vol(a, N, D, H, W, C).detach().clone().requires_grad_(True)
+        F.max_pool3d(x, 2).backward(_vol(dp, N, D // 2, H // 2, W // 2, C))
+    g = _unvol(x.grad).reshape(da.shape)
+    da.copy_(da + g if accumulate else g)
+
+
+def upsample3d2x_fwd(x, y, N, D, H, W, C):
+    y.copy_(_unvol(F.interpolate(_vol(x, N, D, H, W, C), scale_factor=2, mode="trilinear", align_corners=False)).reshape(y.shape))
+
+
+def upsample3d2x_bwd(dy, dx, N, D, H, W, C, accumulate=False):
+    with torch.enable_grad():
+        x = torch.zeros(N, C, D, H, W, requires_grad=True)
+        F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False).backward(_vol(dy, N, 2 * D, 2 * H, 2 * W, C))
+    g = _unvol(x.grad).reshape(dx.shape)
+    dx.copy_(dx + g if accumulate else g)
+
+
 # ------------------------------------------------------------------ 2x2x2 stride-2 views
 def s2d_gather3d(x, xs, N, D, H, W, C):
     v = x.reshape(N, D // 2, 2, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 5, 2, 4, 6, 7)     # n do ho wo kd kh kw c

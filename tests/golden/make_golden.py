@@ -707,8 +707,36 @@ def uamt2d_fixture():
     print("uamt2d: loss", float(loss), "cons", float(consistency_loss), "mask fraction", float(mask.mean()))
 
 
+def unet3d_fixture():
+    """The reference's own unet_3D (code/networks/unet_3D.py, built as net_factory_3d does): logits, supervised loss and
+    gradient norms on a 2 x 32^3 batch.  The 23 MB of weights are not stored: they are regenerated from a seed
+    (oracle/unet3d_oracle.py:fixture_state_dict) and loaded into the reference module with load_state_dict."""
+    from networks.unet_3D import unet_3D as RefUNet3D
+    from oracle import unet3d_oracle as U3
+    from oracle import ssl_oracle as O
+    seed, B, P = 1357, 2, 32
+    model = RefUNet3D(n_classes=2, in_channels=1)
+    sd = U3.fixture_state_dict(seed)
+    assert list(model.state_dict().keys()) == list(sd.keys()), "unet_3D state_dict key schema differs from oracle/unet3d_oracle.py"
+    model.load_state_dict(sd)
+    no_dropout(model)                    # nn.Dropout(p=0.3) off: masks cannot be shared with torch's RNG
+    model.train()
+    x, y = U3.fixture_inputs(seed + 1, B, P)
+    logits = model(x)
+    loss, ce, dice = O.supervised_loss(logits, y, 2)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    torch.save(dict(seed=seed, B=B, P=P, checksum=checksum(sd), logits_sub=logits[:, :, ::2, ::2, ::2].detach().clone(),
+                    logits_stat=(float(logits.mean()), float(logits.abs().mean()), float(logits.abs().max())),
+                    loss=loss.detach(), ce=ce.detach(), dice=dice.detach(),
+                    grad_norm={k: float(g.norm()) for k, g in grads.items()},
+                    grad_head={k: g.flatten()[:8].clone() for k, g in grads.items()}),
+               os.path.join(HERE, "unet3d.pt"))
+    print("unet3d: loss", float(loss), "logits |mean|", float(logits.abs().mean()))
+
+
 if __name__ == "__main__":
-    fixtures = dict(uamt2d=uamt2d_fixture, mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture,
+    fixtures = dict(unet3d=unet3d_fixture, uamt2d=uamt2d_fixture, mt_vit=mt_vit_fixture, unet=unet_fixture, losses=losses_fixture,
                     losses_dropin=losses_dropin_fixture, ramps=ramps_fixture, mt_step=mt_step_fixture,
                     vnet=vnet_fixture, swin=swin_fixture, cps_ict=cps_ict_fixture)
     for name in (sys.argv[1:] or list(fixtures)):

@@ -63,7 +63,7 @@ def test_3d_clis(cpu_env):
                       "--uncertainty_T", "2"] + COMMON) == "Training Finished!"
     assert fs.main(["--model", "vnet", "--batch_size", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
     with pytest.raises(SystemExit):
-        fs.main(["--model", "unet_3D"] + COMMON)
+        fs.main(["--model", "voxresnet"] + COMMON)
 
 
 def test_ict_cli(cpu_env):
@@ -122,4 +122,5 @@ def test_reference_script_names(cpu_env):
     assert cps.main(small + COMMON) == "Training Finished!"
     assert (cpu_env / "model" / "ACDC" / "Cross_Pseudo_Supervision_1_labeled" / "unet" / "model2_iter_2.pth").exists()
     assert mt3d.main(["--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
+    assert (cpu_env / "model" / "BraTs2019_Mean_Teacher_25_labeled" / "unet_3D" / "iter_2.pth").exists()       # the reference's default model
     assert mtvit.DEFAULTS["model"] == "ViT_Seg" and mtvit.DEFAULTS["exp"] == "ACDC/Mean_Teacher_ViT"

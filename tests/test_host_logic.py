@@ -519,3 +519,43 @@ def test_ict_trainer_matches_oracle(fake):
                      num_classes=4, mix_seed=5)
     out = tr2.step(x, y, read_loss=True)
     assert all(v == v for v in out) and 0.0 <= float(tr2.mix.min()) and float(tr2.mix.max()) <= 1.0
+
+
+def unet3d_drops(seed, B, P, filters=(16, 32, 64, 128, 256), p=0.3):
+    """(center, up1) element-wise keep masks / (1 - p) of one unet_3D forward: Philox stream 2 b + site per sample."""
+    S4, S0 = (P // 16) ** 3, P ** 3
+    m0 = [torch.from_numpy(philox.keep_mask(seed, 2 * b, S4, filters[4], p, 1)) for b in range(B)]
+    m1 = [torch.from_numpy(philox.keep_mask(seed, 2 * b + 1, S0, filters[0], p, 1)) for b in range(B)]
+    cl = lambda ms, side, c: torch.stack(ms).reshape(B, side, side, side, c).permute(0, 4, 1, 2, 3) / (1 - p)
+    return cl(m0, P // 16, filters[4]), cl(m1, P, filters[0])
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_unet3d_plan_matches_oracle(fake, dropout):
+    """unet_3D launch schedule (per-sample InstanceNorm plans, 3-D pooling / trilinear up-sampling, virtual concats,
+    element-wise dropout) against the functional oracle and its autograd gradients."""
+    from oracle import unet3d_oracle as U3
+    from cv_ssl_mis_b200.networks import unet_3d as u3
+    net = u3.unet_3D(n_classes=2, in_channels=1)
+    sd = U3.fixture_state_dict(31)
+    net.load_state_dict(sd)
+    B, P = 2, 32
+    x, y = U3.fixture_inputs(32, B, P)
+    FlatParams(net, "cpu")
+    rt = Runtime("cpu", seed=77)
+    plan = u3.UNet3DPlan(net, rt, B, P, P, P, True)
+    logits = plan.forward(x, train=dropout).view(B, 2, P, P, P)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = U3.unet3d_forward(leaf, x, unet3d_drops(77, B, P) if dropout else None)
+    torch.testing.assert_close(logits, ref, rtol=1e-3, atol=2e-4)
+    loss, _, _ = O.supervised_loss(ref, y, 2)
+    keys = list(sd.keys())
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys] + [ref], allow_unused=True)
+    plan.backward(grads[-1].permute(0, 2, 3, 4, 1).reshape(B * P ** 3, 2).contiguous())
+    named = dict(net.named_parameters())
+    for k, gr in zip(keys, grads[:-1]):
+        if k.endswith("0.bias"):          # a bias in front of InstanceNorm: analytically zero gradient
+            assert float(named[k].grad.abs().max()) < 1e-4
+            continue
+        rel = float((named[k].grad - gr).norm() / (gr.norm() + 1e-12))
+        assert rel < 2e-2, (k, rel)

@@ -493,3 +493,37 @@ def test_k2s2_views_and_gemm_match_torch(case):
         assert torch.equal(out.cpu(), out_r)
         want = F.conv_transpose3d(xn, wt.double(), bt.double(), stride=2).permute(0, 2, 3, 4, 1).reshape(-1, co)
         torch.testing.assert_close(out.cpu().double(), want, rtol=2e-2, atol=5e-3)
+
+
+@pytest.mark.parametrize("case", [(2, 4, 6, 8, 16), (1, 2, 2, 2, 4), (1, 6, 4, 10, 32)])
+def test_maxpool3d_and_trilinear_match_torch(case):
+    """nn.MaxPool3d(2) fwd/bwd (ties after ReLU: first maximum in scan order) and trilinear x2 (align_corners=False) fwd/bwd
+    against torch (code/networks/unet_3D.py:35-48, code/networks/utils.py:264)."""
+    n, dd, h, w, c = case
+    g = torch.Generator().manual_seed(sum(case))
+    a = torch.relu(torch.randn(n * dd * h * w, c, generator=g))                # many exact-zero ties
+    a[: a.shape[0] // 3] = 0.0
+    M2 = n * dd * h * w // 8
+    out, out_r = torch.empty(M2, c, device=DEV), torch.empty(M2, c)
+    ops.maxpool3d_fwd(cu(a), out, n, dd, h, w, c)
+    ref.maxpool3d_fwd(a, out_r, n, dd, h, w, c)
+    assert torch.equal(out.cpu(), out_r)
+    dp = torch.randn(M2, c, generator=g)
+    da, da_r = torch.full(a.shape, 7.0, device=DEV), torch.full(a.shape, 7.0)
+    ops.maxpool3d_bwd(cu(a), cu(dp), da, n, dd, h, w, c, False)
+    ref.maxpool3d_bwd(a, dp, da_r, n, dd, h, w, c, False)
+    assert torch.equal(da.cpu(), da_r)
+    ops.maxpool3d_bwd(cu(a), cu(dp), da, n, dd, h, w, c, True)
+    torch.testing.assert_close(da.cpu(), 2 * da_r, rtol=0, atol=0)
+    x = torch.randn(n * dd * h * w, c, generator=g)
+    y, y_r = torch.empty(8 * x.shape[0], c, device=DEV), torch.empty(8 * x.shape[0], c)
+    ops.upsample3d2x_fwd(cu(x), y, n, dd, h, w, c)
+    ref.upsample3d2x_fwd(x, y_r, n, dd, h, w, c)
+    torch.testing.assert_close(y.cpu(), y_r, rtol=1e-6, atol=1e-6)
+    dy = torch.randn(8 * x.shape[0], c, generator=g)
+    dx, dx_r = torch.full(x.shape, 3.0, device=DEV), torch.full(x.shape, 3.0)
+    ops.upsample3d2x_bwd(cu(dy), dx, n, dd, h, w, c, False)
+    ref.upsample3d2x_bwd(dy, dx_r, n, dd, h, w, c, False)
+    torch.testing.assert_close(dx.cpu(), dx_r, rtol=1e-5, atol=1e-5)
+    ops.upsample3d2x_bwd(cu(dy), dx, n, dd, h, w, c, True)
+    torch.testing.assert_close(dx.cpu(), 2 * dx_r, rtol=1e-5, atol=2e-5)

@@ -279,3 +279,24 @@ def test_uamt_2d_trainer_matches_reference_fixture(golden, fake_no_dropout):
                                rtol=2e-4, atol=1e-6)
     torch.testing.assert_close(student.state_dict()[g["key"]], g["w_student"], rtol=1e-3, atol=2e-6)
     torch.testing.assert_close(teacher.state_dict()[g["key"]], g["w_teacher"], rtol=1e-3, atol=2e-6)
+
+
+def test_unet3d_oracle_matches_reference_fixture(golden):
+    """oracle/unet3d_oracle.py against tests/golden/unet3d.pt (the reference's own unet_3D module, weights regenerated from
+    the seed): logits, supervised loss, gradient norms."""
+    from oracle import unet3d_oracle as U3
+    g = golden("unet3d.pt")
+    sd = U3.fixture_state_dict(g["seed"])
+    ck = float(sum(v.double().abs().sum() for v in sd.values()))
+    if abs(ck - g["checksum"]) > 1e-6 * g["checksum"]:
+        pytest.skip("torch RNG stream differs from the fixture's")
+    x, y = U3.fixture_inputs(g["seed"] + 1, g["B"], g["P"])
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits = U3.unet3d_forward(leaf, x)
+    torch.testing.assert_close(logits[:, :, ::2, ::2, ::2], g["logits_sub"], rtol=1e-3, atol=1e-4)
+    loss, ce, dice = O.supervised_loss(logits, y, 2)
+    torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-4, atol=1e-6)
+    loss.backward()
+    for k, v in leaf.items():
+        gn = float(v.grad.norm())
+        assert abs(gn - g["grad_norm"][k]) <= 1e-2 * g["grad_norm"][k] + 1e-5, (k, gn, g["grad_norm"][k])

@@ -1,0 +1,67 @@
+"""unet_3D (code/networks/unet_3D.py, the reference's default 3-D model) on the GPU: the reference-generated fixture
+tests/golden/unet3d.pt through the exact (3xTF32) schedule and through the production TF32 path (3-D halo-block tcgen05
+convolutions, row-ring weight gradient, 3-D pooling / trilinear kernels), and a Mean-Teacher step over two unet_3Ds."""
+import pytest
+import torch
+
+from cv_ssl_mis_b200.networks import unet_3d as u3
+from cv_ssl_mis_b200.networks.net_factory_3d import net_factory_3d
+from cv_ssl_mis_b200.trainers import MeanTeacherTrainer
+from oracle import ssl_oracle as O
+from oracle import unet3d_oracle as U3
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_unet3d_matches_reference_fixture(golden, exact, monkeypatch):
+    g = golden("unet3d.pt")
+    sd = U3.fixture_state_dict(g["seed"])
+    ck = float(sum(v.double().abs().sum() for v in sd.values()))
+    if abs(ck - g["checksum"]) > 1e-6 * g["checksum"]:
+        pytest.skip("torch RNG stream differs from the fixture's")
+    monkeypatch.setattr(u3, "P_DROP", 0.0)               # the fixture ran with nn.Dropout off
+    net = u3.unet_3D(n_classes=2, in_channels=1, exact=exact)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    x, y = U3.fixture_inputs(g["seed"] + 1, g["B"], g["P"])
+    logits = net(x.cuda())
+    sub = logits[:, :, ::2, ::2, ::2].detach().cpu()
+    if exact:
+        torch.testing.assert_close(sub, g["logits_sub"], rtol=2e-3, atol=3e-4)
+    else:
+        assert float((sub - g["logits_sub"]).abs().max()) <= 5e-2 * float(g["logits_sub"].abs().max())
+    loss, ce, dice = O.supervised_loss(logits, y.cuda(), 2)
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-3 if exact else 1e-2, atol=1e-5)
+    loss.backward()
+    for k, p in net.named_parameters():
+        if k.endswith("0.bias"):                          # bias in front of InstanceNorm: zero gradient up to round-off
+            continue
+        gn = float(p.grad.norm())
+        assert abs(gn - g["grad_norm"][k]) <= (1e-2 if exact else 0.15) * g["grad_norm"][k] + 1e-5, (k, gn, g["grad_norm"][k])
+        if exact:
+            torch.testing.assert_close(p.grad.flatten()[:8].cpu(), g["grad_head"][k], rtol=2e-2, atol=2e-5, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_unet3d_mean_teacher_step_runs_and_replays():
+    """train_mean_teacher_3D.py's default model through MeanTeacherTrainer: eager and CUDA-graph schedules agree bit for bit,
+    losses are finite, the teacher moves towards the student."""
+    g = torch.Generator().manual_seed(5)
+    B, Lb, P = 2, 1, 32
+    x = torch.randn(B, 1, P, P, P, generator=g).pin_memory()
+    y = (torch.rand(B, P, P, P, generator=g) > 0.5).long().pin_memory()
+
+    def run(graph):
+        torch.manual_seed(3)
+        s, t = net_factory_3d("unet_3D", 1, 2, seed=1), net_factory_3d("unet_3D", 1, 2, seed=2)
+        for p in t.parameters():
+            p.detach_()
+        tr = MeanTeacherTrainer(s, t, batch_size=B, labeled_bs=Lb, patch_size=(P, P, P), num_classes=2, start_iter=1500,
+                                label_dtype=torch.int64, use_cuda_graph=graph)
+        losses = [tr.step(x, y, read_loss=True) for _ in range(2)]
+        return losses, tr.flat.data.clone(), tr.ema_flat.data.clone()
+
+    l0, p0, e0 = run(False)
+    l1, p1, e1 = run(True)
+    assert all(torch.isfinite(torch.tensor(l)).all() for l in l0) and l0[0][3] > 0
+    assert l0 == l1 and torch.equal(p0, p1) and torch.equal(e0, e1)

@@ -24,9 +24,7 @@ groups = {"bn_reduce_kernel<1>": [], "bn_bwd_finalize_kernel": [], "bn_act_bwd_k
 for r in data:
     name = r[ix["Kernel Name"]]
     for k in groups:
-        if name.startswith(k.split("<")[0]) and (("<" not in k) or k.split("<")[1].rstrip(">") in name.split("(")[0].replace("(int)", "")):
-            if k.startswith("bn_reduce") and "0>" in name.split("(")[0]:
-                continue
+        if k in name:
             groups[k].append(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"))
             break
 per = {k: v[-calls:] for k, v in groups.items()}
