@@ -10,6 +10,7 @@ def main(argv=None, loader=None, defaults=None):
     p = base_parser("ACDC/Cross_Teaching_Between_CNN_Transformer", "unet", 16, (224, 224), 8, 7, "../data/ACDC", num_classes=4)
     add_swin_flags(p)
     p.add_argument('--model2', type=str, default="ViT_Seg", help='second network (reference: the Swin-UNet ViT_seg)')
+    p.add_argument('--vit1', type=int, default=0, help='1: model 1 is a Swin-UNet as well (train_cross_pseudo_supervision_2D_ViT.py)')
     p.add_argument('--pseudo_loss', type=str, default="dice", choices=["dice", "ce"],
                    help='dice: cross teaching (:242-245); ce: cross pseudo supervision')
     if defaults:                                                  # same loop under another reference script name
@@ -19,8 +20,11 @@ def main(argv=None, loader=None, defaults=None):
     from ..networks.net_factory import net_factory
     from ..trainers import CrossTeachingTrainer
     pg, rank = process_group()
-    model1 = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)              # :134-141
-    config = build_swin_config(args) if args.model2 == "ViT_Seg" else None                        # config.py:get_config(args)
+    config = build_swin_config(args) if (args.model2 == "ViT_Seg" or args.vit1) else None         # config.py:get_config(args)
+    if args.vit1:
+        model1 = net_factory(net_type="ViT_Seg", in_chns=1, class_num=args.num_classes, config=config, img_size=args.patch_size)
+    else:
+        model1 = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)          # :134-141
     model2 = net_factory(net_type=args.model2, in_chns=1, class_num=args.num_classes, config=config,
                          img_size=args.patch_size)                                                # :142-144 (ViT_seg)
     if model1 is None or model2 is None:

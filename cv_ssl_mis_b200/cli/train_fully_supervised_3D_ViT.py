@@ -5,8 +5,10 @@ import sys
 from ._common import base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None):
+def main(argv=None, loader=None, defaults=None):
     p = base_parser("BraTs2019_Fully_Supervised", "unetr", 2, (96, 96, 96), 2, 25, "../data/BraTS2019", semi=False)
+    if defaults:
+        p.set_defaults(**defaults)
     args = p.parse_args(argv)
     args.num_classes = 2
     seed_everything(args)

@@ -1,12 +1,16 @@
 """Command line of code/train_interpolation_consistency_training_2D.py (flags :38-76, incl. --ict_alpha)."""
 import sys
 
-from ._common import base_parser, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
+from ._common import add_swin_flags, base_parser, build_swin_config, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None):
+def main(argv=None, loader=None, defaults=None):
     p = base_parser("ACDC/Interpolation_Consistency_Training", "unet", 24, (256, 256), 12, 300, "../data/ACDC", num_classes=4)
     p.add_argument('--ict_alpha', type=int, default=0.2, help='ict_alpha')           # reference declares type=int, default 0.2
+    p.add_argument('--vit', type=int, default=0, help='1: build the Swin-UNet ViT_seg (train_interpolation_consistency_training_2D_ViT.py)')
+    add_swin_flags(p)
+    if defaults:
+        p.set_defaults(**defaults)
     args = p.parse_args(argv)
     seed_everything(args)
     from ..networks.net_factory import net_factory
@@ -14,7 +18,9 @@ def main(argv=None, loader=None):
     pg, rank = process_group()
 
     def create_model(ema=False):
-        model = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes)
+        name = "ViT_Seg" if (args.vit or args.model == "ViT_Seg") else args.model
+        kw = dict(config=build_swin_config(args), img_size=args.patch_size) if name == "ViT_Seg" else {}
+        model = net_factory(net_type=name, in_chns=1, class_num=args.num_classes, **kw)
         if model is None:
             raise SystemExit(f"--model {args.model}: not built (available: unet, ViT_Seg)")
         if ema:

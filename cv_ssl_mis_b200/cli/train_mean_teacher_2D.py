@@ -9,7 +9,8 @@ def main(argv=None, loader=None, defaults=None):
     p = base_parser("ACDC/Mean_Teacher", "unet", 24, (224, 224), 12, 7, "../data/ACDC", num_classes=4)
     p.add_argument('--uncertainty_T', type=int, default=0, help='8: the uncertainty-aware variant (MC-dropout mask)')
     p.add_argument('--supervised', type=int, default=0, help='1: no unlabeled half (train_fully_supervised_2D.py)')
-    add_swin_flags(p)                                             # only used by --model ViT_Seg (train_mean_teacher_ViT.py)
+    p.add_argument('--vit', type=int, default=0, help='1: build the Swin-UNet ViT_seg whatever --model says (the *_ViT.py scripts)')
+    add_swin_flags(p)                                             # only used by the Swin-UNet
     if defaults:                                                  # same loop under another reference script name
         p.set_defaults(**defaults)
     args = p.parse_args(argv)
@@ -21,8 +22,9 @@ def main(argv=None, loader=None, defaults=None):
     pg, rank = process_group()
 
     def create_model(ema=False):                                  # code/train_mean_teacher_2D.py:136-144
-        kw = dict(config=build_swin_config(args), img_size=args.patch_size) if args.model == "ViT_Seg" else {}
-        model = net_factory(net_type=args.model, in_chns=1, class_num=args.num_classes, **kw)
+        name = "ViT_Seg" if (args.vit or args.model == "ViT_Seg") else args.model
+        kw = dict(config=build_swin_config(args), img_size=args.patch_size) if name == "ViT_Seg" else {}
+        model = net_factory(net_type=name, in_chns=1, class_num=args.num_classes, **kw)
         if model is None:
             raise SystemExit(f"--model {args.model}: not built (available: unet, ViT_Seg)")
         if ema:

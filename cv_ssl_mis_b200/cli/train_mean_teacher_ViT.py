@@ -1,9 +1,9 @@
-"""Command line of code/train_mean_teacher_ViT.py (Mean Teacher over two Swin-UNets): the loop of cli/train_mean_teacher_2D.py with the defaults of this script."""
+"""Command line of code/train_mean_teacher_ViT.py (Mean Teacher over two Swin-UNets; --model stays 'unet' for the snapshot path, like the reference): the loop of cli/train_mean_teacher_2D.py with the defaults of this script."""
 import sys
 
 from . import train_mean_teacher_2D as _impl
 
-DEFAULTS = dict(exp='ACDC/Mean_Teacher_ViT', patch_size=[224, 224], labeled_num=7, model='ViT_Seg')
+DEFAULTS = dict(exp='ACDC/Mean_Teacher_ViT', patch_size=[224, 224], labeled_num=7, vit=1)
 
 
 def main(argv=None, loader=None):

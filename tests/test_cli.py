@@ -123,4 +123,13 @@ def test_reference_script_names(cpu_env):
     assert (cpu_env / "model" / "ACDC" / "Cross_Pseudo_Supervision_1_labeled" / "unet" / "model2_iter_2.pth").exists()
     assert mt3d.main(["--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
     assert (cpu_env / "model" / "BraTs2019_Mean_Teacher_25_labeled" / "unet_3D" / "iter_2.pth").exists()       # the reference's default model
-    assert mtvit.DEFAULTS["model"] == "ViT_Seg" and mtvit.DEFAULTS["exp"] == "ACDC/Mean_Teacher_ViT"
+    assert mtvit.DEFAULTS["vit"] == 1 and mtvit.DEFAULTS["exp"] == "ACDC/Mean_Teacher_ViT"
+    from cv_ssl_mis_b200.cli import (train_fully_supervised_3D as fs3d, train_fully_supervised_2D_ViT as fsvit,
+                                     train_uncertainty_aware_mean_teacher_ViT_2D as uamtvit,
+                                     train_interpolation_consistency_training_2D_ViT as ictvit,
+                                     train_cross_pseudo_supervision_2D_ViT as cpsvit)
+    assert fs3d.main(["--batch_size", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
+    assert (cpu_env / "model" / "BraTS2019" / "Fully_Supervised_25_labeled" / "unet_3D" / "iter_2.pth").exists()
+    # the Swin-UNet variants are only parsed here (a 224^2 Swin-UNet step is a GPU job)
+    assert fsvit.DEFAULTS["supervised"] == 1 and uamtvit.DEFAULTS["uncertainty_T"] == 8 and ictvit.DEFAULTS["vit"] == 1
+    assert cpsvit.DEFAULTS["vit1"] == 1 and cpsvit.DEFAULTS["pseudo_loss"] == "ce"
