@@ -669,7 +669,7 @@ def _read_config(config):
               qkv_bias=_Cfg.QKV_BIAS, drop_path_rate=_Cfg.DROP_PATH_RATE, patch_norm=_Cfg.PATCH_NORM)
     if config is None:
         return kw
-    if isinstance(config, dict):
+    if isinstance(config, dict) and "MODEL" not in config:        # plain keyword dict (a yacs-like dict node has MODEL / DATA)
         kw.update(config)
         return kw
     sw = config.MODEL.SWIN

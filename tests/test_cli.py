@@ -106,6 +106,16 @@ def test_swin_config_from_cfg_and_opts(tmp_path):
         build_swin_config(argparse.Namespace(cfg=str(tmp_path / "missing.yaml"), opts=None, batch_size=8))
 
 
+def test_swin_config_reaches_the_model():
+    """build_swin_config's yacs-like node must be read as a config, not as a keyword dict (found by tools/gpu_smoke_cli_vit.py)."""
+    import argparse
+    from cv_ssl_mis_b200.cli._common import build_swin_config
+    from cv_ssl_mis_b200.networks.swin_unet import _read_config
+    cfg = build_swin_config(argparse.Namespace(cfg=None, opts=["MODEL.DROP_PATH_RATE", "0.3"]))
+    kw = _read_config(cfg)
+    assert kw["depths"] == (2, 2, 2, 2) and abs(kw["drop_path_rate"] - 0.3) < 1e-12 and kw["img_size"] == 224
+
+
 def test_reference_script_names(cpu_env):
     """The reference's other script names on the path run the same loops with their own defaults
     (code/train_uncertainty_aware_mean_teacher_2D.py, train_fully_supervised_2D.py, train_mean_teacher_3D.py,
