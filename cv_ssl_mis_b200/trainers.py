@@ -434,7 +434,7 @@ class CrossTeachingTrainer(_Pipelined):
         pin = dev.type == "cuda"
         self.hp_ring = PinnedRing(8, dev)
         self.hp = torch.zeros(8, dtype=torch.float32, device=dev)
-        self.S = self.patch[0] * self.patch[1]
+        self.S = math.prod(self.patch)             # 2-D slices or 3-D patches (train_cross_pseudo_supervision_3D.py)
         self.x = torch.empty((self.B, 1, *self.patch), dtype=torch.float32, device=dev)
         self.y = torch.empty((self.B, *self.patch), dtype=label_dtype, device=dev)
         # per model: [ce, dice, pseudo-label dice, total, coefficients...]

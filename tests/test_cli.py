@@ -140,6 +140,10 @@ def test_reference_script_names(cpu_env):
                                      train_cross_pseudo_supervision_2D_ViT as cpsvit)
     assert fs3d.main(["--batch_size", "1", "--patch_size", "16", "16", "16"] + COMMON) == "Training Finished!"
     assert (cpu_env / "model" / "BraTS2019" / "Fully_Supervised_25_labeled" / "unet_3D" / "iter_2.pth").exists()
+    from cv_ssl_mis_b200.cli import train_cross_pseudo_supervision_3D as cps3d
+    assert cps3d.main(["--model", "vnet", "--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16"] + COMMON) \
+        == "Training Finished!"
+    assert (cpu_env / "model" / "BraTs2019_Cross_Pseudo_Supervision_25_labeled" / "vnet" / "model2_iter_2.pth").exists()
     # the Swin-UNet variants are only parsed here (a 224^2 Swin-UNet step is a GPU job)
     assert fsvit.DEFAULTS["supervised"] == 1 and uamtvit.DEFAULTS["uncertainty_T"] == 8 and ictvit.DEFAULTS["vit"] == 1
     assert cpsvit.DEFAULTS["vit1"] == 1 and cpsvit.DEFAULTS["pseudo_loss"] == "ce"

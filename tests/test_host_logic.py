@@ -559,3 +559,42 @@ def test_unet3d_plan_matches_oracle(fake, dropout):
             continue
         rel = float((named[k].grad - gr).norm() / (gr.norm() + 1e-12))
         assert rel < 2e-2, (k, rel)
+
+
+def test_cross_pseudo_supervision_3d_trainer_matches_oracle(fake, monkeypatch):
+    """code/train_cross_pseudo_supervision_3D.py:152-176 over two unet_3Ds (dropout off): both losses and one SGD update of
+    CrossTeachingTrainer(pseudo_loss="ce") on 3-D patches with int64 labels."""
+    import torch.nn.functional as F
+    from oracle import unet3d_oracle as U3
+    from cv_ssl_mis_b200.networks import unet_3d as u3
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+    monkeypatch.setattr(u3, "P_DROP", 0.0)
+    sds = [U3.fixture_state_dict(61), U3.fixture_state_dict(62)]
+    nets = []
+    for sd in sds:
+        n = u3.unet_3D(n_classes=2, in_channels=1)
+        n.load_state_dict(sd)
+        nets.append(n)
+    B, Lb, P, it = 2, 1, 32, 3000              # 16^3 would leave a single voxel per channel in `center` (InstanceNorm undefined)
+    tr = CrossTeachingTrainer(nets[0], nets[1], batch_size=B, labeled_bs=Lb, patch_size=(P, P, P), num_classes=2, start_iter=it,
+                              label_dtype=torch.int64, pseudo_loss="ce")
+    x, y = U3.fixture_inputs(63, B, P)
+    got = tr.step(x, y, read_loss=True)
+    leaf = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in sds]
+    outs = [U3.unet3d_forward(leaf[i], x) for i in range(2)]
+    w = O.consistency_weight(it)
+    want, total = [], 0.0
+    for i in range(2):
+        sup, ce, dice = O.supervised_loss(outs[i][:Lb], y[:Lb], 2)
+        pseudo = torch.argmax(torch.softmax(outs[1 - i][Lb:].detach(), 1), 1)
+        ps = F.cross_entropy(outs[i][Lb:], pseudo)
+        m = sup + w * ps
+        total = total + m
+        want += [ce, dice, ps, m]
+    total.backward()
+    torch.testing.assert_close(torch.tensor(got), torch.stack(want).detach(), rtol=1e-4, atol=1e-5)
+    lr = O.poly_lr(0.01, it, 30000)
+    for i, n in enumerate(nets):
+        k = "up_concat1.conv.conv2.0.weight"
+        new = sds[i][k] - lr * (leaf[i][k].grad + 1e-4 * sds[i][k])
+        torch.testing.assert_close(n.state_dict()[k], new, rtol=2e-3, atol=1e-6)

@@ -65,3 +65,36 @@ def test_unet3d_mean_teacher_step_runs_and_replays():
     l1, p1, e1 = run(True)
     assert all(torch.isfinite(torch.tensor(l)).all() for l in l0) and l0[0][3] > 0
     assert l0 == l1 and torch.equal(p0, p1) and torch.equal(e0, e1)
+
+
+def test_unet3d_cross_pseudo_supervision_and_uamt_steps():
+    """The other two reference loops whose default model is unet_3D: Cross Pseudo Supervision 3-D (two networks, CE on the
+    other's pseudo labels) and uncertainty-aware Mean Teacher (T = 4 stochastic teacher passes): finite losses, CUDA-graph
+    replay equal to the eager schedule."""
+    from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
+    g = torch.Generator().manual_seed(6)
+    B, Lb, P = 2, 1, 32
+    x = torch.randn(B, 1, P, P, P, generator=g).pin_memory()
+    y = (torch.rand(B, P, P, P, generator=g) > 0.5).long().pin_memory()
+
+    def cps(graph):
+        torch.manual_seed(3)
+        m1, m2 = net_factory_3d("unet_3D", 1, 2, seed=1), net_factory_3d("unet_3D", 1, 2, seed=2)
+        tr = CrossTeachingTrainer(m1, m2, batch_size=B, labeled_bs=Lb, patch_size=(P, P, P), num_classes=2, start_iter=3000,
+                                  label_dtype=torch.int64, use_cuda_graph=graph, pseudo_loss="ce")
+        return [tr.step(x, y, read_loss=True) for _ in range(2)], tr.flats[0].data.clone()
+
+    def uamt(graph):
+        torch.manual_seed(3)
+        s, t = net_factory_3d("unet_3D", 1, 2, seed=1), net_factory_3d("unet_3D", 1, 2, seed=2)
+        for p in t.parameters():
+            p.detach_()
+        tr = MeanTeacherTrainer(s, t, batch_size=B, labeled_bs=Lb, patch_size=(P, P, P), num_classes=2, start_iter=1500,
+                                uncertainty_T=4, consistency_gate_iters=0, use_cuda_graph=graph)
+        return [tr.step(x, y, read_loss=True) for _ in range(2)], tr.flat.data.clone()
+
+    for fn in (cps, uamt):
+        l0, p0 = fn(False)
+        l1, p1 = fn(True)
+        assert all(torch.isfinite(torch.tensor(l)).all() for l in l0) and l0[0][3] > 0, l0
+        assert l0 == l1 and torch.equal(p0, p1), fn.__name__
