@@ -312,7 +312,7 @@ class ICTTrainer(MeanTeacherTrainer):
         self.x_in = torch.empty((self.B_in, 1, *self.patch), dtype=torch.float32, device=dev)
         self.y_in = torch.empty((self.B_in, *self.patch), dtype=self.y.dtype, device=dev)
         self.mix_ring = PinnedRing(h, dev)
-        self.mix = torch.zeros((h, 1, 1, 1), dtype=torch.float32, device=dev)
+        self.mix = torch.zeros((h, 1) + (1,) * len(self.patch), dtype=torch.float32, device=dev)     # 2-D slices or 3-D patches
         self.p0 = torch.empty((h, self.C, self.S), dtype=torch.float32, device=dev)
         self.p1 = torch.empty_like(self.p0)
         self.pseudo_logits = torch.empty_like(self.p0)
@@ -348,7 +348,7 @@ class ICTTrainer(MeanTeacherTrainer):
         ops.sgd_ema_step(self.flat.data, self.flat.grad, self.momentum_buf, self.ema_flat.data, self.hp)
 
     def step(self, images, labels, read_loss=False, mix_factors=None):
-        """images [batch_size, 1, H, W], labels [batch_size, H, W]; mix_factors: optional [labeled_bs // 2] values
+        """images [batch_size, 1, *patch], labels [batch_size, *patch]; mix_factors: optional [labeled_bs // 2] values
         (default: numpy Beta(ict_alpha, ict_alpha) draws, :155-158)."""
         if mix_factors is None:
             mix_factors = self.mix_rng.beta(self.ict_alpha, self.ict_alpha, size=(self.h,))

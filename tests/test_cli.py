@@ -144,6 +144,9 @@ def test_reference_script_names(cpu_env):
     assert cps3d.main(["--model", "vnet", "--batch_size", "2", "--labeled_bs", "1", "--patch_size", "16", "16", "16"] + COMMON) \
         == "Training Finished!"
     assert (cpu_env / "model" / "BraTs2019_Cross_Pseudo_Supervision_25_labeled" / "vnet" / "model2_iter_2.pth").exists()
+    from cv_ssl_mis_b200.cli import train_interpolation_consistency_training_3D as ict3d
+    assert ict3d.main(["--model", "vnet", "--batch_size", "4", "--labeled_bs", "2", "--patch_size", "16", "16", "16"] + COMMON) \
+        == "Training Finished!"
     # the Swin-UNet variants are only parsed here (a 224^2 Swin-UNet step is a GPU job)
     assert fsvit.DEFAULTS["supervised"] == 1 and uamtvit.DEFAULTS["uncertainty_T"] == 8 and ictvit.DEFAULTS["vit"] == 1
     assert cpsvit.DEFAULTS["vit1"] == 1 and cpsvit.DEFAULTS["pseudo_loss"] == "ce"

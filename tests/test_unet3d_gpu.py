@@ -68,9 +68,9 @@ def test_unet3d_mean_teacher_step_runs_and_replays():
 
 
 def test_unet3d_cross_pseudo_supervision_and_uamt_steps():
-    """The other two reference loops whose default model is unet_3D: Cross Pseudo Supervision 3-D (two networks, CE on the
-    other's pseudo labels) and uncertainty-aware Mean Teacher (T = 4 stochastic teacher passes): finite losses, CUDA-graph
-    replay equal to the eager schedule."""
+    """The other reference loops whose default model is unet_3D: Cross Pseudo Supervision 3-D (two networks, CE on the
+    other's pseudo labels), uncertainty-aware Mean Teacher (T = 4 stochastic teacher passes) and ICT 3-D (mixed unlabeled
+    patches): finite losses, CUDA-graph replay equal to the eager schedule."""
     from cv_ssl_mis_b200.trainers import CrossTeachingTrainer
     g = torch.Generator().manual_seed(6)
     B, Lb, P = 2, 1, 32
@@ -93,7 +93,20 @@ def test_unet3d_cross_pseudo_supervision_and_uamt_steps():
                                 uncertainty_T=4, consistency_gate_iters=0, use_cuda_graph=graph)
         return [tr.step(x, y, read_loss=True) for _ in range(2)], tr.flat.data.clone()
 
-    for fn in (cps, uamt):
+    def ict(graph):
+        from cv_ssl_mis_b200.trainers import ICTTrainer
+        torch.manual_seed(3)
+        s, t = net_factory_3d("unet_3D", 1, 2, seed=1), net_factory_3d("unet_3D", 1, 2, seed=2)
+        for p in t.parameters():
+            p.detach_()
+        g4 = torch.Generator().manual_seed(8)
+        x4 = torch.randn(4, 1, P, P, P, generator=g4).pin_memory()
+        y4 = (torch.rand(4, P, P, P, generator=g4) > 0.5).long().pin_memory()
+        tr = ICTTrainer(s, t, batch_size=4, labeled_bs=2, patch_size=(P, P, P), num_classes=2, start_iter=1500, mix_seed=5,
+                        use_cuda_graph=graph)
+        return [tr.step(x4, y4, read_loss=True) for _ in range(2)], tr.flat.data.clone()
+
+    for fn in (cps, uamt, ict):
         l0, p0 = fn(False)
         l1, p1 = fn(True)
         assert all(torch.isfinite(torch.tensor(l)).all() for l in l0) and l0[0][3] > 0, l0
