@@ -133,3 +133,45 @@ def test_full_size_uamt_step_properties():
     assert net_factory_3d("does_not_exist") is None
     sd = net_factory_3d("vnet", 1, 2).state_dict()
     assert len(sd) == 205 and sum(1 for k in sd if "num_batches" not in k and "running" not in k) == 118
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_full_size_vnet_fwd_bwd_matches_cpu_oracle(exact):
+    """BASELINE config-4 volume size (96^3, two volumes) through the kernels the bench times -- exact=False: 3-D halo-block
+    tcgen05 forward / data gradient (64-byte rows at the 16-channel level), row-ring weight gradient, GEMM-formulated
+    2x2x2 stride-2 convs -- against the CPU oracle (torch fp32) with the same Philox dropout masks: logits within
+    5e-2 of the largest logit (1e-3 exact), loss 1e-2 (1e-4), per-tensor weight gradients 0.15 relative / cosine >= 0.99
+    (1e-2 / 0.9999) -- the TF32 gradient budget measured for the 2-D network (tests/test_unet_gpu.py)."""
+    torch.manual_seed(17)
+    net = vnet_mod.VNet(1, 2, has_dropout=True, seed=501, exact=exact)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda().train()
+    B, P = 2, 96
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, 1, P, P, P, generator=g)
+    low = torch.randint(0, 2, (B, P // 8, P // 8, P // 8), generator=g)
+    y = low.repeat_interleave(8, 1).repeat_interleave(8, 2).repeat_interleave(8, 3).long()
+    logits = net(x.cuda())                                             # the autograd bridge bumps the RNG epoch once
+    loss, ce, dice = O.supervised_loss(logits, y.cuda(), 2)
+    loss.backward()
+    keys = O.param_keys(sd0)
+    leaf = {k: (v.clone().requires_grad_(True) if k in keys else v.clone()) for k, v in sd0.items()}
+    d5, d9 = vnet_drops(501 + 1, B)
+    ref = O.vnet_forward(leaf, x, True, d5, d9, update_running=False)
+    rloss, _, _ = O.supervised_loss(ref, y, 2)
+    rloss.backward()
+    big = float(ref.abs().max())
+    err = float((logits.detach().cpu() - ref.detach()).abs().max())
+    assert err <= (1e-3 if exact else 5e-2) * big, (err, big)
+    assert abs(float(loss) - float(rloss)) <= (1e-4 if exact else 1e-2) * abs(float(rloss))
+    named = dict(net.named_parameters())
+    worst = 0.0
+    for k in keys:
+        if not k.endswith("weight") or leaf[k].grad.dim() < 2:          # conv weights (biases in front of BatchNorm: ~0 gradient)
+            continue
+        a, b = named[k].grad.detach().cpu().flatten(), leaf[k].grad.flatten()
+        rel = float((a - b).norm() / (b.norm() + 1e-20))
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-20))
+        worst = max(worst, rel)
+        assert rel < (1e-2 if exact else 0.15) and cos > (0.9999 if exact else 0.99), (k, rel, cos)
+    print("worst relative weight-gradient error", worst)
