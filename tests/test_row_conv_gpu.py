@@ -260,3 +260,63 @@ def test_blk3d_dgrad(case):
     got = dx.clone()
     ops.conv_blk_dgrad(d, dy.to(DEV), wpk, dx, None, accumulate=True)
     torch.testing.assert_close(dx, 2 * got, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ production shapes, on device
+@pytest.mark.parametrize("case", [(2, 96, 96, 96, 16), (2, 48, 48, 48, 32), (4, 24, 24, 24, 64), (4, 12, 12, 12, 128), (4, 6, 6, 6, 256)])
+def test_3d_tcgen05_kernels_at_config4_shapes_match_exact_kernels(case):
+    """The VNet layer shapes of BASELINE config 4 (96^3 volumes): halo-block forward / data gradient and the row-ring weight
+    gradient (TF32 products) against the generic implicit-GEMM kernels in their exact 3xTF32 mode, all on the device -- every
+    tile of the full-size launch is compared, error budget = TF32 round-off of a 27 * C long dot product."""
+    from cv_ssl_mis_b200._lib import PACK_CONV_FWD, PACK_CONV_DGRAD
+    n, dd, h, w, c = case
+    g = torch.Generator(device=DEV).manual_seed(sum(case))
+    M = n * dd * h * w
+    x = torch.randn(M, c, device=DEV, generator=g)
+    dy = torch.randn(M, c, device=DEV, generator=g)
+    wgt = torch.randn(c, c, 3, 3, 3, device=DEV, generator=g) * (c * 27) ** -0.5
+    bias = torch.randn(c, device=DEV, generator=g)
+    d = ops.conv_desc(n, dd, h, w, c, 0, c, 3, 1, 1, 3)
+
+    def generic_pack(mode):
+        out = torch.empty(ops.conv_packed_floats(mode, c, c, 27), device=DEV)
+        ops.conv_pack_weights(wgt, out, mode, c, c, 27)
+        return out
+
+    def check(got, want, what, tol=4e-3):
+        scale = float(want.abs().max())
+        err = float((got - want).abs().max())
+        assert err <= tol * scale, (what, err, scale)
+
+    # forward (+ fused BatchNorm sums)
+    mode = ops.conv_blk_supported(d, False) - 8
+    assert mode >= 0
+    wpk = torch.empty(27 * c * c, device=DEV)
+    ops.conv_blk_pack_weights(wgt, wpk, mode, c, c, 27)
+    y = torch.full((M, c), float("nan"), device=DEV)
+    nb = ops.conv_blk_stats_blocks(d)
+    part = torch.zeros(nb * 2 * c, dtype=torch.float64, device=DEV)
+    ops.conv_blk_fwd(d, x, None, wpk, bias, y, part)
+    y_ref = torch.empty_like(y)
+    ops.conv_fwd(d, x, None, generic_pack(PACK_CONV_FWD), bias, y_ref, False, True)
+    check(y, y_ref, "forward")
+    s = part.view(nb, 2, c).sum(0)
+    torch.testing.assert_close(s[0], y.double().sum(0), rtol=1e-6, atol=1e-6 * M)
+    torch.testing.assert_close(s[1], (y.double() ** 2).sum(0), rtol=1e-6, atol=1e-6 * M)
+    # data gradient
+    mode = ops.conv_blk_supported(d, True) - 8
+    ops.conv_blk_pack_weights(wgt, wpk, mode, c, c, 27)
+    dx = torch.full((M, c), float("nan"), device=DEV)
+    ops.conv_blk_dgrad(d, dy, wpk, dx, None)
+    dx_ref = torch.empty_like(dx)
+    ops.conv_dgrad(d, dy, generic_pack(PACK_CONV_DGRAD), dx_ref, None, False, True)
+    check(dx, dx_ref, "data gradient")
+    # weight gradient
+    assert ops.conv_row_wgrad_supported(d)
+    ws = torch.empty(ops.conv_row_wgrad_workspace_bytes(d) // 4 + 4, device=DEV)
+    dw = torch.full((c, c, 3, 3, 3), float("nan"), device=DEV)
+    ops.conv_row_wgrad(d, x, None, dy, ws, dw)
+    ws2 = torch.empty(ops.conv_wgrad_workspace_bytes(d) // 4 + 4, device=DEV)
+    dw_ref, db_ref = torch.empty_like(dw), torch.empty(c, device=DEV)
+    ops.conv_wgrad(d, x, None, dy, ws2, dw_ref, db_ref, False, True)
+    check(dw, dw_ref, "weight gradient", tol=6e-3)
