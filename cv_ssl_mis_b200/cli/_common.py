@@ -45,6 +45,8 @@ def base_parser(exp, model, batch_size, patch_size, labeled_bs, labeled_num, roo
     p.add_argument('--synthetic', type=int, default=1, help='draw synthetic batches of the dataset\'s shape (no h5 reader here)')
     p.add_argument('--log_every', type=int, default=50, help='read the losses back every k iterations (0: never)')
     p.add_argument('--save_every', type=int, default=3000, help='checkpoint interval (reference: 3000)')
+    p.add_argument('--val_every', type=int, default=200, help='validation interval when main() gets a val_loader (reference: 200)')
+    p.add_argument('--tensorboard', type=int, default=1, help='write the reference\'s tensorboard scalars under <snapshot>/log')
     p.add_argument('--no_graph', action='store_true', help='launch eagerly instead of replaying one CUDA graph per step')
     return p
 
@@ -185,11 +187,57 @@ def setup_logging(path):
     logging.getLogger().addHandler(logging.StreamHandler(sys.stdout))
 
 
-def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0):
+def _summary_writer(snapshot_path):
+    """tensorboard scalars like the reference's tensorboardX writer (code/train_mean_teacher_2D.py:193); None if unavailable."""
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(os.path.join(snapshot_path, "log"))
+    except Exception:                                            # tensorboard not installed: the text log carries the numbers
+        return None
+
+
+def _validate(args, trainer, val_loader, snapshot_path, models, writer, best, val_fn):
+    """In-loop validation of the reference scripts (code/train_mean_teacher_2D.py:263-294, two-model form:
+    code/train_cross_teaching_between_cnn_transformer_2D.py:283-345): per-class Dice / HD95 averaged over the validation
+    volumes, best-so-far checkpoints `iter_<n>_dice_<d>.pth` and `<model>_best_model.pth`."""
+    import numpy as np
+    it = trainer.iter_num
+    named = [(k, m) for k, m in models.items() if not k.startswith("ema")]
+    for idx, (prefix, model) in enumerate(named):
+        tag = "" if len(named) == 1 else f"model{idx + 1}_"
+        was_training = model.training
+        model.eval()
+        metric_list, n = 0.0, 0
+        for batch in val_loader:
+            metric_list = metric_list + np.array(val_fn(batch["image"], batch["label"], model), dtype=float)
+            n += 1
+        model.train(was_training)
+        if n == 0:
+            raise ValueError("the validation loader yielded no volumes")
+        metric_list = metric_list / n
+        performance, mean_hd95 = float(np.mean(metric_list, axis=0)[0]), float(np.mean(metric_list, axis=0)[1])
+        if writer is not None:
+            for c in range(metric_list.shape[0]):
+                writer.add_scalar(f"info/{tag}val_{c + 1}_dice", metric_list[c, 0], it)
+                writer.add_scalar(f"info/{tag}val_{c + 1}_hd95", metric_list[c, 1], it)
+            writer.add_scalar(f"info/{tag}val_mean_dice", performance, it)
+            writer.add_scalar(f"info/{tag}val_mean_hd95", mean_hd95, it)
+        if performance > best.get(prefix, 0.0):
+            best[prefix] = performance
+            stem = prefix if len(named) > 1 else ""
+            torch.save(model.state_dict(), os.path.join(snapshot_path, f"{stem}iter_{it}_dice_{round(performance, 4)}.pth"))
+            torch.save(model.state_dict(), os.path.join(snapshot_path, f"{args.model}_best_{prefix.rstrip('_') or 'model'}.pth"))
+        logging.info('iteration %d : %smean_dice : %f %smean_hd95 : %f' % (it, tag, performance, tag, mean_hd95))
+
+
+def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0, val_loader=None, val_fn=None, scalars=None):
     """The iteration loop of the reference scripts with the body replaced by `trainer.step`.
-    models: {checkpoint prefix: module}; fmt(iter_num, losses) -> log line."""
+    models: {checkpoint prefix: module}; fmt(iter_num, losses) -> log line; scalars(iter_num, losses) -> {tag: value} for
+    tensorboard; val_loader / val_fn(image, label, model) -> [(dice, hd95)] per class: validation every --val_every iterations."""
     it0 = trainer.iter_num
     t0 = time.time()
+    writer = _summary_writer(snapshot_path) if (rank == 0 and getattr(args, "tensorboard", 1)) else None
+    best = {}
     # the reference wraps its loader in `for epoch_num in range(max_iterations // len(trainloader) + 1)`
     # (code/train_mean_teacher_2D.py:199-201,296-301): a finite loader is re-iterated until max_iterations is reached
     while trainer.iter_num < args.max_iterations:
@@ -200,6 +248,12 @@ def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0):
             out = trainer.step(batch["image"], batch["label"], read_loss=bool(log))
             if log and rank == 0:
                 logging.info(fmt(trainer.iter_num, out))
+                if writer is not None and scalars is not None:
+                    for tag, v in scalars(trainer.iter_num, out).items():
+                        writer.add_scalar(tag, v, trainer.iter_num)
+            if (rank == 0 and val_loader is not None and getattr(args, "val_every", 0) and trainer.iter_num > 0
+                    and trainer.iter_num % args.val_every == 0):
+                _validate(args, trainer, val_loader, snapshot_path, models, writer, best, val_fn)
             if rank == 0 and args.save_every and trainer.iter_num % args.save_every == 0:
                 for prefix, m in models.items():
                     torch.save(m.state_dict(), os.path.join(snapshot_path, f"{prefix}iter_{trainer.iter_num}.pth"))
@@ -215,4 +269,6 @@ def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0):
         logging.info("%d iterations in %.2f s (%.1f samples/s per GPU)" % (n, dt, n * args.batch_size / max(dt, 1e-9)))
         for prefix, m in models.items():
             torch.save(m.state_dict(), os.path.join(snapshot_path, f"{prefix}iter_{trainer.iter_num}.pth"))
+        if writer is not None:
+            writer.close()
     return "Training Finished!"

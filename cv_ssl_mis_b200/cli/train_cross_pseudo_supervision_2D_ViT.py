@@ -6,8 +6,8 @@ from . import train_cross_teaching_between_cnn_transformer_2D as _impl
 DEFAULTS = dict(exp='ACDC/Cross_Teaching_Between_CNN_Transformer', pseudo_loss='ce', vit1=1)
 
 
-def main(argv=None, loader=None):
-    return _impl.main(argv, loader, defaults=DEFAULTS)
+def main(argv=None, loader=None, val_loader=None):
+    return _impl.main(argv, loader, defaults=DEFAULTS, val_loader=val_loader)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ from ._common import (add_swin_flags, base_parser, build_swin_config, process_gr
                       snapshot_dir, synthetic_batches)
 
 
-def main(argv=None, loader=None, defaults=None):
+def main(argv=None, loader=None, defaults=None, val_loader=None):
     p = base_parser("ACDC/Cross_Teaching_Between_CNN_Transformer", "unet", 16, (224, 224), 8, 7, "../data/ACDC", num_classes=4)
     add_swin_flags(p)
     p.add_argument('--model2', type=str, default="ViT_Seg", help='second network (reference: the Swin-UNet ViT_seg)')
@@ -55,7 +55,11 @@ def main(argv=None, loader=None, defaults=None):
     path = snapshot_dir(args)
     setup_logging(path)
     fmt = lambda it, l: 'iteration %d : model1 loss : %f model2 loss : %f' % (it, l[3], l[7])      # :271-272
-    return run_loop(args, trainer, loader, path, {"model1_": model1, "model2_": model2}, fmt, rank)
+    from ..val_2D import test_single_volume
+    val_fn = lambda image, label, net: test_single_volume(image, label, net, classes=args.num_classes, patch_size=args.patch_size)
+    scalars = lambda it, l: {'lr': trainer.lr, 'consistency_weight/consistency_weight': trainer.consistency_weight(it),       # :263-268
+                             'loss/model1_loss': l[3], 'loss/model2_loss': l[7]}
+    return run_loop(args, trainer, loader, path, {"model1_": model1, "model2_": model2}, fmt, rank, val_loader=val_loader, val_fn=val_fn, scalars=scalars)
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ import sys
 from ._common import add_swin_flags, base_parser, build_swin_config, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None, defaults=None):
+def main(argv=None, loader=None, defaults=None, val_loader=None):
     p = base_parser("ACDC/Interpolation_Consistency_Training", "unet", 24, (256, 256), 12, 300, "../data/ACDC", num_classes=4)
     p.add_argument('--ict_alpha', type=int, default=0.2, help='ict_alpha')           # reference declares type=int, default 0.2
     p.add_argument('--vit', type=int, default=0, help='1: build the Swin-UNet ViT_seg (train_interpolation_consistency_training_2D_ViT.py)')
@@ -44,7 +44,11 @@ def main(argv=None, loader=None, defaults=None):
     path = snapshot_dir(args)
     setup_logging(path)
     fmt = lambda it, l: 'iteration %d : loss : %f, loss_ce: %f, loss_dice: %f' % (it, l[3], l[0], l[1])
-    return run_loop(args, trainer, loader, path, {"": model}, fmt, rank)
+    from ..val_2D import test_single_volume
+    val_fn = lambda image, label, net: test_single_volume(image, label, net, classes=args.num_classes, patch_size=args.patch_size)
+    scalars = lambda it, l: {'info/lr': trainer.lr, 'info/total_loss': l[3], 'info/loss_ce': l[0], 'info/loss_dice': l[1],
+                             'info/consistency_loss': l[2], 'info/consistency_weight': trainer.consistency_weight(it)}
+    return run_loop(args, trainer, loader, path, {"": model}, fmt, rank, val_loader=val_loader, val_fn=val_fn, scalars=scalars)
 
 
 if __name__ == "__main__":

@@ -5,7 +5,7 @@ import sys
 from ._common import add_swin_flags, base_parser, build_swin_config, process_group, run_loop, seed_everything, setup_logging, snapshot_dir, synthetic_batches
 
 
-def main(argv=None, loader=None, defaults=None):
+def main(argv=None, loader=None, defaults=None, val_loader=None):
     p = base_parser("ACDC/Mean_Teacher", "unet", 24, (224, 224), 12, 7, "../data/ACDC", num_classes=4)
     p.add_argument('--uncertainty_T', type=int, default=0, help='8: the uncertainty-aware variant (MC-dropout mask)')
     p.add_argument('--supervised', type=int, default=0, help='1: no unlabeled half (train_fully_supervised_2D.py)')
@@ -57,7 +57,11 @@ def main(argv=None, loader=None, defaults=None):
     models = {"": model}
     if ema_model is not None:
         models["ema_"] = ema_model
-    return run_loop(args, trainer, loader, path, models, fmt, rank)
+    from ..val_2D import test_single_volume
+    val_fn = lambda image, label, net: test_single_volume(image, label, net, classes=args.num_classes, patch_size=args.patch_size)
+    scalars = lambda it, l: {'info/lr': trainer.lr, 'info/total_loss': l[3], 'info/loss_ce': l[0], 'info/loss_dice': l[1],      # :238-246
+                             'info/consistency_loss': l[2], 'info/consistency_weight': trainer.consistency_weight(it)}
+    return run_loop(args, trainer, loader, path, models, fmt, rank, val_loader=val_loader, val_fn=val_fn, scalars=scalars)
 
 
 if __name__ == "__main__":

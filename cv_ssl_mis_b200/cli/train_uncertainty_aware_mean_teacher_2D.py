@@ -6,8 +6,8 @@ from . import train_mean_teacher_2D as _impl
 DEFAULTS = dict(exp='ACDC/Uncertainty_Aware_Mean_Teacher', patch_size=[256, 256], labeled_num=136, uncertainty_T=8)
 
 
-def main(argv=None, loader=None):
-    return _impl.main(argv, loader, defaults=DEFAULTS)
+def main(argv=None, loader=None, val_loader=None):
+    return _impl.main(argv, loader, defaults=DEFAULTS, val_loader=val_loader)
 
 
 if __name__ == "__main__":

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) ssl_loss_bwd_kernel(const LossGeom g, con
 
 static inline int loss_grid(long long total) {
     long long blocks = (total + 255) / 256;
-    long long cap = (long long)b200_num_sms() * 4;
+    long long cap = (long long)b200_num_sms() * 8;      // 2048 resident threads per SM: the per-pixel exp / log chains need the warps
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 static inline int cpad_of(int C) { return C <= 2 ? 2 : (C <= 4 ? 4 : SSL_MAXC); }

@@ -150,3 +150,17 @@ def test_reference_script_names(cpu_env):
     # the Swin-UNet variants are only parsed here (a 224^2 Swin-UNet step is a GPU job)
     assert fsvit.DEFAULTS["supervised"] == 1 and uamtvit.DEFAULTS["uncertainty_T"] == 8 and ictvit.DEFAULTS["vit"] == 1
     assert cpsvit.DEFAULTS["vit1"] == 1 and cpsvit.DEFAULTS["pseudo_loss"] == "ce"
+
+
+def test_in_loop_validation_and_best_checkpoint(cpu_env):
+    """code/train_mean_teacher_2D.py:263-294: every --val_every iterations the validation volumes go through
+    test_single_volume in eval mode; mean Dice / HD95 are logged and the best model is saved under the reference's names."""
+    from cv_ssl_mis_b200.cli import train_mean_teacher_2D as cli
+    g = torch.Generator().manual_seed(9)
+    val = [{"image": torch.rand(1, 3, 40, 36, generator=g), "label": torch.randint(0, 4, (1, 3, 40, 36), generator=g)} for _ in range(2)]
+    out = cli.main(["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32", "--val_every", "2"] + COMMON, val_loader=val)
+    assert out == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Mean_Teacher_7_labeled" / "unet"
+    assert (snap / "unet_best_model.pth").exists() and list(snap.glob("iter_2_dice_*.pth"))
+    assert "mean_dice" in (snap / "log.txt").read_text()
+    assert list((snap / "log").glob("events.out.tfevents.*"))            # tensorboard scalars (info/lr, info/total_loss, ...)
