@@ -93,6 +93,7 @@ struct MhaP {
     float* dqkv;           // [B*N][3C]
     float* ds;             // [B*heads][N][N]
     int B, N, heads, hd, C;
+    int QB;                // queries (bwd_kv: keys) per CTA
     float scale;
 };
 
@@ -149,13 +150,14 @@ __device__ __forceinline__ void mha_mm_nn(const float* __restrict__ P, int ldp, 
 
 __global__ void __launch_bounds__(256) mha_fwd_kernel(const MhaP p) {
     extern __shared__ float sm[];
+    const int QB = p.QB;
     const int N = p.N, hd = p.hd, LD = hd + 1, LS = N + 1;
     float* sk = sm;                       // [N][LD]
     float* sv = sk + N * LD;              // [N][LD]
     float* sq = sv + N * LD;              // [QB][LD]
-    float* ss = sq + MHA_QB * LD;         // [QB][LS]
+    float* ss = sq + QB * LD;         // [QB][LS]
     const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
-    const int q0 = blockIdx.x * MHA_QB, nq = min(MHA_QB, N - q0);
+    const int q0 = blockIdx.x * QB, nq = min(QB, N - q0);
     const int tid = threadIdx.x, C3 = 3 * p.C;
     const float* base = p.qkv + (size_t)b * N * C3 + h * hd;
     for (int idx = tid; idx < N * hd; idx += 256) {
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(const MhaP p) {
     }
     __syncthreads();
     // S = q k^T, one 4 x 8 accumulator tile per thread (0.375 shared loads per FMA instead of 2)
-    for (int tile = tid; tile < (MHA_QB / 4) * ((N + 7) / 8); tile += 256) {
-        const int i0 = (tile % (MHA_QB / 4)) * 4, j0 = (tile / (MHA_QB / 4)) * 8;
+    for (int tile = tid; tile < (QB / 4) * ((N + 7) / 8); tile += 256) {
+        const int i0 = (tile % (QB / 4)) * 4, j0 = (tile / (QB / 4)) * 8;
         float acc[4][8];
         mha_mm_nt<4, 8>(sq, sk, LD, hd, i0, nq, j0, N, acc);
 #pragma unroll
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(const MhaP p) {
     }
     __syncthreads();
     // out = P v, 2 x 4 tiles
-    for (int tile = tid; tile < (MHA_QB / 2) * (hd / 4); tile += 256) {
+    for (int tile = tid; tile < (QB / 2) * (hd / 4); tile += 256) {
         const int d0 = (tile % (hd / 4)) * 4, i0 = (tile / (hd / 4)) * 2;
         float acc[2][4];
         mha_mm_nn<2, 4>(ss, LS, sv, LD, N, i0, nq, d0, acc);
@@ -217,13 +219,14 @@ __global__ void __launch_bounds__(256) mha_fwd_kernel(const MhaP p) {
 
 __global__ void __launch_bounds__(256) mha_bwd_q_kernel(const MhaP p) {
     extern __shared__ float sm[];
+    const int QB = p.QB;
     const int N = p.N, hd = p.hd, LD = hd + 1, LS = N + 1;
     float* sk = sm;
     float* sv = sk + N * LD;
     float* sdo = sv + N * LD;             // [QB][LD]
-    float* ss = sdo + MHA_QB * LD;        // [QB][LS]  P, then dS
+    float* ss = sdo + QB * LD;        // [QB][LS]  P, then dS
     const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
-    const int q0 = blockIdx.x * MHA_QB, nq = min(MHA_QB, N - q0);
+    const int q0 = blockIdx.x * QB, nq = min(QB, N - q0);
     const int tid = threadIdx.x, C3 = 3 * p.C;
     const float* base = p.qkv + (size_t)b * N * C3 + h * hd;
     for (int idx = tid; idx < N * hd; idx += 256) {
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(256) mha_bwd_q_kernel(const MhaP p) {
     }
     __syncthreads();
     // dq = dS k * scale, 2 x 4 tiles
-    for (int tile = tid; tile < (MHA_QB / 2) * (hd / 4); tile += 256) {
+    for (int tile = tid; tile < (QB / 2) * (hd / 4); tile += 256) {
         const int d0 = (tile % (hd / 4)) * 4, i0 = (tile / (hd / 4)) * 2;
         float acc[2][4];
         mha_mm_nn<2, 4>(ss, LS, sk, LD, N, i0, nq, d0, acc);
@@ -283,13 +286,14 @@ __global__ void __launch_bounds__(256) mha_bwd_q_kernel(const MhaP p) {
 
 __global__ void __launch_bounds__(256) mha_bwd_kv_kernel(const MhaP p) {
     extern __shared__ float sm[];
+    const int QB = p.QB;
     const int N = p.N, hd = p.hd, LD = hd + 1;
     float* sq = sm;                       // [N][LD]  (scaled q)
     float* sdo = sq + N * LD;             // [N][LD]
     float* sp = sdo + N * LD;             // [N][QB + 1]  P columns of this key block
-    float* sds = sp + N * (MHA_QB + 1);   // [N][QB + 1]  dS columns
+    float* sds = sp + N * (QB + 1);   // [N][QB + 1]  dS columns
     const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
-    const int j0 = blockIdx.x * MHA_QB, nk = min(MHA_QB, N - j0);
+    const int j0 = blockIdx.x * QB, nk = min(QB, N - j0);
     const int tid = threadIdx.x, C3 = 3 * p.C;
     const float* base = p.qkv + (size_t)b * N * C3 + h * hd;
     for (int idx = tid; idx < N * hd; idx += 256) {
@@ -299,12 +303,12 @@ __global__ void __launch_bounds__(256) mha_bwd_kv_kernel(const MhaP p) {
     }
     for (int idx = tid; idx < N * nk; idx += 256) {
         const int i = idx / nk, j = idx % nk;
-        sp[i * (MHA_QB + 1) + j] = __ldg(p.probs + ((size_t)bh * N + i) * N + j0 + j);
-        sds[i * (MHA_QB + 1) + j] = __ldg(p.ds + ((size_t)bh * N + i) * N + j0 + j);
+        sp[i * (QB + 1) + j] = __ldg(p.probs + ((size_t)bh * N + i) * N + j0 + j);
+        sds[i * (QB + 1) + j] = __ldg(p.ds + ((size_t)bh * N + i) * N + j0 + j);
     }
     __syncthreads();
     // dv = P^T dO and dk = dS^T q (q carries the scale): 2 x 4 tiles, both products share the loop over the queries
-    for (int tile = tid; tile < (MHA_QB / 2) * (hd / 4); tile += 256) {
+    for (int tile = tid; tile < (QB / 2) * (hd / 4); tile += 256) {
         const int d0 = (tile % (hd / 4)) * 4, jj = (tile / (hd / 4)) * 2;
         const int c0 = min(jj, nk - 1), c1 = min(jj + 1, nk - 1);
         float dv[2][4], dk[2][4];
@@ -314,8 +318,8 @@ __global__ void __launch_bounds__(256) mha_bwd_kv_kernel(const MhaP p) {
             for (int c = 0; c < 4; ++c) { dv[r][c] = 0.f; dk[r][c] = 0.f; }
 #pragma unroll 2
         for (int i = 0; i < N; ++i) {
-            const float p0 = sp[i * (MHA_QB + 1) + c0], p1 = sp[i * (MHA_QB + 1) + c1];
-            const float s0 = sds[i * (MHA_QB + 1) + c0], s1 = sds[i * (MHA_QB + 1) + c1];
+            const float p0 = sp[i * (QB + 1) + c0], p1 = sp[i * (QB + 1) + c1];
+            const float s0 = sds[i * (QB + 1) + c0], s1 = sds[i * (QB + 1) + c1];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float g = sdo[i * LD + d0 + c], q = sq[i * LD + d0 + c];
@@ -341,8 +345,19 @@ static int fill_mha(MhaP& p, int B, int N, int heads, int hd, const char* who) {
     p.scale = 1.0f / sqrtf((float)hd);
     return B200_OK;
 }
-static size_t mha_smem_q(int N, int hd) { return (size_t)(2 * N * (hd + 1) + MHA_QB * (hd + 1) + MHA_QB * (N + 1)) * sizeof(float); }
-static size_t mha_smem_kv(int N, int hd) { return (size_t)(2 * N * (hd + 1) + 2 * N * (MHA_QB + 1)) * sizeof(float); }
+static size_t mha_smem_q(int N, int hd, int QB) { return (size_t)(2 * N * (hd + 1) + QB * (hd + 1) + QB * (N + 1)) * sizeof(float); }
+static size_t mha_smem_kv(int N, int hd, int QB) { return (size_t)(2 * N * (hd + 1) + 2 * N * (QB + 1)) * sizeof(float); }
+// Queries per CTA: K and V of a head fill most of an SM's shared memory (one CTA per SM), so the grid should be ONE wave --
+// the smallest block of 32 .. 64 queries whose CTA count fits the SMs (UNETR: 216 tokens x 24 (batch, head) pairs: 48 queries =
+// 120 CTAs instead of 168 in two waves), as long as both kernels' shared memory fits.
+static int mha_choose_qb(int B, int N, int heads, int hd) {
+    for (int qb = MHA_QB; qb <= 64; qb += 8) {
+        const size_t need = mha_smem_q(N, hd, qb) > mha_smem_kv(N, hd, qb) ? mha_smem_q(N, hd, qb) : mha_smem_kv(N, hd, qb);
+        if (need > 227 * 1024) break;
+        if ((long long)((N + qb - 1) / qb) * B * heads <= b200_num_sms()) return qb;
+    }
+    return MHA_QB;
+}
 
 B200_API long long b200_mha_probs_floats(int B, int N, int heads) { return (long long)B * heads * N * N; }
 
@@ -351,9 +366,10 @@ B200_API int b200_mha_fwd(const float* qkv, float* out, float* probs, int B, int
     if (int rc = fill_mha(p, B, N, heads, hd, "mha_fwd")) return rc;
     B200_REQUIRE(qkv && out, "mha_fwd: null pointer");
     p.qkv = qkv; p.out = out; p.probs = probs;
-    const size_t smem = mha_smem_q(N, hd);
-    cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem_q(MHA_MAXN, MHA_MAXHD));
-    mha_fwd_kernel<<<dim3((N + MHA_QB - 1) / MHA_QB, B * heads), 256, smem, st>>>(p);
+    p.QB = mha_choose_qb(B, N, heads, hd);
+    const size_t smem = mha_smem_q(N, hd, p.QB);
+    cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    mha_fwd_kernel<<<dim3((N + p.QB - 1) / p.QB, B * heads), 256, smem, st>>>(p);
     B200_CHECK_LAUNCH("mha_fwd");
     return B200_OK;
 }
@@ -366,12 +382,13 @@ B200_API int b200_mha_bwd(const float* qkv, const float* probs, const float* dou
     B200_REQUIRE(qkv && probs && dout && dqkv && workspace, "mha_bwd: null pointer");
     B200_REQUIRE(workspace_bytes >= b200_mha_probs_floats(B, N, heads) * (long long)sizeof(float), "mha_bwd: workspace too small");
     p.qkv = qkv; p.probs = const_cast<float*>(probs); p.dout = dout; p.dqkv = dqkv; p.ds = workspace;
-    cudaFuncSetAttribute(mha_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem_q(MHA_MAXN, MHA_MAXHD));
-    cudaFuncSetAttribute(mha_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_smem_kv(MHA_MAXN, MHA_MAXHD));
-    const dim3 grid((N + MHA_QB - 1) / MHA_QB, B * heads);
-    mha_bwd_q_kernel<<<grid, 256, mha_smem_q(N, hd), st>>>(p);
+    p.QB = mha_choose_qb(B, N, heads, hd);
+    cudaFuncSetAttribute(mha_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(mha_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const dim3 grid((N + p.QB - 1) / p.QB, B * heads);
+    mha_bwd_q_kernel<<<grid, 256, mha_smem_q(N, hd, p.QB), st>>>(p);
     B200_CHECK_LAUNCH("mha_bwd_q");
-    mha_bwd_kv_kernel<<<grid, 256, mha_smem_kv(N, hd), st>>>(p);
+    mha_bwd_kv_kernel<<<grid, 256, mha_smem_kv(N, hd, p.QB), st>>>(p);
     B200_CHECK_LAUNCH("mha_bwd_kv");
     return B200_OK;
 }
