@@ -151,7 +151,12 @@ class ConvLayer:
                 self.k2s2_gemm = bool(ops.linear_supported(n * id_ * ih * iw, 8 * self.cout, c0, 0))
                 shape = (n * id_ * ih * iw, 8 * self.cout)
             if self.k2s2_gemm:
-                self.gview = torch.empty(shape, dtype=torch.float32, device=dev)       # xs (conv) / ys (transposed conv)
+                self.gview = torch.empty(shape, dtype=torch.float32, device=dev)       # xs (conv) / ys, then d(ys) (transposed conv)
+                if not is_conv and need_grad:
+                    # transposed conv backward on the same GEMM: d(ys) = space-to-depth view of dy, dx = d(ys) W2d,
+                    # dW2d = d(ys)^T x (copied into the framework layout [cin][cout][2][2][2])
+                    self.dw_gemm = torch.empty((8 * self.cout, c0), dtype=torch.float32, device=dev)
+                    rt.need_scratch(ops.linear_wgrad_workspace_bytes(shape[0], 8 * self.cout, c0))
                 self.gemm_mode = PACK_CONV_DGRAD_D2S if is_conv else PACK_DECONV_DGRAD  # [cout][8 cin] / [8 cout][cin]
                 self.wp_gemm = torch.empty(ops.conv_packed_floats(self.gemm_mode, O, I, self.T), dtype=torch.float32, device=dev)
         # 2D 3x3: tcgen05/TMEM kernel (B200_CONV=tile falls back to the mma.sync tile kernel for A/B comparisons)
@@ -369,6 +374,21 @@ class ConvLayer:
                     ops.conv_dgrad(self.desc, dy, self.wp_bwd, dx0, dx1, accumulate_dx, rt.exact)
                 else:
                     ops.conv_k2s2_dgrad(self.desc, dy, self.wp_bwd, dx0, accumulate_dx, rt.exact)
+        elif self.k2s2_gemm:
+            d, M_in, O8 = self.desc, self.gview.shape[0], 8 * self.cout
+            ops.s2d_gather3d(dy, self.gview, d.n, 2 * d.id, 2 * d.ih, 2 * d.iw, self.cout)
+            with rt.side_stream():
+                ops.linear_wgrad(src0, None, self.gview, self.dw_gemm, rt.scratch_side, M_in, O8, False)
+                wg = conv.weight.grad.view(self.cin, self.cout, 8)
+                part = self.dw_gemm.view(8, self.cout, self.cin).permute(2, 1, 0)          # [(tap, co)][ci] -> [ci][co][tap]
+                if accumulate_w:
+                    wg.add_(part)
+                else:
+                    wg.copy_(part)
+                if bias_grad is not None:
+                    ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side, accumulate_w)
+            if dx0 is not None:
+                ops.linear_dgrad(self.gview, self.wp_gemm.view(O8, self.cin), dx0, None, accumulate_dx, M_in, O8)
         else:
             with rt.side_stream():
                 ops.deconv_k2s2_wgrad(self.desc, src0, dy, rt.scratch_side, conv.weight.grad, accumulate_w, rt.exact)
