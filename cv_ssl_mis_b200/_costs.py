@@ -77,7 +77,7 @@ def cost_of(name, a):
         if name == "b200_s2d_gather3d":
             return 8.0 * a[2] * a[3] * a[4] * a[5] * a[6], 0.0
         if name == "b200_d2s_scatter3d":
-            return 8.0 * a[3] * a[4] * a[5] * a[6] * 8 * a[7], 0.0
+            return (12.0 if a[8] else 8.0) * a[3] * a[4] * a[5] * a[6] * 8 * a[7], 0.0
         if name == "b200_maxpool2_fwd":
             return 4.0 * a[2] * a[3] * a[4] * a[5] * 1.25, 0.0
         if name == "b200_maxpool2_bwd":

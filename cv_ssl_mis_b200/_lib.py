@@ -78,7 +78,7 @@ SIGNATURES = {
     "b200_upsample3d2x_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
     "b200_upsample3d2x_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "b200_s2d_gather3d": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
-    "b200_d2s_scatter3d": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _S]),
+    "b200_d2s_scatter3d": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "b200_conv_blk_supported": (_I, [_D, _I]),
     "b200_conv_blk_stats_blocks": (_L, [_D]),
     "b200_conv_blk_pack_weights": (_I, [_P, _P, _I, _I, _I, _I, _S]),

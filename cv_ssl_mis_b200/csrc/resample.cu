@@ -572,7 +572,7 @@ struct S2dP {
 // gather: DIR = 0: xs[m][(tap, c)] = x[fine voxel]     scatter: DIR = 1: y[fine voxel] = ys[m][(tap, c)] + bias[c]
 template <int DIR>
 __global__ void __launch_bounds__(256) s2d_kernel(const float4* __restrict__ src, float4* __restrict__ dst, const float* __restrict__ bias,
-                                                  long long total4, const S2dP p) {
+                                                  long long total4, int accumulate, const S2dP p) {
     const int Wc = DIR == 0 ? p.W / 2 : p.W, Hc = DIR == 0 ? p.H / 2 : p.H, Dc = DIR == 0 ? p.D / 2 : p.D;   // coarse grid
     const int Wf = 2 * Wc, Hf = 2 * Hc, Df = 2 * Dc;                                                          // fine grid
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -593,14 +593,15 @@ __global__ void __launch_bounds__(256) s2d_kernel(const float4* __restrict__ src
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
                 v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
+            if (accumulate) { const float4 old = dst[fine]; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
             dst[fine] = v;
         }
     }
     (void)Wc; (void)Hc; (void)Dc;
 }
 
-static int s2d_launch(int dir, const float* src, float* dst, const float* bias, int N, int D, int H, int W, int C, cudaStream_t st,
-                      const char* who) {
+static int s2d_launch(int dir, const float* src, float* dst, const float* bias, int N, int D, int H, int W, int C, int accumulate,
+                      cudaStream_t st, const char* who) {
     B200_REQUIRE(src && dst && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "%s: bad arguments (C %% 4 == 0)", who);
     B200_REQUIRE(dir == 1 || ((D | H | W) & 1) == 0, "%s: D, H, W must be even", who);
     S2dP p;
@@ -609,18 +610,19 @@ static int s2d_launch(int dir, const float* src, float* dst, const float* bias, 
     p.fdC4.init(p.C4); p.fdW2.init(Wc); p.fdH2.init(Hc); p.fdD2.init(Dc);
     const long long total4 = (long long)N * Dc * Hc * Wc * 8 * p.C4;
     B200_REQUIRE(total4 < (1ll << 32), "%s: tensor too large", who);
-    if (dir == 0) s2d_kernel<0><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), nullptr, total4, p);
-    else s2d_kernel<1><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), bias, total4, p);
+    if (dir == 0) s2d_kernel<0><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), nullptr, total4, 0, p);
+    else s2d_kernel<1><<<ew_grid(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), bias, total4, accumulate, p);
     B200_CHECK_LAUNCH(who);
     return B200_OK;
 }
 
 B200_API int b200_s2d_gather3d(const float* x, float* xs, int N, int D, int H, int W, int C, cudaStream_t st) {
-    return s2d_launch(0, x, xs, nullptr, N, D, H, W, C, st, "s2d_gather3d");
+    return s2d_launch(0, x, xs, nullptr, N, D, H, W, C, 0, st, "s2d_gather3d");
 }
 
-B200_API int b200_d2s_scatter3d(const float* ys, const float* bias, float* y, int N, int D, int H, int W, int C, cudaStream_t st) {
-    return s2d_launch(1, ys, y, bias, N, D, H, W, C, st, "d2s_scatter3d");
+B200_API int b200_d2s_scatter3d(const float* ys, const float* bias, float* y, int N, int D, int H, int W, int C, int accumulate,
+                                cudaStream_t st) {
+    return s2d_launch(1, ys, y, bias, N, D, H, W, C, accumulate, st, "d2s_scatter3d");
 }
 
 B200_API int b200_add(const float* a, const float* b, float* c, long long n, cudaStream_t st) {

@@ -152,6 +152,11 @@ class ConvLayer:
                 shape = (n * id_ * ih * iw, 8 * self.cout)
             if self.k2s2_gemm:
                 self.gview = torch.empty(shape, dtype=torch.float32, device=dev)       # xs (conv) / ys, then d(ys) (transposed conv)
+                if is_conv and need_grad:
+                    # strided conv backward on the same GEMM: d(xs) = dy W2 scattered depth-to-space, dW2 = dy^T xs
+                    self.gview_g = torch.empty(shape, dtype=torch.float32, device=dev)
+                    self.dw_gemm = torch.empty((self.cout, 8 * c0), dtype=torch.float32, device=dev)
+                    rt.need_scratch(ops.linear_wgrad_workspace_bytes(self.M, self.cout, 8 * c0))
                 if not is_conv and need_grad:
                     # transposed conv backward on the same GEMM: d(ys) = space-to-depth view of dy, dx = d(ys) W2d,
                     # dW2d = d(ys)^T x (copied into the framework layout [cin][cout][2][2][2])
@@ -344,6 +349,25 @@ class ConvLayer:
                     ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side, accumulate_w)
             if dx0 is not None:
                 ops.linear_dgrad(dy, conv.weight.view(self.cout, self.cin), dx0, dx1, accumulate_dx, self.M, self.cout)
+        elif self.kind == "conv" and self.k2s2_gemm:
+            d, K8 = self.desc, 8 * self.cin
+            with rt.side_stream():
+                ops.linear_wgrad(self.gview, None, dy, self.dw_gemm, rt.scratch_side, self.M, self.cout, False)
+                wg = conv.weight.grad.view(self.cout, self.cin, 8)
+                part = self.dw_gemm.view(self.cout, 8, self.cin).permute(0, 2, 1)        # [co][(tap, ci)] -> [co][ci][tap]
+                if accumulate_w:
+                    wg.add_(part)
+                else:
+                    wg.copy_(part)
+                if bias_grad is not None:
+                    zero_db = self.has_act and getattr(self, "bn_train", True)           # bias in front of a train-mode BatchNorm
+                    if zero_db and not accumulate_w:
+                        bias_grad.zero_()
+                    elif not zero_db:
+                        ops.colsum(dy, self.M, self.cout, bias_grad, rt.scratch_side, accumulate_w)
+            if dx0 is not None:
+                ops.linear_dgrad(dy, self.wp_gemm.view(self.cout, K8), self.gview_g, None, False, self.M, self.cout)
+                ops.d2s_scatter3d(self.gview_g, None, dx0, d.n, d.id // 2, d.ih // 2, d.iw // 2, self.cin, accumulate_dx)
         elif self.kind == "conv":
             with rt.side_stream():
                 ws = rt.scratch_side

@@ -183,9 +183,9 @@ def s2d_gather3d(x, xs, N, D, H, W, C):
     _lib.call("b200_s2d_gather3d", _pf(x), _pf(xs), N, D, H, W, C, _st())
 
 
-def d2s_scatter3d(ys, bias, y, N, D, H, W, C):
-    """y[n][2d+kd][2h+kh][2w+kw][c] = ys[(n,d,h,w)][(kd,kh,kw,c)] + bias[c]  (depth-to-space of the transposed 2x2x2 convs)"""
-    _lib.call("b200_d2s_scatter3d", _pf(ys), _pf(bias), _pf(y), N, D, H, W, C, _st())
+def d2s_scatter3d(ys, bias, y, N, D, H, W, C, accumulate=False):
+    """y[n][2d+kd][2h+kh][2w+kw][c] (+)= ys[(n,d,h,w)][(kd,kh,kw,c)] + bias[c]  (depth-to-space of the transposed 2x2x2 convs)"""
+    _lib.call("b200_d2s_scatter3d", _pf(ys), _pf(bias), _pf(y), N, D, H, W, C, int(accumulate), _st())
 
 
 def conv_blk_supported(d, dgrad=False) -> int:

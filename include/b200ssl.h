@@ -147,9 +147,10 @@ int b200_upsample3d2x_bwd(const float* dy, float* dx, int N, int D, int H, int W
  * b200_s2d_gather3d writes the space-to-depth view xs[(n,do,ho,wo)][(kd,kh,kw,c)] of x[N][D][H][W][C] (D, H, W even), so that
  * the strided convolution is b200_linear_fwd(xs, W2[cout][8 cin]) (weights packed with B200_PACK_CONV_DGRAD_D2S);
  * b200_d2s_scatter3d writes y[N][2D][2H][2W][C] from ys[(n,d,h,w)][(kd,kh,kw,c)] (+ bias[c]), ys = b200_linear_fwd(x,
- * W2d[8 cout][cin]) (weights packed with B200_PACK_DECONV_DGRAD). */
+ * W2d[8 cout][cin]) (weights packed with B200_PACK_DECONV_DGRAD); accumulate adds to y (data gradient of the strided conv). */
 int b200_s2d_gather3d(const float* x, float* xs, int N, int D, int H, int W, int C, cudaStream_t stream);
-int b200_d2s_scatter3d(const float* ys, const float* bias, float* y, int N, int D, int H, int W, int C, cudaStream_t stream);
+int b200_d2s_scatter3d(const float* ys, const float* bias, float* y, int N, int D, int H, int W, int C, int accumulate,
+                       cudaStream_t stream);
 
 /* Halo-block tcgen05 forward / data gradient of the narrow-image 2D 3x3 stride-1 pad-1 convolutions (csrc/conv_blk.cu;
  * code/networks/unet.py:37,41 at the 64^2 / 32^2 / 16^2 levels): width <= 96, input channels a multiple of 32, GEMM

@@ -403,11 +403,12 @@ def s2d_gather3d(x, xs, N, D, H, W, C):
     xs.copy_(v.reshape(xs.shape))
 
 
-def d2s_scatter3d(ys, bias, y, N, D, H, W, C):
+def d2s_scatter3d(ys, bias, y, N, D, H, W, C, accumulate=False):
     v = ys.reshape(N, D, H, W, 2, 2, 2, C)
     if bias is not None:
         v = v + bias
-    y.copy_(v.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(y.shape))                               # n d kd h kh w kw c
+    v = v.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(y.shape)                                    # n d kd h kh w kw c
+    y.copy_(y + v if accumulate else v)
 
 
 # ------------------------------------------------------------------ halo-block tcgen05 forward / data gradient
