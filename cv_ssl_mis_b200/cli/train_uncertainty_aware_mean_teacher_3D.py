@@ -6,7 +6,8 @@ from ._common import base_parser, process_group, run_loop, seed_everything, setu
 
 
 def main(argv=None, loader=None, defaults=None):
-    p = base_parser("BraTs2019_Uncertainty_Aware_Mean_Teacher", "vnet", 4, (96, 96, 96), 2, 25, "../data/BraTS2019")
+    # the reference's defaults, including its experiment name (train_uncertainty_aware_mean_teacher_3D.py:33-36)
+    p = base_parser("BraTs2019_Mean_Teacher", "unet_3D", 4, (96, 96, 96), 2, 25, "../data/BraTS2019")
     p.add_argument('--uncertainty_T', type=int, default=8, help='stochastic teacher passes (reference: T = 8)')
     if defaults:                                                  # same loop under another reference script name
         p.set_defaults(**defaults)
