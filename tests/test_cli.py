@@ -164,3 +164,18 @@ def test_in_loop_validation_and_best_checkpoint(cpu_env):
     assert (snap / "unet_best_model.pth").exists() and list(snap.glob("iter_2_dice_*.pth"))
     assert "mean_dice" in (snap / "log.txt").read_text()
     assert list((snap / "log").glob("events.out.tfevents.*"))            # tensorboard scalars (info/lr, info/total_loss, ...)
+
+
+def test_in_loop_validation_two_models(cpu_env):
+    """code/train_cross_teaching_between_cnn_transformer_2D.py:283-345: both networks are validated, each with its own
+    best-model files (`model1_iter_<n>_dice_<d>.pth`, `<model>_best_model1.pth`, ...)."""
+    from cv_ssl_mis_b200.cli import train_cross_pseudo_supervision_2D as cli
+    g = torch.Generator().manual_seed(10)
+    val = [{"image": torch.rand(1, 2, 40, 36, generator=g), "label": torch.randint(0, 4, (1, 2, 40, 36), generator=g)}]
+    assert cli.main(["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32", "--val_every", "2"] + COMMON,
+                    val_loader=val) == "Training Finished!"
+    snap = cpu_env / "model" / "ACDC" / "Cross_Pseudo_Supervision_1_labeled" / "unet"
+    for k in (1, 2):
+        assert (snap / f"unet_best_model{k}.pth").exists() and list(snap.glob(f"model{k}_iter_2_dice_*.pth"))
+    log = (snap / "log.txt").read_text()
+    assert "model1_mean_dice" in log and "model2_mean_dice" in log
