@@ -45,6 +45,7 @@ def base_parser(exp, model, batch_size, patch_size, labeled_bs, labeled_num, roo
     p.add_argument('--synthetic', type=int, default=1, help='draw synthetic batches of the dataset\'s shape (no h5 reader here)')
     p.add_argument('--log_every', type=int, default=50, help='read the losses back every k iterations (0: never)')
     p.add_argument('--save_every', type=int, default=3000, help='checkpoint interval (reference: 3000)')
+    p.add_argument('--resume_trainer', type=str, default=None, help='trainer_iter_<n>.pth written next to the checkpoints: continue that run')
     p.add_argument('--val_every', type=int, default=200, help='validation interval when main() gets a val_loader (reference: 200)')
     p.add_argument('--tensorboard', type=int, default=1, help='write the reference\'s tensorboard scalars under <snapshot>/log')
     p.add_argument('--no_graph', action='store_true', help='launch eagerly instead of replaying one CUDA graph per step')
@@ -234,6 +235,9 @@ def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0, val_load
     """The iteration loop of the reference scripts with the body replaced by `trainer.step`.
     models: {checkpoint prefix: module}; fmt(iter_num, losses) -> log line; scalars(iter_num, losses) -> {tag: value} for
     tensorboard; val_loader / val_fn(image, label, model) -> [(dice, hd95)] per class: validation every --val_every iterations."""
+    if getattr(args, "resume_trainer", None):
+        trainer.load_state_dict(torch.load(args.resume_trainer, weights_only=False))
+        logging.info("resumed from %s at iteration %d" % (args.resume_trainer, trainer.iter_num))
     it0 = trainer.iter_num
     t0 = time.time()
     writer = _summary_writer(snapshot_path) if (rank == 0 and getattr(args, "tensorboard", 1)) else None
@@ -257,6 +261,7 @@ def run_loop(args, trainer, loader, snapshot_path, models, fmt, rank=0, val_load
             if rank == 0 and args.save_every and trainer.iter_num % args.save_every == 0:
                 for prefix, m in models.items():
                     torch.save(m.state_dict(), os.path.join(snapshot_path, f"{prefix}iter_{trainer.iter_num}.pth"))
+                torch.save(trainer.state_dict(), os.path.join(snapshot_path, f"trainer_iter_{trainer.iter_num}.pth"))
             if trainer.iter_num >= args.max_iterations:
                 break
         if seen == 0:

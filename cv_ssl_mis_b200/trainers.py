@@ -39,7 +39,31 @@ class PendingLoss:
         return self._host.tolist()
 
 
-class _Pipelined:
+class _Resumable:
+    """True resume, which the reference lacks (its checkpoints hold the student weights only): parameters, momentum buffers,
+    the teacher, BatchNorm running statistics, the dropout / noise RNG epochs, the iteration counter and the learning rate."""
+
+    def _networks(self):
+        return [m for m in (getattr(self, "models", None) or (self.model, self.ema_model)) if m is not None]
+
+    def state_dict(self):
+        return {"iter_num": self.iter_num, "lr": self.lr, "tensors": [t.detach().clone().cpu() for t in self._state_tensors()],
+                "rng_seeds": [m._rt.seed for m in self._networks()]}          # base seeds of the dropout / DropPath streams
+
+    def load_state_dict(self, sd):
+        """Call before the first step (a captured CUDA graph has the RNG seeds baked into its kernel arguments)."""
+        assert getattr(self, "graph", None) is None, "load_state_dict after the step graph was captured"
+        for m, seed in zip(self._networks(), sd["rng_seeds"]):
+            m._rt.seed = seed
+        ts = self._state_tensors()
+        assert len(ts) == len(sd["tensors"]), "trainer state does not match this trainer (different models?)"
+        for t, v in zip(ts, sd["tensors"]):
+            assert t.shape == v.shape, (tuple(t.shape), tuple(v.shape))
+            t.copy_(v)
+        self.iter_num, self.lr = int(sd["iter_num"]), float(sd["lr"])
+
+
+class _Pipelined(_Resumable):
     """`submit(images, labels)` is `step(..., read_loss=True)` without the stall: the pinned host batch goes up on a copy
     stream into one of two device staging pairs while the previous step is still running, the step is enqueued behind
     it, and the 16/32-byte loss read-back gets its own event.  A loop that calls `result()` of step i after `submit` of

@@ -179,3 +179,33 @@ def test_in_loop_validation_two_models(cpu_env):
         assert (snap / f"unet_best_model{k}.pth").exists() and list(snap.glob(f"model{k}_iter_2_dice_*.pth"))
     log = (snap / "log.txt").read_text()
     assert "model1_mean_dice" in log and "model2_mean_dice" in log
+
+
+def test_resume_continues_the_same_run(cpu_env):
+    """A run interrupted after 2 of 4 iterations and resumed from trainer_iter_2.pth ends with the weights of the
+    uninterrupted run (parameters, momentum, teacher, BatchNorm statistics, RNG epochs, iteration counter, learning rate)."""
+    from cv_ssl_mis_b200.cli import train_mean_teacher_2D as cli
+    from cv_ssl_mis_b200.networks import unet as unet_mod
+    base = ["--batch_size", "4", "--labeled_bs", "2", "--patch_size", "32", "32", "--log_every", "1", "--no_graph", "--seed", "7"]
+
+    def fresh_process():                 # the default dropout seeds count the networks built in this process
+        unet_mod.UNet._instances = 0
+
+    fresh_process()
+    assert cli.main(base + ["--max_iterations", "4", "--save_every", "0", "--exp", "R/straight"]) == "Training Finished!"
+    fresh_process()
+    from cv_ssl_mis_b200.cli._common import synthetic_batches
+    two = synthetic_batches(4, [32, 32], 4, 7, pinned=False)
+    with pytest.raises(ValueError):      # the "interruption": the data stream ends after two batches of the same 4-iteration run
+        cli.main(base + ["--max_iterations", "4", "--save_every", "2", "--exp", "R/first"], loader=(next(two) for _ in range(2)))
+    first = cpu_env / "model" / "R" / "first_7_labeled" / "unet"
+    # same data stream as the straight run from iteration 2 on: skip the two batches the first leg consumed
+    it = synthetic_batches(4, [32, 32], 4, 7, pinned=False)
+    next(it), next(it)
+    fresh_process()
+    assert cli.main(base + ["--max_iterations", "4", "--save_every", "0", "--exp", "R/second",
+                            "--resume_trainer", str(first / "trainer_iter_2.pth")], loader=it) == "Training Finished!"
+    a = torch.load(cpu_env / "model" / "R" / "straight_7_labeled" / "unet" / "iter_4.pth")
+    b = torch.load(cpu_env / "model" / "R" / "second_7_labeled" / "unet" / "iter_4.pth")
+    for k in a:
+        torch.testing.assert_close(a[k], b[k], rtol=0, atol=0, msg=lambda m, k=k: f"{k}: {m}")
